@@ -1,0 +1,165 @@
+/*
+ * qob200.h — C ABI of libqob200.so: B200-native (sm_100a) operator application
+ * `mul!(result, op, state, alpha, beta)` for QuantumOpticsBase.jl's LazyTensor,
+ * LazySum, LazyProduct, SparseOperator and dense Operator acting on Ket / Bra /
+ * dense Operator data in ComplexF64.
+ *
+ * The reference has NO FFI for this path: the boundary is Julia multiple dispatch
+ * on `LinearAlgebra.mul!` (reference src/QuantumOpticsBase.jl:4).  Every entry
+ * point below cites the reference method(s) it replaces; `INTEGRATION.md` shows
+ * the `ccall` stubs a maintainer adds (julia/QOB200.jl holds the full glue).
+ *
+ * Conventions (all taken from the reference):
+ *   - ComplexF64 = two IEEE doubles (re, im), interleaved.
+ *   - all dense data column-major; composite index has subsystem 1 fastest
+ *     (src/states.jl:105, src/operators_dense.jl:134,296-308).
+ *   - site indices are 1-based and sorted (src/operators_lazytensor.jl:26).
+ *   - CSC arrays are Julia SparseMatrixCSC{ComplexF64,Int64}: colptr/rowval 1-based.
+ *   - Y = alpha*A*B + beta*Y; alpha==0 -> only the beta update; beta==0 -> Y is
+ *     never read (NaNs die) (src/operators_lazysum.jl:179-192,
+ *     src/operators_lazytensor.jl:540, src/sparsematrix.jl:103-107).
+ *   - state/result pointers are DEVICE pointers owned by the caller (CuPtr);
+ *     operator definitions (factors, CSC arrays, coefficients) are HOST pointers
+ *     copied at creation time.
+ *   - every function returns a qob_status; qob_last_error() gives the message
+ *     of the calling thread's last failure.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     returns QOB_STATUS_CUDA_ERROR.
+ */
+#ifndef QOB200_H
+#define QOB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QOB200_VERSION 100
+
+typedef struct { double re, im; } qob_c64;
+
+typedef enum {
+  QOB_STATUS_OK = 0,
+  QOB_STATUS_DIM_MISMATCH = 1,   /* Julia DimensionMismatch (sparsematrix.jl:100-102, operators_lazytensor.jl:695-703) */
+  QOB_STATUS_ALIASING = 2,       /* Julia ArgumentError: result aliases an input (operators_lazytensor.jl:704-708) */
+  QOB_STATUS_INVALID_ARG = 3,    /* Julia ArgumentError / AssertionError in constructors (operators_lazytensor.jl:23-32) */
+  QOB_STATUS_UNSUPPORTED = 4,    /* Julia MethodError / "not implemented" (sparsematrix.jl:177-188) */
+  QOB_STATUS_CUDA_ERROR = 5,
+  QOB_STATUS_NCCL_ERROR = 6,
+  QOB_STATUS_ALLOC = 7
+} qob_status;
+
+typedef enum { QOB_SIDE_LEFT = 0, QOB_SIDE_RIGHT = 1 } qob_side;
+
+/* how a stored matrix enters: as is, transposed, or adjoint (Julia `Adjoint` wrapper,
+ * operators_dense.jl:128, operators_sparse.jl:6) */
+typedef enum { QOB_OP_N = 0, QOB_OP_T = 1, QOB_OP_C = 2 } qob_trans;
+
+typedef enum {
+  QOB_FACTOR_DENSE = 0,  /* Matrix{ComplexF64}, column-major nrows x ncols                 */
+  QOB_FACTOR_CSC = 1,    /* SparseMatrixCSC{ComplexF64,Int64}                              */
+  QOB_FACTOR_EYE = 2     /* FillArrays.Eye(nrows, ncols), possibly non-square (isometry)   */
+} qob_factor_kind;
+
+/* One site operator (`.data` of an Operator) as the reference stores it. HOST pointers. */
+typedef struct {
+  int32_t kind;           /* qob_factor_kind */
+  int32_t trans;          /* qob_trans applied to the STORED matrix */
+  int64_t nrows, ncols;   /* shape of the STORED matrix (before trans) */
+  const qob_c64 *dense;   /* kind DENSE: nrows*ncols values, column-major */
+  const int64_t *colptr;  /* kind CSC: ncols+1 entries, 1-based */
+  const int64_t *rowval;  /* kind CSC: nnz entries, 1-based */
+  const qob_c64 *nzval;   /* kind CSC: nnz entries */
+} qob_factor;
+
+typedef struct qob_ctx qob_ctx;  /* one per (process, device) */
+typedef struct qob_op qob_op;    /* immutable operator handle (refcounted by sums/products that hold it) */
+
+int qob_version(void);
+const char *qob_last_error(void);
+const char *qob_status_string(int status);
+
+/* Device context: binds to CUDA device `device`, owns scratch (the analogue of the
+ * reference's LRU temp cache, operators_lazytensor.jl:222-279, keyed per stream). */
+int qob_ctx_create(int device, qob_ctx **out);
+int qob_ctx_destroy(qob_ctx *ctx);
+/* lazytensor_cachesize()/lazytensor_clear_cache() analogues (operators_lazytensor.jl:241-279) */
+int qob_ctx_scratch_bytes(qob_ctx *ctx, int64_t *bytes);
+int qob_ctx_clear_scratch(qob_ctx *ctx);
+
+/* LazyTensor(bl, br, indices, operators, factor) — operators_lazytensor.jl:15-37.
+ * dims_l/dims_r: per-subsystem dimensions (`_comp_size`, :517-518); sites: 1-based sorted. */
+int qob_lazytensor_create(qob_ctx *ctx, int32_t nsub, const int64_t *dims_l, const int64_t *dims_r,
+                          int32_t nfac, const int32_t *sites, const qob_factor *factors,
+                          qob_c64 factor, qob_op **out);
+
+/* SparseOperator (Operator{…,SparseMatrixCSC} or its lazy Adjoint) — operators_sparse.jl:5-23,199-202 */
+int qob_sparse_create(qob_ctx *ctx, const qob_factor *m, qob_op **out);
+
+/* DenseOperator used as an operator (BLAS path, operators_dense.jl:394-396). */
+int qob_dense_create(qob_ctx *ctx, const qob_factor *m, qob_op **out);
+
+/* LazySum(basis_l, basis_r, factors, operators) — operators_lazysum.jl:41-51.
+ * dim_l/dim_r are the total dimensions (needed for the empty sum, :118-121,190-192). */
+int qob_lazysum_create(qob_ctx *ctx, int64_t dim_l, int64_t dim_r, int32_t nterms,
+                       const qob_c64 *coefs, qob_op *const *terms, qob_op **out);
+/* TimeDependentSum set_time! rewrites LazySum.factors (time_dependent_operator.jl:279-290): cheap update. */
+int qob_lazysum_set_coefs(qob_op *sum, int32_t nterms, const qob_c64 *coefs);
+
+/* LazyProduct(operators, factor) — operators_lazyproduct.jl:32-52; temporaries are plan-owned
+ * device buffers (the reference pre-allocates ket_l/bra_r, :12-21). */
+int qob_lazyproduct_create(qob_ctx *ctx, int32_t nops, qob_op *const *ops, qob_c64 factor, qob_op **out);
+
+int qob_op_destroy(qob_op *op);
+int qob_op_dims(const qob_op *op, int64_t *dim_l, int64_t *dim_r);
+
+/* mul!(result, op, b, alpha, beta)  [side LEFT ]: y(dim_l x batch) = alpha*op*x(dim_r x batch) + beta*y
+ * mul!(result, a, op, alpha, beta)  [side RIGHT]: y(batch x dim_r) = alpha*x(batch x dim_l)*op + beta*y
+ * batch = 1 is the Ket (LEFT) / Bra (RIGHT) case.
+ * Replaces: operators_lazytensor.jl:539-609, operators_lazysum.jl:189-238,
+ * operators_lazyproduct.jl:103-163, operators_sparse.jl:199-202, operators_dense.jl:394-396.
+ * x, y: device pointers to ComplexF64, column-major. stream: a cudaStream_t (0 = legacy default). */
+int qob_op_apply(qob_op *op, int32_t side, qob_c64 alpha, const void *x, qob_c64 beta, void *y,
+                 int64_t batch, void *stream);
+
+/* Same call with HOST buffers: stages x (and y when beta != 0) to the device, applies, copies y back.
+ * This is the end-to-end path bench.py times as `e2e`. */
+int qob_op_apply_host(qob_op *op, int32_t side, qob_c64 alpha, const qob_c64 *x, qob_c64 beta,
+                      qob_c64 *y, int64_t batch);
+
+/* Introspection used by tests/bench: number of kernel launches issued by this library in this
+ * process, and a text description of the plan chosen for `op` (passes, tiles, kernels). */
+int64_t qob_launch_count(void);
+int qob_op_describe(qob_op *op, int32_t side, int64_t batch, char *buf, int64_t buflen);
+
+/* Counter-based synthetic input generator shared with the oracle (oracle/qob_oracle.c:orc_fill_state):
+ * x[i] = scale * (u(seed, 2i), u(seed, 2i+1)), u uniform in [-1, 1) from splitmix64. */
+int qob_fill_state(void *x, int64_t offset, int64_t n, uint64_t seed, double scale, void *stream);
+/* sum |x|^2 and <x|y> reductions for size-independent parity properties (device result -> host). */
+int qob_norm2(const void *x, int64_t n, double *out, void *stream);
+int qob_dot(const void *x, const void *y, int64_t n, qob_c64 *out, void *stream);
+
+/* ---- sharded (multi-GPU) LazySum apply: one process per GPU -----------------------------------
+ * The state is sharded on its highest-stride axes: rank r of P=2^p owns the contiguous slab
+ * [r*D/P, (r+1)*D/P) of the reference's linear array, i.e. the top p index bits are the rank.
+ * The library provides the per-rank compute for ANY index layout; the host (python/dist.py, or the
+ * Julia glue) owns the exchange step (NCCL all-to-all axis swap) between layouts:
+ *   - qob_lazysum_term_masks: which subsystems a LazyTensor term touches / touches off-diagonally
+ *     (a diagonal factor on a sharded axis needs no communication, only a rank-dependent weight);
+ *   - qob_layout_plan_create: tile program for the selected terms of a spin-1/2 LazySum when
+ *     subsystem k's index bit sits at position bitpos[k] of a virtual index whose positions
+ *     < nbits_local address the local buffer and whose positions >= nbits_local are constant on this
+ *     rank (bit j of hi_value = position nbits_local + j).  Off-diagonal factors must be local.
+ *   - qob_layout_plan_apply: y = alpha * (selected terms) x + beta * y on the local buffers. */
+int qob_lazysum_term_masks(qob_op *sum, int32_t term, uint64_t *offdiag_mask, uint64_t *site_mask);
+int qob_layout_plan_create(qob_op *sum, int32_t nbits_local, const int32_t *bitpos, uint64_t hi_value,
+                           const uint8_t *term_select, int32_t *plan_id);
+int qob_layout_plan_apply(qob_op *sum, int32_t plan_id, qob_c64 alpha, const void *x, qob_c64 beta, void *y,
+                          void *stream);
+int qob_layout_plan_describe(qob_op *sum, int32_t plan_id, char *buf, int64_t buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QOB200_H */

@@ -1,0 +1,277 @@
+// qob_kernels_axis.cu — dense single-axis contraction on FP64 tensor cores (DMMA) and the
+// sparse x dense kernels.
+//
+//   y[l, i, r] = alpha * sum_j A[i, j] * x[l, j, r] + beta * y[l, i, r]
+//
+// replaces `_tp_matmul!` (src/operators_lazytensor.jl:406-428): the reference runs zgemm on a 2-D
+// reshape for the first/last axis (:281-301) and permute -> zgemm -> permute for a middle axis
+// (:333-404, three extra passes over the state).  Here any axis position is one kernel: the state is
+// viewed as (L, d, R), the "GEMM" column index n = l + L*r addresses x[l + L*(j + dr*r)] directly, so
+// no permutation is ever materialised.  Complex products are four real m8n8k4 DMMAs on split re/im
+// shared-memory planes (tcgen05 has no FP64 kind; `mma.sync ... f64` -> SASS DMMA.8x8x4 is the FP64
+// tensor path on sm_100a).  Used for genuinely dense factors (d >= 16, BASELINE config 3, d = 48).
+#include <algorithm>
+#include <cstdio>
+
+#include "qob_internal.h"
+
+#define AX_KT 16
+#define AX_LD (AX_KT + 4)  // +4 doubles: conflict-free 64-bit fragment loads (ld = 4 mod 16)
+
+struct AxisParams {
+  const double *a_re, *a_im;  // [dl_pad][dr_pad] row-major
+  int dl, dr, dl_pad, dr_pad;
+  long long L, R, N;          // N = L*R
+  double2 alpha, beta;
+  int beta_zero;
+};
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int MW, int NW>
+__global__ void __launch_bounds__(32 * MW * NW)
+    axis_dmma_kernel(const __grid_constant__ AxisParams P, const double2 *__restrict__ x, double2 *__restrict__ y) {
+  constexpr int TM = 16 * MW, TN = 32 * NW, NT = 32 * MW * NW;
+  __shared__ double As_re[TM * AX_LD], As_im[TM * AX_LD];
+  __shared__ double Xs_re[TN * AX_LD], Xs_im[TN * AX_LD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp % MW, wn = warp / MW;
+  const int g = lane >> 2, t = lane & 3;
+  const long long n0 = (long long)blockIdx.x * TN;
+  const int m0 = blockIdx.y * TM;
+  const bool n_fast = P.L >= 8;  // which index is contiguous in global memory for the x tile
+
+  double cre[2][4][2], cim[2][4][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
+
+  for (int k0 = 0; k0 < P.dr; k0 += AX_KT) {
+    // A tile (zero padded on the host to multiples of 16 in both directions)
+    for (int e = tid; e < TM * AX_KT; e += NT) {
+      int i = e / AX_KT, k = e % AX_KT;
+      double re = 0.0, im = 0.0;
+      if (m0 + i < P.dl_pad) {
+        re = P.a_re[(long long)(m0 + i) * P.dr_pad + k0 + k];
+        im = P.a_im[(long long)(m0 + i) * P.dr_pad + k0 + k];
+      }
+      As_re[i * AX_LD + k] = re;
+      As_im[i * AX_LD + k] = im;
+    }
+    // x tile: element (n, k) <- x[l + L*((k0+k) + dr*r)],  n0+n = l + L*r
+    for (int e = tid; e < TN * AX_KT; e += NT) {
+      int n, k;
+      if (n_fast) {
+        n = e % TN;
+        k = e / TN;
+      } else {
+        k = e % AX_KT;
+        n = e / AX_KT;
+      }
+      double2 v = make_double2(0.0, 0.0);
+      long long nn = n0 + n;
+      if (nn < P.N && k0 + k < P.dr) {
+        long long r = nn / P.L, l = nn - r * P.L;
+        v = x[l + P.L * ((long long)(k0 + k) + (long long)P.dr * r)];
+      }
+      Xs_re[n * AX_LD + k] = v.x;
+      Xs_im[n * AX_LD + k] = v.y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < AX_KT; kk += 4) {
+      double are[2], aim[2], naim[2];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        int row = wm * 16 + mb * 8 + g;
+        are[mb] = As_re[row * AX_LD + kk + t];
+        aim[mb] = As_im[row * AX_LD + kk + t];
+        naim[mb] = -aim[mb];
+      }
+#pragma unroll
+      for (int nb = 0; nb < 4; ++nb) {
+        int col = wn * 32 + nb * 8 + g;
+        double bre = Xs_re[col * AX_LD + kk + t];
+        double bim = Xs_im[col * AX_LD + kk + t];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          dmma884(cre[mb][nb][0], cre[mb][nb][1], are[mb], bre);
+          dmma884(cre[mb][nb][0], cre[mb][nb][1], naim[mb], bim);
+          dmma884(cim[mb][nb][0], cim[mb][nb][1], are[mb], bim);
+          dmma884(cim[mb][nb][0], cim[mb][nb][1], aim[mb], bre);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // epilogue: thread holds C[row g][cols 2t, 2t+1] of each 8x8 block
+#pragma unroll
+  for (int mb = 0; mb < 2; ++mb) {
+    int i = m0 + wm * 16 + mb * 8 + g;
+    if (i >= P.dl) continue;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        long long nn = n0 + wn * 32 + nb * 8 + 2 * t + e;
+        if (nn >= P.N) continue;
+        long long r = nn / P.L, l = nn - r * P.L;
+        long long addr = l + P.L * ((long long)i + (long long)P.dl * r);
+        double ar = cre[mb][nb][e], ai = cim[mb][nb][e];
+        double2 o = make_double2(P.alpha.x * ar - P.alpha.y * ai, P.alpha.x * ai + P.alpha.y * ar);
+        if (!P.beta_zero) {
+          double2 yo = y[addr];
+          o.x += P.beta.x * yo.x - P.beta.y * yo.y;
+          o.y += P.beta.x * yo.y + P.beta.y * yo.x;
+        }
+        y[addr] = o;
+      }
+  }
+}
+
+int prepare_axis_matrix(const HostMat &m, AxisMatrixDev &out) {
+  out.dl = (int)m.rows;
+  out.dr = (int)m.cols;
+  out.dl_pad = (out.dl + 15) / 16 * 16;
+  out.dr_pad = (out.dr + AX_KT - 1) / AX_KT * AX_KT;
+  std::vector<double> h((size_t)2 * out.dl_pad * out.dr_pad, 0.0);
+  const size_t plane = (size_t)out.dl_pad * out.dr_pad;
+  for (int i = 0; i < out.dl; ++i)
+    for (int j = 0; j < out.dr; ++j) {
+      cplx v = m.at(i, j);
+      h[(size_t)i * out.dr_pad + j] = v.real();
+      h[plane + (size_t)i * out.dr_pad + j] = v.imag();
+    }
+  return out.planes.upload(h);
+}
+
+int launch_axis_dense(const AxisMatrixDev &A, int64_t L, int64_t R, cplx alpha, const void *x, cplx beta, void *y,
+                      cudaStream_t s) {
+  AxisParams P;
+  P.a_re = A.planes.ptr;
+  P.a_im = A.planes.ptr + (size_t)A.dl_pad * A.dr_pad;
+  P.dl = A.dl;
+  P.dr = A.dr;
+  P.dl_pad = A.dl_pad;
+  P.dr_pad = A.dr_pad;
+  P.L = L;
+  P.R = R;
+  P.N = L * R;
+  P.alpha = make_double2(alpha.real(), alpha.imag());
+  P.beta = make_double2(beta.real(), beta.imag());
+  P.beta_zero = beta == cplx(0.0, 0.0);
+  if (P.N == 0 || A.dl == 0) return QOB_STATUS_OK;
+  const double2 *xp = (const double2 *)x;
+  double2 *yp = (double2 *)y;
+#define AX_LAUNCH(MW, NW)                                                            \
+  do {                                                                               \
+    constexpr int TM = 16 * MW, TN = 32 * NW;                                        \
+    long long gx = (P.N + TN - 1) / TN;                                              \
+    if (gx > 0x7FFFFFFFll) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "axis kernel: grid too large"); \
+    dim3 grid((unsigned)gx, (unsigned)((A.dl + TM - 1) / TM));                       \
+    axis_dmma_kernel<MW, NW><<<grid, 32 * MW * NW, 0, s>>>(P, xp, yp);               \
+  } while (0)
+  // static shared memory must stay under 48 KiB: (TM + TN) * AX_LD * 16 B
+  if (A.dl <= 16)
+    AX_LAUNCH(1, 4);
+  else if (A.dl <= 32)
+    AX_LAUNCH(2, 3);
+  else if (A.dl <= 48)
+    AX_LAUNCH(3, 2);
+  else
+    AX_LAUNCH(4, 2);
+#undef AX_LAUNCH
+  QOB_LAUNCHED();
+  QOB_CUDA(cudaGetLastError());
+  return QOB_STATUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------ SpMM
+// SparseOperator x dense (src/operators_sparse.jl:199-202 -> gemm!/gemv!, src/sparsematrix.jl:99-238).
+// Julia's dense operands are column-major, so the coalesced direction is the ROW index of the dense
+// matrices: one thread per output element with lanes running down a column ("thread-per-row-element";
+// a warp-per-row split would read B with stride k).  The reference's scatter over CSC columns
+// (R[row, j] += v*B[col, j]) becomes a gather over CSR rows: no atomics, no beta pre-pass.
+__global__ void __launch_bounds__(256)
+    spmm_left_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double2 *__restrict__ val,
+                     long long m, long long k, long long n, double2 alpha, double2 beta, int beta_zero,
+                     const double2 *__restrict__ B, double2 *__restrict__ R) {
+  const long long total = m * n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long c = idx / m, i = idx - c * m;
+    const double2 *b = B + c * k;
+    double re = 0.0, im = 0.0;
+    for (int p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+      double2 v = val[p], w = b[colidx[p]];
+      re = fma(v.x, w.x, re);
+      re = fma(-v.y, w.y, re);
+      im = fma(v.x, w.y, im);
+      im = fma(v.y, w.x, im);
+    }
+    double2 o = make_double2(alpha.x * re - alpha.y * im, alpha.x * im + alpha.y * re);
+    if (!beta_zero) {
+      double2 yo = R[idx];
+      o.x += beta.x * yo.x - beta.y * yo.y;
+      o.y += beta.x * yo.y + beta.y * yo.x;
+    }
+    R[idx] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    spmm_right_kernel(const int *__restrict__ colptr, const int *__restrict__ rowidx, const double2 *__restrict__ val,
+                      long long q, long long m, long long n, double2 alpha, double2 beta, int beta_zero,
+                      const double2 *__restrict__ B, double2 *__restrict__ R) {
+  const long long total = q * n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long c = idx / q, r = idx - c * q;
+    double re = 0.0, im = 0.0;
+    for (int p = colptr[c]; p < colptr[c + 1]; ++p) {
+      double2 v = val[p], w = B[r + q * (long long)rowidx[p]];
+      re = fma(v.x, w.x, re);
+      re = fma(-v.y, w.y, re);
+      im = fma(v.x, w.y, im);
+      im = fma(v.y, w.x, im);
+    }
+    double2 o = make_double2(alpha.x * re - alpha.y * im, alpha.x * im + alpha.y * re);
+    if (!beta_zero) {
+      double2 yo = R[idx];
+      o.x += beta.x * yo.x - beta.y * yo.y;
+      o.y += beta.x * yo.y + beta.y * yo.x;
+    }
+    R[idx] = o;
+  }
+}
+
+int launch_spmm_left(const SparseDev &csr, int64_t m, int64_t k, int64_t n, cplx alpha, const void *B, cplx beta,
+                     void *R, cudaStream_t s) {
+  if (m * n == 0) return QOB_STATUS_OK;
+  int64_t blocks = std::min<int64_t>((m * n + 255) / 256, (int64_t)1 << 30);
+  spmm_left_kernel<<<(unsigned)blocks, 256, 0, s>>>(csr.ptr.ptr, csr.idx.ptr, csr.val.ptr, m, k, n,
+                                                    make_double2(alpha.real(), alpha.imag()),
+                                                    make_double2(beta.real(), beta.imag()), beta == cplx(0.0, 0.0),
+                                                    (const double2 *)B, (double2 *)R);
+  QOB_LAUNCHED();
+  QOB_CUDA(cudaGetLastError());
+  return QOB_STATUS_OK;
+}
+
+int launch_spmm_right(const SparseDev &csc, int64_t q, int64_t m, int64_t n, cplx alpha, const void *B, cplx beta,
+                      void *R, cudaStream_t s) {
+  if (q * n == 0) return QOB_STATUS_OK;
+  int64_t blocks = std::min<int64_t>((q * n + 255) / 256, (int64_t)1 << 30);
+  spmm_right_kernel<<<(unsigned)blocks, 256, 0, s>>>(csc.ptr.ptr, csc.idx.ptr, csc.val.ptr, q, m, n,
+                                                     make_double2(alpha.real(), alpha.imag()),
+                                                     make_double2(beta.real(), beta.imag()), beta == cplx(0.0, 0.0),
+                                                     (const double2 *)B, (double2 *)R);
+  QOB_LAUNCHED();
+  QOB_CUDA(cudaGetLastError());
+  return QOB_STATUS_OK;
+}

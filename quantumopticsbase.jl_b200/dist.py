@@ -1,0 +1,147 @@
+"""Sharded (multi-GPU) LazySum apply: one process per GPU, torch.distributed for the plumbing.
+
+The reference has no distributed path at all: a state must fit one array.  Here a
+spin-1/2 state of N subsystems is sharded on its highest-stride axes: rank r of P = 2^p holds the
+contiguous slab [r*2^(N-p), (r+1)*2^(N-p)) of the reference's column-major array, i.e. index bits
+N-p..N-1 are the rank.
+
+  * Terms whose OFF-DIAGONAL factors all sit on local bits run with no communication; diagonal factors
+    on sharded bits (sigma_z, number) only select a rank-dependent weight (`hi_value` in the tile plan).
+  * The remaining terms (sigma_x/sigma_y on a sharded axis) run in a SWAPPED layout: the p sharded bits
+    trade places with a window of p local bits that those terms do not touch, by ONE all-to-all each
+    way (`axis_swap`, NCCL all_to_all_single over NVLink).  The swap is an involution.
+
+Compute kernels are libqob200's tile programs (`qob_layout_plan_*`); this module only decides layouts
+and moves data.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib
+from ._lib import c64, lib
+from .operators import LazySum, handle
+
+
+def swap_window(nloc: int, p: int, touched_mask: int) -> int:
+    """Lowest bit of the highest window of p local bits that no swapped term touches."""
+    for c in range(nloc - p, -1, -1):
+        win = ((1 << p) - 1) << c
+        if not (touched_mask & win):
+            return c
+    raise _lib.MethodError(f"no free window of {p} local bits for the axis swap")
+
+
+def swapped_bitpos(n: int, nloc: int, p: int, s: int):
+    """Virtual position of every subsystem bit after the axis swap: sharded bits move to [s, s+p),
+    the window bits become the rank bits."""
+    pos = list(range(n))
+    for k in range(nloc, n):
+        pos[k] = s + (k - nloc)
+    for k in range(s, s + p):
+        pos[k] = nloc + (k - s)
+    return pos
+
+
+def axis_swap(t, s: int, p: int, out, group=None):
+    """All-to-all axis swap of a local slab `t` (2^nloc complex128): local bits [s, s+p) <-> rank bits.
+
+    Viewed as (hi, P, lo) with lo = 2^s, block [h, d, :] goes to rank d and lands at [h, src, :].
+    Works on CUDA tensors (NCCL) and on CPU tensors (gloo, used by the world_size-2 tests)."""
+    import torch
+    import torch.distributed as dist
+
+    P = 1 << p
+    lo = 1 << s
+    n = t.numel()
+    hi = n // (P * lo)
+    tin = torch.view_as_real(t).view(hi, P * lo * 2)
+    tout = torch.view_as_real(out).view(hi, P * lo * 2)
+    if P == 1:
+        tout.copy_(tin)
+        return out
+    for h in range(hi):
+        dist.all_to_all_single(tout[h], tin[h], group=group)
+    return out
+
+
+class ShardedLazySum:
+    """`mul!(y, H, x, alpha, beta)` for a Ket sharded over the ranks of a torch.distributed group."""
+
+    def __init__(self, H: LazySum, rank: int, world: int, group=None, ctx=None):
+        assert world & (world - 1) == 0, "world size must be a power of two"
+        self.H, self.rank, self.world, self.group = H, rank, world, group
+        self.n = len(H.basis_l.shape)
+        self.p = world.bit_length() - 1
+        self.nloc = self.n - self.p
+        self.ctx = ctx
+        self.h = handle(H, ctx)
+        nterms = len(H.operators)
+        od, al = C.c_uint64(), C.c_uint64()
+        local_sel = (C.c_uint8 * max(nterms, 1))()
+        remote_sel = (C.c_uint8 * max(nterms, 1))()
+        touched = 0
+        lowmask = (1 << self.nloc) - 1
+        self.n_local = self.n_remote = 0
+        for i in range(nterms):
+            _lib.check(lib.qob_lazysum_term_masks(self.h, i, C.byref(od), C.byref(al)))
+            if od.value & ~lowmask:
+                remote_sel[i] = 1
+                touched |= al.value
+                self.n_remote += 1
+            else:
+                local_sel[i] = 1
+                self.n_local += 1
+        pid = C.c_int32()
+        pos = (C.c_int32 * self.n)(*range(self.n))
+        _lib.check(lib.qob_layout_plan_create(self.h, self.nloc, pos, C.c_uint64(rank), local_sel, C.byref(pid)))
+        self.plan_local = pid.value
+        self.plan_swapped = None
+        self.swap_lo = None
+        if self.n_remote:
+            self.swap_lo = swap_window(self.nloc, self.p, touched & lowmask)
+            sp = swapped_bitpos(self.n, self.nloc, self.p, self.swap_lo)
+            pos2 = (C.c_int32 * self.n)(*sp)
+            _lib.check(lib.qob_layout_plan_create(self.h, self.nloc, pos2, C.c_uint64(rank), remote_sel, C.byref(pid)))
+            self.plan_swapped = pid.value
+        self._buf = None
+
+    def describe(self):
+        buf = C.create_string_buffer(1 << 14)
+        _lib.check(lib.qob_layout_plan_describe(self.h, self.plan_local, buf, len(buf)))
+        out = f"local[{self.n_local} terms]: {buf.value.decode()}"
+        if self.plan_swapped is not None:
+            _lib.check(lib.qob_layout_plan_describe(self.h, self.plan_swapped, buf, len(buf)))
+            out += f" | swapped[{self.n_remote} terms, window bit {self.swap_lo}]: {buf.value.decode()}"
+        return out
+
+    def _apply(self, plan, alpha, x, beta, y):
+        import torch
+
+        # coefficients may have been mutated (TimeDependentSum): handle() re-sends them
+        handle(self.H, self.ctx)
+        _lib.check(lib.qob_layout_plan_apply(self.h, plan, c64.of(alpha), C.c_void_p(x.data_ptr()), c64.of(beta),
+                                             C.c_void_p(y.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def mul_(self, y, x, alpha=1.0, beta=0.0):
+        """y_local = alpha * (H x)_local + beta * y_local;  x, y: torch complex128 CUDA slabs of 2^nloc."""
+        import torch
+
+        assert x.numel() == 1 << self.nloc and y.numel() == 1 << self.nloc
+        alpha, beta = complex(alpha), complex(beta)
+        if self.plan_swapped is None or alpha == 0:
+            self._apply(self.plan_local, alpha, x, beta, y)
+            return y
+        if self._buf is None or self._buf[0].numel() != x.numel():
+            self._buf = (torch.empty_like(x), torch.empty_like(x))
+        b1, b2 = self._buf
+        axis_swap(x, self.swap_lo, self.p, b1, self.group)        # x in the swapped layout
+        self._apply(self.plan_swapped, alpha, b1, 0.0, b2)         # partial result, swapped layout
+        if beta == 0:
+            axis_swap(b2, self.swap_lo, self.p, y, self.group)     # lands directly in y
+            self._apply(self.plan_local, alpha, x, 1.0, y)
+        else:
+            self._apply(self.plan_local, alpha, x, beta, y)
+            axis_swap(b2, self.swap_lo, self.p, b1, self.group)
+            y.add_(b1)
+        return y

@@ -1,0 +1,710 @@
+"""Host-side mirror of the reference's operator interface for the `mul!` hot path.
+
+Same names, argument meaning and error behaviour as QuantumOpticsBase.jl (citations relative to
+/root/reference): bases (QuantumInterface, src/bases.jl:1-3), `Ket`/`Bra` (src/states.jl:11-32),
+`Operator` (src/operators_dense.jl:12-20), `SparseOperator` (src/operators_sparse.jl:5-23),
+`LazyTensor` (src/operators_lazytensor.jl:15-58), `LazySum` (src/operators_lazysum.jl:41-72),
+`LazyProduct` (src/operators_lazyproduct.jl:32-59) and `mul_` = `mul!(result, a, b, alpha, beta)`.
+
+State data (`Ket.data`, `Bra.data`, a dense `Operator.data` used as a state) are torch complex128
+CUDA tensors (column-major); operator DEFINITIONS (site factors, CSC matrices, coefficients) stay on
+the host as numpy / scipy objects, exactly like `.data` of the reference's small site operators, and
+are compiled once into a libqob200 handle.  All arithmetic happens in libqob200.so; nothing here
+computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import (ArgumentError, CudaError, DimensionMismatch, IncompatibleBases, MethodError, c64, lib)
+
+C128 = np.complex128
+
+
+# ------------------------------------------------------------------------------------ bases
+class Basis:
+    """QuantumInterface.Basis: `shape` + value equality."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(s) for s in shape)
+
+    def __len__(self):
+        return int(np.prod(self.shape)) if self.shape else 1
+
+    def _key(self):
+        return (type(self).__name__, self.shape)
+
+    def __eq__(self, other):
+        return isinstance(other, Basis) and self._key() == other._key()
+
+    def __hash__(self):
+        return hash(self._key())
+
+    def __repr__(self):
+        return f"{type(self).__name__}{self._key()[1:]}"
+
+
+class GenericBasis(Basis):
+    def __init__(self, n):
+        super().__init__((int(n),))
+
+
+class SpinBasis(Basis):
+    def __init__(self, spinnumber):
+        self.spinnumber = float(spinnumber)
+        n = 2 * self.spinnumber + 1
+        assert abs(n - round(n)) < 1e-12 and n >= 1
+        super().__init__((int(round(n)),))
+
+    def _key(self):
+        return ("SpinBasis", self.shape, self.spinnumber)
+
+
+class FockBasis(Basis):
+    def __init__(self, N, offset=0):
+        self.N, self.offset = int(N), int(offset)
+        super().__init__((self.N - self.offset + 1,))
+
+    def _key(self):
+        return ("FockBasis", self.shape, self.N, self.offset)
+
+
+class NLevelBasis(Basis):
+    def __init__(self, N):
+        self.N = int(N)
+        super().__init__((self.N,))
+
+
+class CompositeBasis(Basis):
+    def __init__(self, bases):
+        self.bases = list(bases)
+        super().__init__(tuple(len(b) for b in self.bases))
+
+    def _key(self):
+        return ("CompositeBasis", tuple(b._key() for b in self.bases))
+
+
+def tensor(*xs):
+    """b1 ⊗ b2 ⊗ …  for bases (composite bases are flattened like the reference's `tensor`)."""
+    if all(isinstance(x, Basis) for x in xs):
+        out = []
+        for b in xs:
+            out.extend(b.bases if isinstance(b, CompositeBasis) else [b])
+        return CompositeBasis(out)
+    raise MethodError("tensor of operators/states is host-side construction outside the hot path; "
+                      "build LazyTensor terms instead")
+
+
+def _comp_size(b):
+    """`_comp_size` (src/operators_lazytensor.jl:517-518)."""
+    return tuple(len(x) for x in b.bases) if isinstance(b, CompositeBasis) else (len(b),)
+
+
+# ------------------------------------------------------------------------------------ data wrappers
+class Eye:
+    """FillArrays.Eye(m, n)."""
+
+    def __init__(self, m, n=None):
+        self.shape = (int(m), int(m if n is None else n))
+
+
+class Adjoint:
+    """LinearAlgebra.Adjoint wrapper (lazy `dagger`, src/operators_dense.jl:128)."""
+
+    def __init__(self, parent):
+        self.parent = parent
+        self.shape = (parent.shape[1], parent.shape[0])
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _device_colmajor(arr2d):
+    """numpy (rows, cols) -> torch CUDA complex128 tensor of the same logical shape, column-major storage."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise CudaError("no CUDA device available: quantumopticsbase.jl_b200 has no CPU fallback")
+    a = np.asarray(arr2d, dtype=C128)
+    t = torch.from_numpy(np.ascontiguousarray(a.T)).cuda()
+    return t.t()
+
+
+def _device_vector(arr):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise CudaError("no CUDA device available: quantumopticsbase.jl_b200 has no CPU fallback")
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(arr, dtype=C128).reshape(-1))).cuda()
+
+
+# ------------------------------------------------------------------------------------ states
+class StateVector:
+    def __init__(self, basis, data=None):
+        import torch
+
+        self.basis = basis
+        n = len(basis)
+        if data is None:
+            if not torch.cuda.is_available():
+                raise CudaError("no CUDA device available: quantumopticsbase.jl_b200 has no CPU fallback")
+            data = torch.zeros(n, dtype=torch.complex128, device="cuda")
+        elif not _is_torch(data):
+            data = _device_vector(data)
+        if data.numel() != n:  # src/states.jl:16-17
+            raise DimensionMismatch(f"Tried to assign data of length {data.numel()} to basis of length {n}.")
+        assert data.dtype == torch.complex128 and data.is_cuda and data.is_contiguous()
+        self.data = data
+
+    def to_host(self):
+        return self.data.cpu().numpy()
+
+    def copy(self):
+        return type(self)(self.basis, self.data.clone())
+
+
+class Ket(StateVector):
+    """Ket{B,T} with CuPtr-backed ComplexF64 data."""
+
+
+class Bra(StateVector):
+    """Bra{B,T}; `.data` are the plain components (no conjugation), as in the reference."""
+
+
+# ------------------------------------------------------------------------------------ operators
+class AbstractOperator:
+    basis_l: Basis
+    basis_r: Basis
+    _handle = None
+    _handle_ctx = None
+
+    @property
+    def shape(self):
+        return (len(self.basis_l), len(self.basis_r))
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                lib.qob_op_destroy(h)
+            except Exception:
+                pass
+
+
+class Operator(AbstractOperator):
+    """Operator{BL,BR,T}.  `data`: numpy matrix / scipy sparse / Eye / Adjoint (an operator definition,
+    host side) or a torch CUDA tensor (a dense state such as a density matrix, device side)."""
+
+    def __init__(self, basis_l, basis_r=None, data=None):
+        if data is None and basis_r is not None and not isinstance(basis_r, Basis):
+            basis_r, data = basis_l, basis_r
+        if basis_r is None:
+            basis_r = basis_l
+        self.basis_l, self.basis_r = basis_l, basis_r
+        if data is None:
+            data = _device_colmajor(np.zeros((len(basis_l), len(basis_r)), dtype=C128))
+        if sp.issparse(data):
+            data = sp.csc_matrix(data, dtype=C128)
+        elif isinstance(data, np.ndarray) or isinstance(data, (list, tuple)):
+            data = np.asfortranarray(np.asarray(data, dtype=C128))
+        if tuple(data.shape) != (len(basis_l), len(basis_r)):  # src/operators_dense.jl:16-17
+            raise DimensionMismatch(f"Tried to assign data of size {tuple(data.shape)} to bases of length "
+                                    f"{len(basis_l)} and {len(basis_r)}!")
+        if _is_torch(data):
+            import torch
+
+            assert data.dtype == torch.complex128 and data.is_cuda
+            assert data.stride() == (1, data.shape[0]) or data.numel() <= max(data.shape), \
+                "dense device operators must be column-major (use DenseOperator(...))"
+        self.data = data
+
+    # classification helpers (the reference's type aliases)
+    @property
+    def is_device_dense(self):  # DenseOpType holding device memory
+        return _is_torch(self.data)
+
+    @property
+    def is_sparse(self):  # SparseOpType (pure or adjoint)
+        d = self.data
+        return sp.issparse(d) or (isinstance(d, Adjoint) and sp.issparse(d.parent))
+
+    @property
+    def is_eye(self):
+        d = self.data
+        return isinstance(d, Eye) or (isinstance(d, Adjoint) and isinstance(d.parent, Eye))
+
+    def to_host(self):
+        d = self.data
+        if _is_torch(d):
+            return np.asfortranarray(d.cpu().numpy())
+        return _materialize(d)
+
+    def copy(self):
+        d = self.data
+        return Operator(self.basis_l, self.basis_r, d.clone() if _is_torch(d) else (d.copy() if hasattr(d, "copy") else d))
+
+
+def DenseOperator(basis_l, basis_r=None, data=None):
+    """Dense operator whose data live on the device (density matrices, Ket batches)."""
+    if data is None and basis_r is not None and not isinstance(basis_r, Basis):
+        basis_r, data = basis_l, basis_r
+    if basis_r is None:
+        basis_r = basis_l
+    if data is None:
+        data = np.zeros((len(basis_l), len(basis_r)), dtype=C128)
+    if not _is_torch(data):
+        data = _device_colmajor(data)
+    return Operator(basis_l, basis_r, data)
+
+
+def SparseOperator(basis_l, basis_r=None, data=None):
+    if data is None and basis_r is not None and not isinstance(basis_r, Basis):
+        basis_r, data = basis_l, basis_r
+    if basis_r is None:
+        basis_r = basis_l
+    if data is None:
+        data = sp.csc_matrix((len(basis_l), len(basis_r)), dtype=C128)
+    if isinstance(data, Operator):
+        data = data.data
+    return Operator(basis_l, basis_r, sp.csc_matrix(_materialize(data) if not sp.issparse(data) else data, dtype=C128))
+
+
+def _materialize(d):
+    if isinstance(d, Adjoint):
+        return np.asfortranarray(_materialize(d.parent).conj().T)
+    if isinstance(d, Eye):
+        return np.asfortranarray(np.eye(d.shape[0], d.shape[1], dtype=C128))
+    if sp.issparse(d):
+        return np.asfortranarray(d.toarray().astype(C128))
+    if _is_torch(d):
+        return np.asfortranarray(d.cpu().numpy())
+    return np.asfortranarray(np.asarray(d, dtype=C128))
+
+
+def dagger(op: Operator):
+    """Lazy adjoint (src/operators_dense.jl:128)."""
+    d = op.data
+    if _is_torch(d):
+        raise MethodError("dagger of a device state is outside the mul! hot path")
+    return Operator(op.basis_r, op.basis_l, d.parent if isinstance(d, Adjoint) else Adjoint(d))
+
+
+def dense(op: Operator):
+    return Operator(op.basis_l, op.basis_r, _materialize(op.data))
+
+
+def sparse(op: Operator):
+    return Operator(op.basis_l, op.basis_r, sp.csc_matrix(_materialize(op.data)))
+
+
+def identityoperator(b1, b2=None, kind="sparse"):
+    """identityoperator(b1, b2) (src/operators_sparse.jl:180-186); kind='eye' gives the FillArrays form."""
+    b2 = b1 if b2 is None else b2
+    if kind == "eye":
+        return Operator(b1, b2, Eye(len(b1), len(b2)))
+    return Operator(b1, b2, sp.csc_matrix(sp.eye(len(b1), len(b2), dtype=C128)))
+
+
+class LazyTensor(AbstractOperator):
+    """LazyTensor(b1[, b2], indices, operators[, factor=1])  (src/operators_lazytensor.jl:4-58)."""
+
+    def __init__(self, basis_l, *args):
+        args = list(args)
+        if args and isinstance(args[0], Basis):
+            basis_r = args.pop(0)
+        else:
+            basis_r = basis_l
+        indices, operators = args[0], args[1]
+        factor = args[2] if len(args) > 2 else 1.0
+        if not isinstance(basis_l, CompositeBasis):
+            basis_l = CompositeBasis([basis_l])
+        if not isinstance(basis_r, CompositeBasis):
+            basis_r = CompositeBasis([basis_r])
+        if isinstance(indices, (int, np.integer)):
+            indices, operators = [int(indices)], (operators,)
+        if isinstance(operators, list):
+            operators = tuple(operators)  # deprecated Vector form (:38-42)
+        self.basis_l, self.basis_r = basis_l, basis_r
+        self.indices = [int(i) for i in indices]
+        self.operators = tuple(operators)
+        self.factor = complex(factor)
+        N = len(basis_l.bases)
+        if N != len(basis_r.bases):
+            raise AssertionError("N == length(br.bases)")
+        for i in self.indices:  # check_indices
+            if not 1 <= i <= N:
+                raise ArgumentError("indices out of range")
+        if len(set(self.indices)) != len(self.indices):
+            raise ArgumentError("indices must be unique")
+        if len(self.indices) != len(self.operators):
+            raise AssertionError("length(indices) == length(ops)")
+        if self.indices != sorted(self.indices):
+            raise AssertionError("issorted(indices)")
+        for i, o in zip(self.indices, self.operators):
+            if not isinstance(o, AbstractOperator):
+                raise AssertionError("isa(ops[n], AbstractOperator)")
+            if o.basis_l != basis_l.bases[i - 1] or o.basis_r != basis_r.bases[i - 1]:
+                raise AssertionError("ops[n].basis_l == bl.bases[indices[n]] && ops[n].basis_r == br.bases[indices[n]]")
+
+    def __mul__(self, x):
+        return LazyTensor(self.basis_l, self.basis_r, self.indices, self.operators, self.factor * complex(x))
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return self * -1.0
+
+
+class LazySum(AbstractOperator):
+    """LazySum([Tf,] [factors,] operators) / LazySum(basis_l, basis_r, [factors, operators])
+    (src/operators_lazysum.jl:13-72).  `factors` may be mutated between calls (TimeDependentSum
+    set_time!, src/time_dependent_operator.jl:279-290): they are re-sent on every mul_."""
+
+    def __init__(self, *args):
+        args = list(args)
+        if args and isinstance(args[0], Basis):
+            self.basis_l, self.basis_r = args[0], args[1]
+            rest = args[2:]
+            factors, operators = (rest[0], rest[1]) if rest else ([], [])
+        elif len(args) == 2 and not isinstance(args[0], AbstractOperator):
+            factors, operators = args
+            if len(operators) == 0:
+                raise ArgumentError("LazySum needs a basis, or at least one operator!")
+            self.basis_l, self.basis_r = operators[0].basis_l, operators[0].basis_r
+        else:
+            operators = args
+            if len(operators) == 0:
+                raise ArgumentError("LazySum needs a basis, or at least one operator!")
+            factors = [1.0] * len(operators)
+            self.basis_l, self.basis_r = operators[0].basis_l, operators[0].basis_r
+        if len(factors) != len(operators):
+            raise ArgumentError("LazySum `operators` and `factors` have different lengths.")
+        self.factors = [complex(f) for f in factors]
+        self.operators = list(operators)
+        for o in self.operators:  # _check_bases, :6-11
+            if o.basis_l != self.basis_l or o.basis_r != self.basis_r:
+                raise IncompatibleBases()
+
+
+class LazyProduct(AbstractOperator):
+    """LazyProduct(operators[, factor=1]) / LazyProduct(op1, op2, …)  (src/operators_lazyproduct.jl:23-59)."""
+
+    def __init__(self, *args):
+        if len(args) >= 1 and isinstance(args[0], (list, tuple)):
+            operators = list(args[0])
+            factor = args[1] if len(args) > 1 else 1.0
+        else:
+            operators, factor = list(args), 1.0
+        if not operators:
+            raise ArgumentError("LazyProduct needs at least one operator!")
+        for a, b in zip(operators[:-1], operators[1:]):  # check_multiplicable
+            if a.basis_r != b.basis_l:
+                raise IncompatibleBases()
+        self.operators = operators
+        self.factor = complex(factor)
+        self.basis_l, self.basis_r = operators[0].basis_l, operators[-1].basis_r
+
+
+# ------------------------------------------------------------------------------------ handles
+def _factor_struct(d, keep):
+    """qob_factor for operator data `d`; numpy arrays referenced by the struct are appended to `keep`."""
+    f = _lib.Factor()
+    trans = _lib.OP_N
+    if isinstance(d, Adjoint):
+        trans = _lib.OP_C
+        d = d.parent
+        if isinstance(d, Adjoint):
+            raise MethodError("nested Adjoint")
+    f.trans = trans
+    f.nrows, f.ncols = int(d.shape[0]), int(d.shape[1])
+    if isinstance(d, Eye):
+        f.kind = _lib.FACTOR_EYE
+    elif sp.issparse(d):
+        m = sp.csc_matrix(d, dtype=C128)
+        colptr = (m.indptr.astype(np.int64) + 1)
+        rowval = (m.indices.astype(np.int64) + 1)
+        nzval = np.ascontiguousarray(m.data.astype(C128))
+        keep.extend([colptr, rowval, nzval])
+        f.kind = _lib.FACTOR_CSC
+        f.colptr, f.rowval, f.nzval = colptr.ctypes.data, rowval.ctypes.data, nzval.ctypes.data
+    elif isinstance(d, np.ndarray):
+        a = np.asfortranarray(d.astype(C128))
+        keep.append(a)
+        f.kind = _lib.FACTOR_DENSE
+        f.dense = a.ctypes.data
+    else:
+        # e.g. a device tensor or an arbitrary AbstractOperator used as a site factor:
+        # the reference throws MethodError/ArgumentError (operators_lazytensor.jl:639-641)
+        raise MethodError(f"no kernel for a site factor with data of type {type(d).__name__}")
+    return f
+
+
+def handle(op, ctx=None):
+    """libqob200 handle of an operator definition (built once, cached on the object)."""
+    ctx = _lib.context() if ctx is None else ctx
+    if getattr(op, "_handle", None) and op._handle_ctx is ctx:
+        if isinstance(op, LazySum):
+            _refresh_coefs(op)
+        return op._handle
+    h = C.c_void_p()
+    keep = []
+    if isinstance(op, LazyTensor):
+        dl = (C.c_int64 * len(op.basis_l.shape))(*op.basis_l.shape)
+        dr = (C.c_int64 * len(op.basis_r.shape))(*op.basis_r.shape)
+        n = len(op.indices)
+        sites = (C.c_int32 * max(n, 1))(*op.indices)
+        facs = (_lib.Factor * max(n, 1))()
+        for k, o in enumerate(op.operators):
+            if not isinstance(o, Operator):
+                raise MethodError(f"LazyTensor factor of type {type(o).__name__} has no mul! kernel")
+            facs[k] = _factor_struct(o.data, keep)
+        _lib.check(lib.qob_lazytensor_create(ctx, len(op.basis_l.shape), dl, dr, n, sites, facs, c64.of(op.factor),
+                                             C.byref(h)))
+    elif isinstance(op, Operator):
+        if op.is_device_dense:
+            raise MethodError("dense device x dense device products are BLAS territory (operators_dense.jl:394), "
+                              "not part of the lazy/sparse mul! path")
+        f = _factor_struct(op.data, keep)
+        if op.is_sparse:
+            _lib.check(lib.qob_sparse_create(ctx, C.byref(f), C.byref(h)))
+        elif op.is_eye:
+            one = (C.c_int64 * 1)(len(op.basis_l))
+            two = (C.c_int64 * 1)(len(op.basis_r))
+            site = (C.c_int32 * 1)(1)
+            _lib.check(lib.qob_lazytensor_create(ctx, 1, one, two, 1, site, C.byref(f), c64.of(1.0), C.byref(h)))
+        else:
+            _lib.check(lib.qob_dense_create(ctx, C.byref(f), C.byref(h)))
+    elif isinstance(op, LazySum):
+        hs = [handle(o, ctx) for o in op.operators]
+        n = len(hs)
+        arr = (C.c_void_p * max(n, 1))(*[x.value if isinstance(x, C.c_void_p) else x for x in hs])
+        cf = (c64 * max(n, 1))(*[c64.of(f) for f in op.factors])
+        _lib.check(lib.qob_lazysum_create(ctx, len(op.basis_l), len(op.basis_r), n, cf, arr, C.byref(h)))
+        op._sent_factors = list(op.factors)
+    elif isinstance(op, LazyProduct):
+        hs = [handle(o, ctx) for o in op.operators]
+        arr = (C.c_void_p * len(hs))(*[x.value if isinstance(x, C.c_void_p) else x for x in hs])
+        _lib.check(lib.qob_lazyproduct_create(ctx, len(hs), arr, c64.of(op.factor), C.byref(h)))
+    else:
+        raise MethodError(f"no mul! method for operator type {type(op).__name__}")
+    op._handle, op._handle_ctx = h, ctx
+    return h
+
+
+def _refresh_coefs(op: LazySum):
+    if len(op.factors) != len(op.operators):
+        raise ArgumentError("LazySum `operators` and `factors` have different lengths.")
+    if getattr(op, "_sent_factors", None) != [complex(f) for f in op.factors]:
+        n = len(op.factors)
+        cf = (c64 * max(n, 1))(*[c64.of(f) for f in op.factors])
+        _lib.check(lib.qob_lazysum_set_coefs(op._handle, n, cf))
+        op._sent_factors = [complex(f) for f in op.factors]
+    for o in op.operators:
+        if isinstance(o, LazySum) and getattr(o, "_handle", None):
+            _refresh_coefs(o)
+
+
+def describe(op, side="left", batch=1, ctx=None):
+    """Text description of the device plan chosen for `op` (kernels, passes, tiles)."""
+    buf = C.create_string_buffer(1 << 16)
+    s = _lib.SIDE_LEFT if side in ("left", 0) else _lib.SIDE_RIGHT
+    _lib.check(lib.qob_op_describe(handle(op, ctx), s, int(batch), buf, len(buf)))
+    return buf.value.decode()
+
+
+# ------------------------------------------------------------------------------------ mul!
+def _stream():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _is_state_op(x):
+    return isinstance(x, Operator) and x.is_device_dense
+
+
+def mul_(result, a, b, alpha=1.0, beta=0.0):
+    """mul!(result, a, b, alpha, beta) -> result:  result = alpha*a*b + beta*result.
+
+    Dispatch (who is the operator, who is the state) follows the reference's method table:
+      Ket  <- op * Ket                     (operators_lazytensor.jl:539, lazysum:189, lazyproduct:103, sparse:201)
+      Bra  <- Bra * op                     (:559, :202, :117, sparse:202)
+      Op   <- op * DenseOp                 (:576, :215, :131, sparse:199)
+      Op   <- DenseOp * op                 (:593, :227, :148, sparse:200)
+    alpha/beta: any Python number (bool/int/float/complex), promoted to ComplexF64."""
+    alpha, beta = complex(alpha), complex(beta)
+    if isinstance(b, Ket) and isinstance(a, AbstractOperator):
+        if not isinstance(result, Ket):
+            raise MethodError("result must be a Ket")
+        side, op, state, batch = _lib.SIDE_LEFT, a, b, 1
+        _check_bases(result.basis, op.basis_l, op.basis_r, state.basis, (len(result.basis),), (len(state.basis),), op)
+    elif isinstance(a, Bra) and isinstance(b, AbstractOperator):
+        if not isinstance(result, Bra):
+            raise MethodError("result must be a Bra")
+        side, op, state, batch = _lib.SIDE_RIGHT, b, a, 1
+        _check_bases(state.basis, op.basis_l, op.basis_r, result.basis, (len(state.basis),), (len(result.basis),), op,
+                     right=True)
+    elif _is_state_op(b) and isinstance(a, AbstractOperator) and not _is_state_op(a):
+        if not _is_state_op(result):
+            raise MethodError("result must be a dense device Operator")
+        side, op, state, batch = _lib.SIDE_LEFT, a, b, b.data.shape[1]
+        if result.basis_r != b.basis_r:
+            raise IncompatibleBases()
+        _check_bases(result.basis_l, op.basis_l, op.basis_r, state.basis_l, result.data.shape, state.data.shape, op)
+    elif _is_state_op(a) and isinstance(b, AbstractOperator) and not _is_state_op(b):
+        if not _is_state_op(result):
+            raise MethodError("result must be a dense device Operator")
+        side, op, state, batch = _lib.SIDE_RIGHT, b, a, a.data.shape[0]
+        if result.basis_l != a.basis_l:
+            raise IncompatibleBases()
+        _check_bases(state.basis_r, op.basis_l, op.basis_r, result.basis_r, state.data.shape, result.data.shape, op,
+                     right=True)
+    else:
+        raise MethodError(f"no mul! method for ({type(result).__name__}, {type(a).__name__}, {type(b).__name__})")
+    if isinstance(op, Operator) and op.is_sparse and batch == 1 and isinstance(state, StateVector) \
+            and isinstance(op.data, Adjoint):
+        # gemv! exists for SparseOpPureType only (operators_sparse.jl:201-202)
+        raise MethodError("mul!(Ket/Bra, adjoint sparse operator) has no sparse gemv! method")
+    h = handle(op)
+    _lib.check(lib.qob_op_apply(h, side, c64.of(alpha), C.c_void_p(state.data.data_ptr()), c64.of(beta),
+                                C.c_void_p(result.data.data_ptr()), int(batch), _stream()))
+    return result
+
+
+def _check_bases(out_basis, op_bl, op_br, in_basis, out_shape, in_shape, op, right=False):
+    """Bases are type parameters in the reference: a mismatch never reaches the kernels.  Size
+    mismatches raise DimensionMismatch (sparsematrix.jl:100-102, operators_lazytensor.jl:695-703),
+    equal sizes with different bases raise IncompatibleBases."""
+    if not right:
+        ok = (out_basis == op_bl) and (in_basis == op_br)
+        size_ok = len(out_basis) == len(op_bl) and len(in_basis) == len(op_br)
+    else:
+        ok = (out_basis == op_bl) and (in_basis == op_br)
+        size_ok = len(out_basis) == len(op_bl) and len(in_basis) == len(op_br)
+    if not size_ok:
+        raise DimensionMismatch(f"operator is {len(op_bl)}x{len(op_br)}, state/result have sizes {in_shape}/{out_shape}")
+    if not ok:
+        raise IncompatibleBases()
+
+
+def apply_host(op, x, side="left", alpha=1.0, beta=0.0, y=None, batch=1):
+    """End-to-end call with HOST buffers (numpy, ideally pinned): H2D, apply, D2H inside libqob200
+    (`qob_op_apply_host`).  Returns y (numpy complex128, column-major)."""
+    s = _lib.SIDE_LEFT if side in ("left", 0) else _lib.SIDE_RIGHT
+    dl, dr = len(op.basis_l), len(op.basis_r)
+    n_out = (dl if s == _lib.SIDE_LEFT else dr) * batch
+    xh = np.ascontiguousarray(np.asarray(x, dtype=C128).reshape(-1, order="F"))
+    if y is None:
+        y = np.zeros(n_out, dtype=C128)
+    assert y.dtype == C128 and y.flags.c_contiguous and y.size == n_out
+    _lib.check(lib.qob_op_apply_host(handle(op), s, c64.of(alpha), C.c_void_p(xh.ctypes.data), c64.of(beta),
+                                     C.c_void_p(y.ctypes.data), int(batch)))
+    return y
+
+
+# ------------------------------------------------------------------------------------ site operators
+def _spdiagm(n, offsets):
+    m = sp.lil_matrix((n, n), dtype=C128)
+    for off, vals in offsets.items():
+        for t, v in enumerate(vals):
+            i, j = (t, t + off) if off >= 0 else (t - off, t)
+            m[i, j] = v
+    return sp.csc_matrix(m)
+
+
+def sigmax(b: SpinBasis):
+    """src/spin.jl:14-20"""
+    n, s = len(b), b.spinnumber
+    d = [math.sqrt((s + 1) * 2 * a - a * (a + 1)) for a in range(1, n)]
+    return Operator(b, b, _spdiagm(n, {1: d, -1: d}))
+
+
+def sigmay(b: SpinBasis):
+    """src/spin.jl:34-40"""
+    n, s = len(b), b.spinnumber
+    d = [1j * math.sqrt((s + 1) * 2 * a - a * (a + 1)) for a in range(1, n)]
+    return Operator(b, b, _spdiagm(n, {-1: d, 1: [-v for v in d]}))
+
+
+def sigmaz(b: SpinBasis):
+    """src/spin.jl:54-60"""
+    n, s = len(b), b.spinnumber
+    return Operator(b, b, _spdiagm(n, {0: [2 * (s - t) for t in range(n)]}))
+
+
+def sigmap(b: SpinBasis):
+    """src/spin.jl:68-75"""
+    n, s = len(b), b.spinnumber
+    S = (s + 1) * s
+    return Operator(b, b, _spdiagm(n, {1: [math.sqrt(S - m * (m + 1)) for m in [s - 1 - t for t in range(n - 1)]]}))
+
+
+def sigmam(b: SpinBasis):
+    """src/spin.jl:83-90"""
+    n, s = len(b), b.spinnumber
+    S = (s + 1) * s
+    return Operator(b, b, _spdiagm(n, {-1: [math.sqrt(S - m * (m - 1)) for m in [s - t for t in range(n - 1)]]}))
+
+
+def number(b: FockBasis):
+    """src/fock.jl:8-12"""
+    return Operator(b, b, _spdiagm(len(b), {0: [float(v) for v in range(b.offset, b.N + 1)]}))
+
+
+def destroy(b: FockBasis):
+    """src/fock.jl:22-28"""
+    return Operator(b, b, _spdiagm(len(b), {1: [math.sqrt(float(v)) for v in range(b.offset + 1, b.N + 1)]}))
+
+
+def create(b: FockBasis):
+    """src/fock.jl:38-44"""
+    return Operator(b, b, _spdiagm(len(b), {-1: [math.sqrt(float(v)) for v in range(b.offset + 1, b.N + 1)]}))
+
+
+def transition(b: NLevelBasis, to, frm):
+    """src/nlevel.jl:8-18"""
+    if not (1 <= to <= b.N and 1 <= frm <= b.N):
+        raise IndexError("BoundsError: transition indices must be between 1 and b.N")
+    m = sp.lil_matrix((b.N, b.N), dtype=C128)
+    m[to - 1, frm - 1] = 1.0
+    return Operator(b, b, sp.csc_matrix(m))
+
+
+def randstate(b, seed=0, normalize=True):
+    """randstate(b) (src/state_definitions.jl:6-10) with the counter-based generator shared with the
+    oracle (qob_fill_state): re/im uniform in [-1, 1), then normalised on the device."""
+    import torch
+
+    k = Ket(b)
+    fill_state(k.data, seed)
+    if normalize:
+        k.data /= math.sqrt(norm2(k.data))
+    return k
+
+
+def fill_state(t, seed, scale=1.0, offset=0):
+    _lib.check(lib.qob_fill_state(C.c_void_p(t.data_ptr()), int(offset), t.numel(), C.c_uint64(seed), float(scale),
+                                  _stream()))
+    return t
+
+
+def norm2(t):
+    out = C.c_double()
+    _lib.check(lib.qob_norm2(C.c_void_p(t.data_ptr()), t.numel(), C.byref(out), _stream()))
+    return out.value
+
+
+def dot(x, y):
+    out = c64()
+    _lib.check(lib.qob_dot(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), x.numel(), C.byref(out), _stream()))
+    return complex(out.re, out.im)
+
+
+def launch_count():
+    return int(lib.qob_launch_count())

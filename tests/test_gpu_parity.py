@@ -1,0 +1,363 @@
+"""GPU parity tests: libqob200 (through the C ABI, via the qob200 mirror) against the CPU oracle on the
+same seeded inputs.  Tolerance: relative 2-norm error <= 1e-12 in ComplexF64 (BASELINE.json north_star);
+the reference's own tests use 1e-11 … 1e-13 absolute on O(1) data (test/test_operators_lazytensor.jl:237-416).
+
+The structure follows the reference's tests: test/test_operators_lazytensor.jl (mul! for Ket/Bra/Op-left/
+Op-right, dense vs sparse factors, (alpha,beta) in {(1,0),(1.5,2.1)}, isometries, NaN kill),
+test/test_operators_lazysum.jl:255-347, test/test_operators_lazyproduct.jl:171-244,
+test/test_operators_sparse.jl:318-437.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import helpers as H
+from helpers import O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def Q():
+    import qob200
+
+    return qob200
+
+
+def test_native_library_is_loaded(Q):
+    """The product path is the CUDA library: it must be loaded from the tree and launch kernels."""
+    import torch
+
+    assert torch.cuda.is_available()
+    with open("/proc/self/maps") as f:
+        assert "libqob200.so" in f.read()
+    before = Q.launch_count()
+    b = Q.SpinBasis(0.5)
+    B = Q.tensor(b, b, b)
+    op = Q.LazyTensor(B, [2], (Q.sigmax(b),))
+    x = Q.randstate(B, seed=1)
+    y = Q.Ket(B)
+    Q.mul_(y, op, x)
+    assert Q.launch_count() > before
+    xh = x.to_host().reshape(2, 2, 2, order="F")
+    assert np.allclose(y.to_host().reshape(2, 2, 2, order="F"), xh[:, ::-1, :], atol=1e-15)
+
+
+# ------------------------------------------------------------------ LazyTensor (test_operators_lazytensor.jl:237-416)
+@pytest.mark.parametrize("sparse", [False, True])
+@pytest.mark.parametrize("indices", [[1, 2, 3], [1, 2], [2, 3], [1, 3], [1], [2], [3]])
+def test_lazytensor_rectangular(Q, sparse, indices):
+    rng = np.random.default_rng(10 + len(indices))
+    # b_l = b1a⊗b2a⊗b3a, b_r = b1b⊗b2b⊗b3b with equal sizes where no factor acts
+    dl_full, dr_full = (2, 4, 3), (3, 2, 5)
+    dims_l = tuple(dl_full[k] if (k + 1) in indices else 3 for k in range(3))
+    dims_r = tuple(dr_full[k] if (k + 1) in indices else 3 for k in range(3))
+    datas = []
+    for i in indices:
+        a = H.rnd(rng, dims_l[i - 1], dims_r[i - 1])
+        datas.append(sp.csc_matrix(a) if sparse else a)
+    op = H.lazytensor(dims_l, dims_r, indices, datas, 0.1)
+    H.check_mul(op, dims_l, dims_r, rng, tol=TOL)
+
+
+def test_lazytensor_mixed_and_adjoint_factors(Q):
+    rng = np.random.default_rng(3)
+    dims_l, dims_r = (2, 3, 4), (3, 2, 4)
+    a1 = H.rnd(rng, 2, 3)
+    a2 = ("adj", H.rnd(rng, 2, 3))            # explicit adjoint dense (test_operators_lazytensor.jl:239-240)
+    a3 = ("adj", H.sprnd(rng, 4, 4, 0.6))     # adjoint sparse
+    op = H.lazytensor(dims_l, dims_r, [1, 2, 3], [a1, a2, a3], 0.1)
+    H.check_mul(op, dims_l, dims_r, rng, tol=TOL)
+    op = H.lazytensor(dims_l, dims_r, [1, 2], [sp.csc_matrix(a1), a2], -0.7j)
+    H.check_mul(op, dims_l, dims_r, rng, tol=TOL)
+
+
+def test_lazytensor_no_factors_scaled_identity_and_isometry(Q):
+    """:373-407 — LazyTensor with no operators: scaled identity / scaled isometry."""
+    rng = np.random.default_rng(4)
+    op = H.lazytensor((2, 3), (2, 3), [], [], 0.5 - 0.25j)
+    H.check_mul(op, (2, 3), (2, 3), rng, tol=TOL)
+    op = H.lazytensor((2, 3, 2), (2, 2, 3), [], [], 1.5)
+    H.check_mul(op, (2, 3, 2), (2, 2, 3), rng, tol=TOL)
+
+
+def test_lazytensor_explicit_identities_and_isometries(Q):
+    """:446-494 — explicit identityoperator factors (Eye), non-square isometry, NaN kill, alpha=0."""
+    rng = np.random.default_rng(5)
+    dims_l, dims_r = (3, 2, 2, 1, 2), (3, 2, 2, 2, 1)
+    num = sp.csc_matrix(np.diag([0.0, 1.0, 2.0]).astype(complex))
+    sx = sp.csc_matrix(np.array([[0, 1], [1, 0]], dtype=complex))
+    iso = ("eye", 2, 1)
+    n1 = H.lazytensor(dims_l, dims_r, [1, 3], [num, sx])
+    n1_sp = H.lazytensor(dims_l, dims_r, [1, 2, 3, 5], [num, ("eye", 2, 2), sx, iso])
+    n1_de = H.lazytensor(dims_l, dims_r, [1, 2, 3, 5], [num.toarray(), ("eye", 2, 2), sx, iso])
+    Dl, Dr = int(np.prod(dims_l)), int(np.prod(dims_r))
+    for op in (n1, n1_sp, n1_de):
+        H.check_mul(op, dims_l, dims_r, rng, tol=TOL)
+        # beta = 0 must kill NaNs, alpha = 0 must only scale (:476-488)
+        x = H.rnd(rng, Dr, 4)
+        s = H.denseop(dims_r, (4,), x)
+        for (al, be) in [(0.7, 0), (0, 0.3), (0, 0)]:
+            y0 = H.rnd(rng, Dl, 4)
+            ref = H.denseop(dims_l, (4,), y0)
+            O.mul(ref.o, op.o, s.o, al, be)
+            bad = y0 * (np.nan if be == 0 else 1.0)
+            r = H.denseop(dims_l, (4,), bad)
+            Q.mul_(r.q, op.q, s.q, al, be)
+            out = r.q.to_host()
+            assert np.all(np.isfinite(out))
+            assert H.rel_err(out, ref.o.data) <= TOL
+
+
+def test_lazytensor_many_factors_and_higher_dims(Q):
+    """terms with more factors than the fused kernel handles go through the sequential path"""
+    rng = np.random.default_rng(6)
+    dims = (2, 3, 2, 2, 3, 2)
+    datas = [H.rnd(rng, d, d) for d in dims]
+    op = H.lazytensor(dims, dims, [1, 2, 3, 4, 5, 6], datas, 0.3)
+    H.check_mul(op, dims, dims, rng, tol=TOL, nbatch=3)
+    datas = [H.sprnd(rng, d, d, 0.7) for d in dims[:5]]
+    op = H.lazytensor(dims, dims, [1, 2, 3, 4, 5], datas, 0.3)
+    H.check_mul(op, dims, dims, rng, tol=TOL, nbatch=3)
+
+
+def test_lazytensor_errors(Q):
+    b2, b3 = Q.GenericBasis(2), Q.GenericBasis(3)
+    B = Q.CompositeBasis([b2, b3])
+    a = Q.Operator(b2, b2, np.eye(2))
+    with pytest.raises(AssertionError):  # unsorted indices (operators_lazytensor.jl:26)
+        Q.LazyTensor(B, [2, 1], (Q.Operator(b3, b3, np.eye(3)), a))
+    with pytest.raises(AssertionError):  # wrong site basis (:30-31)
+        Q.LazyTensor(B, [2], (a,))
+    lt = Q.LazyTensor(B, [1], (a,))
+    x = Q.Ket(Q.CompositeBasis([b2, b2]), np.ones(4))
+    with pytest.raises(Q.DimensionMismatch):
+        Q.mul_(Q.Ket(B), lt, x)
+    k = Q.Ket(B, np.ones(6))
+    with pytest.raises(Q.ArgumentError):  # aliasing (:704-708)
+        Q.mul_(k, lt, k)
+
+
+# ------------------------------------------------------------------ dense d>=16 factors: DMMA axis kernel
+@pytest.mark.parametrize("dims,indices", [((20, 3, 17), [1, 3]), ((3, 24, 2), [2]), ((16, 16), [1, 2]), ((5, 33), [2]),
+                                           ((48, 48, 3), [1, 2])])
+def test_lazytensor_dense_axis_kernel(Q, dims, indices):
+    rng = np.random.default_rng(7)
+    datas = [H.rnd(rng, dims[i - 1], dims[i - 1]) / np.sqrt(dims[i - 1]) for i in indices]
+    op = H.lazytensor(dims, dims, indices, datas, 0.9)
+    assert "dmma" in Q.describe(op.q)
+    H.check_mul(op, dims, dims, rng, tol=TOL, nbatch=6)
+
+
+def test_lazytensor_dense_axis_rectangular(Q):
+    rng = np.random.default_rng(8)
+    dims_l, dims_r = (18, 3, 40), (25, 3, 17)
+    datas = [H.rnd(rng, 18, 25) / 5, H.rnd(rng, 40, 17) / 5]
+    op = H.lazytensor(dims_l, dims_r, [1, 3], datas, 1.1)
+    H.check_mul(op, dims_l, dims_r, rng, tol=TOL, nbatch=4)
+
+
+# ------------------------------------------------------------------ LazySum (test_operators_lazysum.jl:255-347)
+def test_lazysum_of_lazytensors_and_mixed_terms(Q):
+    rng = np.random.default_rng(11)
+    dims = (2, 3, 4)
+    D = int(np.prod(dims))
+    t1 = H.lazytensor(dims, dims, [1, 3], [H.rnd(rng, 2, 2), H.sprnd(rng, 4, 4, 0.5)], 0.3)
+    t2 = H.lazytensor(dims, dims, [2], [H.rnd(rng, 3, 3)], 1.0)
+    t3 = H.operator(dims, dims, H.sprnd(rng, D, D, 0.1))           # SparseOperator term
+    t4 = H.operator(dims, dims, H.rnd(rng, D, D) / D)               # dense Operator term
+    t5 = H.lazyproduct([t2, t1], 0.5)                               # LazyProduct term
+    inner = H.lazysum(dims, dims, [0.5, -0.25j], [t1, t3])          # nested LazySum
+    s = H.lazysum(dims, dims, [0.1, 0.3 + 0.1j, -0.7, 0.2, 1.0, 2.0], [t1, t2, t3, t4, t5, inner])
+    H.check_mul(s, dims, dims, rng, tol=TOL)
+    s2 = H.lazysum(dims, dims, [0.1, 0.3], [t1, t2])
+    H.check_mul(s2, dims, dims, rng, tol=TOL)
+    # coefficient update (TimeDependentSum set_time!, time_dependent_operator.jl:279-290)
+    s2.q.factors[0] = 2.5 - 1j
+    s2.o.factors[0] = 2.5 - 1j
+    H.check_mul(s2, dims, dims, rng, tol=TOL)
+
+
+def test_lazysum_empty_and_nan_kill(Q):
+    """:311,335 — empty sum: result = beta*result, beta=0 kills NaN; dimension errors :118-121"""
+    rng = np.random.default_rng(12)
+    dims = (2, 3)
+    s = H.lazysum(dims, dims, [], [])
+    x = H.ket(dims, H.rnd(rng, 6))
+    y0 = H.rnd(rng, 6)
+    r = H.ket(dims, y0 * np.nan)
+    Q.mul_(r.q, s.q, x.q, 1.0, 0.0)
+    assert np.all(r.q.to_host() == 0)
+    r = H.ket(dims, y0)
+    Q.mul_(r.q, s.q, x.q, 1.0, 2.0)
+    assert H.rel_err(r.q.to_host(), 2.0 * y0) <= TOL
+    with pytest.raises(Q.DimensionMismatch):
+        Q.mul_(Q.Ket(Q.CompositeBasis([Q.GenericBasis(2), Q.GenericBasis(2)])), s.q, x.q)
+
+
+# ------------------------------------------------------------------ LazyProduct (test_operators_lazyproduct.jl:171-244)
+@pytest.mark.parametrize("nops", [1, 2, 3])
+def test_lazyproduct_chain(Q, nops):
+    rng = np.random.default_rng(20 + nops)
+    chain_dims = [(2, 3), (3, 2), (2, 2), (4, 1)][: nops + 1]
+    ops = []
+    for k in range(nops):
+        dl, dr = chain_dims[k], chain_dims[k + 1]
+        if k % 2 == 0:
+            ops.append(H.operator(dl, dr, H.sprnd(rng, int(np.prod(dl)), int(np.prod(dr)), 0.6)))
+        else:
+            ops.append(H.lazytensor(dl, dr, [1, 2], [H.rnd(rng, dl[0], dr[0]), H.rnd(rng, dl[1], dr[1])], 0.7))
+    p = H.lazyproduct(ops, 0.5 + 0.5j)
+    H.check_mul(p, chain_dims[0], chain_dims[nops], rng, tol=TOL,
+                scalars=((1, 0), (1.5, 2.1), (0, 1.3)))
+
+
+# ------------------------------------------------------------------ SparseOperator (test_operators_sparse.jl:318-437)
+@pytest.mark.parametrize("shape", [(3, 5, 7), (50, 60, 55)])  # small gemm and the nnz > 550 branch
+def test_sparse_gemm_gemv(Q, shape):
+    rng = np.random.default_rng(30)
+    m, k, n = shape
+    M = H.sprnd(rng, m, k, 0.5)
+    op = H.operator((m,), (k,), M)
+    H.check_mul(op, (m,), (k,), rng, tol=TOL, nbatch=n)
+    # lazy adjoint sparse (gemm! only; gemv! has no adjoint method, operators_sparse.jl:201-202)
+    opa = H.operator((k,), (m,), ("adj", M))
+    H.check_mul(opa, (k,), (m,), rng, tol=TOL, nbatch=n, kinds=("opl", "opr"))
+    with pytest.raises(Q.MethodError):
+        Q.mul_(Q.Ket(opa.q.basis_l), opa.q, Q.Ket(opa.q.basis_r))
+    with pytest.raises(Q.DimensionMismatch):
+        Q.mul_(Q.Ket(Q.GenericBasis(m + 1)), op.q, Q.Ket(op.q.basis_r))
+
+
+def test_dense_operator_as_operator(Q):
+    rng = np.random.default_rng(31)
+    for (m, k) in [(7, 5), (40, 33)]:
+        op = H.operator((m,), (k,), H.rnd(rng, m, k) / k)
+        H.check_mul(op, (m,), (k,), rng, tol=TOL, nbatch=9)
+        opa = H.operator((k,), (m,), ("adj", H.rnd(rng, m, k) / k))
+        H.check_mul(opa, (k,), (m,), rng, tol=TOL, nbatch=9)
+
+
+# ------------------------------------------------------------------ BASELINE configs
+def _pauli():
+    sx = np.array([[0, 1], [1, 0]], dtype=complex)
+    sy = np.array([[0, -1j], [1j, 0]], dtype=complex)
+    sz = np.array([[1, 0], [0, -1]], dtype=complex)
+    return sx, sy, sz
+
+
+def _chain_terms(n, kind, dense, rng):
+    """TFIM (2N terms) or Heisenberg (3N terms) on a periodic chain, sparse factors as spin.jl builds them."""
+    sx, sy, sz = _pauli()
+    wrap = (lambda a: a) if dense else sp.csc_matrix
+    dims = (2,) * n
+    terms, coefs = [], []
+    for i in range(1, n + 1):
+        j = i % n + 1
+        idx = sorted([i, j])
+        if kind == "tfim":
+            terms.append(H.lazytensor(dims, dims, [i], [wrap(sx)]))
+            coefs.append(-rng.uniform(0.5, 1.5))
+            terms.append(H.lazytensor(dims, dims, idx, [wrap(sz), wrap(sz)]))
+            coefs.append(-rng.uniform(0.5, 1.5))
+        else:
+            for s in (sx, sy, sz):
+                terms.append(H.lazytensor(dims, dims, idx, [wrap(s), wrap(s)]))
+                coefs.append(rng.uniform(0.5, 1.5))
+    return dims, coefs, terms
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_config1_tfim_n12(Q, dense):
+    """BASELINE config 1: TFIM N=12, LazySum of 2N embedded terms on a random Ket (generic fused kernel)."""
+    rng = np.random.default_rng(40)
+    dims, coefs, terms = _chain_terms(12, "tfim", dense, rng)
+    s = H.lazysum(dims, dims, coefs, terms)
+    assert "gather" in Q.describe(s.q)
+    H.check_mul(s, dims, dims, rng, tol=TOL, kinds=("ket", "bra", "opl"), nbatch=3)
+
+
+@pytest.mark.parametrize("n,T,L", [(12, 10, 3), (14, 12, 3), (15, 11, 2), (16, 12, 4), (17, 13, 3), (18, 12, 3)])
+@pytest.mark.parametrize("kind", ["tfim", "heis"])
+def test_qtile_chain_vs_oracle(Q, monkeypatch, n, T, L, kind):
+    """The tile kernel (forced on for small chains) against the reference's per-term sparse recursion."""
+    monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    monkeypatch.setenv("QOB_QTILE_T", str(T))
+    monkeypatch.setenv("QOB_QTILE_L", str(L))
+    rng = np.random.default_rng(50 + n)
+    dims, coefs, terms = _chain_terms(n, kind, False, rng)
+    s = H.lazysum(dims, dims, coefs, terms)
+    assert "qtile" in Q.describe(s.q)
+    H.check_mul(s, dims, dims, rng, tol=TOL, kinds=("ket", "bra"))
+    if n <= 14:
+        H.check_mul(s, dims, dims, rng, tol=TOL, kinds=("opl", "opr"), nbatch=4, scalars=((1, 0), (1.5, 2.1)))
+
+
+def test_qtile_general_2x2_factors_and_three_site_terms(Q, monkeypatch):
+    monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    rng = np.random.default_rng(60)
+    n = 14
+    dims = (2,) * n
+    terms, coefs = [], []
+    for idx in ([1], [7], [14], [1, 14], [3, 9], [2, 3, 4], [1, 8, 14], [12, 13]):
+        datas = [H.rnd(rng, 2, 2) if rng.uniform() < 0.5 else H.sprnd(rng, 2, 2, 0.7) for _ in idx]
+        terms.append(H.lazytensor(dims, dims, idx, datas, rng.uniform(0.5, 1.0)))
+        coefs.append(H.rnd(rng, 1)[0])
+    s = H.lazysum(dims, dims, coefs, terms)
+    assert "qtile" in Q.describe(s.q)
+    H.check_mul(s, dims, dims, rng, tol=TOL, kinds=("ket", "bra"))
+
+
+def test_config2_jaynes_cummings_liouvillian(Q):
+    """BASELINE config 2: H (sparse, 258 nnz) x rho (dense 130x130): mul!(drho,H,rho,-i,0); mul!(drho,rho,H,i,1)."""
+    rng = np.random.default_rng(70)
+    nf = 65
+    a = O.destroy(64).data
+    ad = O.create(64).data
+    num = O.number(64).data
+    sz, sp_, sm = O.sigmaz().data, O.sigmap().data, O.sigmam().data
+    i2, inf = sp.identity(2, format="csc"), sp.identity(nf, format="csc")
+    # tensor(a, b) = kron(b, a): subsystem 1 (cavity) is the fast index
+    Hm = (1.0 * sp.kron(i2, num) + 0.5 * 0.9 * sp.kron(sz, inf) + 0.1 * (sp.kron(sp_, a) + sp.kron(sm, ad))).tocsc()
+    assert Hm.nnz == 258
+    op = H.operator((nf, 2), (nf, 2), Hm)
+    rho = H.rnd(rng, 130, 130)
+    s = H.denseop((nf, 2), (nf, 2), rho)
+    r = H.denseop((nf, 2), (nf, 2), np.zeros((130, 130), dtype=complex))
+    O.mul(r.o, op.o, s.o, -1j, 0)
+    O.mul(r.o, s.o, op.o, 1j, 1)
+    Q.mul_(r.q, op.q, s.q, -1j, 0)
+    Q.mul_(r.q, s.q, op.q, 1j, 1)
+    assert H.rel_err(r.q.to_host(), r.o.data) <= TOL
+    # the same H as a LazySum of LazyTensors
+    dims = (nf, 2)
+    terms = [H.lazytensor(dims, dims, [1], [num]), H.lazytensor(dims, dims, [2], [sz]),
+             H.lazytensor(dims, dims, [1, 2], [a, sp_]), H.lazytensor(dims, dims, [1, 2], [ad, sm])]
+    ls = H.lazysum(dims, dims, [1.0, 0.45, 0.1, 0.1], terms)
+    r2 = H.denseop(dims, dims, np.zeros((130, 130), dtype=complex))
+    Q.mul_(r2.q, ls.q, s.q, -1j, 0)
+    Q.mul_(r2.q, s.q, ls.q, 1j, 1)
+    assert H.rel_err(r2.q.to_host(), r.o.data) <= TOL
+
+
+def test_config3_two_mode_fock_dense_factors(Q):
+    """BASELINE config 3 (reduced batch): dims (48,48,3), LazyTensor with two dense d=48 factors on a Ket batch."""
+    rng = np.random.default_rng(80)
+    dims = (48, 48, 3)
+    A1, A2 = H.rnd(rng, 48, 48) / 7, H.rnd(rng, 48, 48) / 7
+    op = H.lazytensor(dims, dims, [1, 2], [A1, A2])
+    assert Q.describe(op.q).count("dmma") == 2
+    H.check_mul(op, dims, dims, rng, tol=TOL, kinds=("ket", "opl"), nbatch=8, scalars=((1, 0), (1.5, 2.1)))
+    H.check_mul(op, dims, dims, rng, tol=TOL, kinds=("bra", "opr"), nbatch=3, scalars=((1, 0),))
+
+
+def test_apply_host_end_to_end(Q):
+    rng = np.random.default_rng(90)
+    dims, coefs, terms = _chain_terms(10, "heis", False, rng)
+    s = H.lazysum(dims, dims, coefs, terms)
+    x = H.rnd(rng, 1 << 10)
+    ref = H.ket(dims, np.zeros(1 << 10, dtype=complex))
+    O.mul(ref.o, s.o, H.ket(dims, x).o, 1.0, 0.0)
+    y = Q.apply_host(s.q, x)
+    assert H.rel_err(y, ref.o.data) <= TOL
