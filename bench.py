@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py — LazySum mul! throughput (amplitude-updates/s and HBM GB/s), BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+N = 1: BASELINE config 4 — Heisenberg spin chain N=28 (periodic, 84 LazyTensor terms with sparse sigma
+factors exactly as src/spin.jl builds them), LazySum mul! on a Ket of 2^28 ComplexF64 amplitudes (4 GiB).
+N > 1: BASELINE config 5 — the same chain at N=33 (99 terms) sharded over the ranks (one process per GPU,
+launched by torchrun), axis swaps over NCCL; if 4 slabs of 2^(33-p) amplitudes do not fit one GPU the largest
+chain that does is used and named in config.workload.
+
+One "step" = one complete mul!(y, H, x, alpha, 0).  One amplitude-update = one output amplitude of one
+complete mul! (all terms accumulated) — SURVEY.md §8(d).  Timing: CUDA events on the launching stream,
+barrier + synchronize on both sides, max over ranks; the 4 GiB+ operands exceed the 126 MB L2 so every step
+streams from HBM (no flush needed; stated in config).
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LazySum mul! amplitude-updates/s"
+UNIT = "amplitude-updates/s"
+
+
+def chain_spec(n, seed=2024):
+    """Heisenberg XYZ chain, periodic: 3N terms J^a_i sigma^a_i sigma^a_{i+1}; coefficients uniform[0.5,1.5)."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    spec = []
+    for i in range(1, n + 1):
+        j = i % n + 1
+        for a in range(3):
+            spec.append((float(rng.uniform(0.5, 1.5)), sorted([i, j]), a))
+    return spec
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+# --------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU algorithm for this workload: per-term passes through the pure-sparse recursion
+    (src/operators_lazysum.jl:189-200 -> src/operators_lazytensor.jl:652-685), restated in oracle/qob_oracle.c
+    (Julia is not installed in this image, so the reference itself cannot run: kind = "port").  The reference has
+    no threading on this path, so 1 thread is all it can use."""
+    if rank != 0:
+        return
+    import numpy as np
+    import scipy.sparse as sp
+
+    from oracle import qob_oracle as O
+
+    n = 28 if world == 1 else 33
+    nterms = 3 * n
+    total = args.steps + args.warmup
+    pa = [np.array([[0, 1], [1, 0]], dtype=complex), np.array([[0, -1j], [1j, 0]], dtype=complex),
+          np.array([[1, 0], [0, -1]], dtype=complex)]
+    # one step = ONE term of the sum applied to a 2^m-amplitude chain with the same bond structure; m is chosen from
+    # a quick calibration (one term at 2^20) so that the whole --steps/--warmup run stays within ~2 minutes
+    cal = (2,) * 20
+    lt = O.LazyTensor(cal, cal, [10, 11], [O.Op((2,), (2,), sp.csc_matrix(pa[0]))] * 2)
+    xc, yc = O.Ket(cal, O.fill_state(1 << 20, 1, 1e-3)), O.Ket(cal, np.zeros(1 << 20, dtype=complex))
+    t0 = time.perf_counter()
+    O.mul(yc, lt, xc, 1.0, 1.0)
+    per_amp = (time.perf_counter() - t0) / (1 << 20)
+    budget = 120.0 / max(total, 1)
+    m = min(28, n)
+    while m > 20 and per_amp * (1 << m) * 1.3 > budget:
+        m -= 1
+    dims = (2,) * m
+    spec = chain_spec(m)
+    x = O.Ket(dims, O.fill_state(1 << m, 7, 2.0 ** (-m / 2)))
+    y = O.Ket(dims, np.zeros(1 << m, dtype=complex))
+    times = []
+    for s in range(total):
+        c, idx, a = spec[(s * 7) % len(spec)]
+        op = [O.Op((2,), (2,), sp.csc_matrix(pa[a]))] * 2
+        lt = O.LazyTensor(dims, dims, idx, op)
+        t0 = time.perf_counter()
+        O.mul(y, lt, x, c, 1.0)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+    t_term = sum(times) / len(times)
+    # a complete mul! = nterms such passes; amplitude-updates/s is size-independent for this streaming algorithm
+    value = (1 << m) / (nterms * t_term)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * nterms * t_term * (2.0 ** (n - m)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Heisenberg XYZ spin-1/2 chain N={n} periodic, LazySum of {nterms} LazyTensor terms, mul! on Ket",
+                   "note": "ms_per_step extrapolated to the full workload from the timed sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{len(times)} single-term passes on a 2^{m}-amplitude state (of {nterms} terms on 2^{n}); "
+                                   f"{t_term:.3f} s/term; reference path has no threading"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(n, nterms, seconds=20.0):
+    """cpu_baseline leg of the default run: the oracle port timed on a bounded sample (rank 0, N=1 only)."""
+    import numpy as np
+    import scipy.sparse as sp
+
+    from oracle import qob_oracle as O
+
+    m = min(n, 26)
+    dims = (2,) * m
+    sx = sp.csc_matrix(np.array([[0, 1], [1, 0]], dtype=complex))
+    sz = sp.csc_matrix(np.array([[1, 0], [0, -1]], dtype=complex))
+    x = O.Ket(dims, O.fill_state(1 << m, 7, 2.0 ** (-m / 2)))
+    y = O.Ket(dims, np.zeros(1 << m, dtype=complex))
+    cases = [([1, 2], sx), ([m // 2, m // 2 + 1], sx), ([m - 1, m], sx), ([1, m], sz)]
+    times = []
+    t_start = time.perf_counter()
+    for idx, s in cases:
+        lt = O.LazyTensor(dims, dims, idx, [O.Op((2,), (2,), s)] * 2)
+        t0 = time.perf_counter()
+        O.mul(y, lt, x, 0.5, 1.0)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > seconds:
+            break
+    t_term = sum(times) / len(times)
+    return {"value": (1 << m) / (nterms * t_term), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{len(times)} single-term passes of the restated sparse recursion (operators_lazytensor.jl:652-685) "
+                      f"on a 2^{m}-amplitude state, {t_term:.3f} s/term, scaled by {nterms} terms per mul!"}
+
+
+# --------------------------------------------------------------------------------------- product arm
+def build_chain(Q, n):
+    b = Q.SpinBasis(0.5)
+    B = Q.tensor(*[b] * n)
+    sig = (Q.sigmax(b), Q.sigmay(b), Q.sigmaz(b))
+    terms, coefs = [], []
+    for c, idx, a in chain_spec(n):
+        terms.append(Q.LazyTensor(B, idx, (sig[a], sig[a])))
+        coefs.append(c)
+    return B, Q.LazySum(coefs, terms)
+
+
+def run_product(args, rank, world, local_rank):
+    import torch
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    import qob200 as Q
+
+    warmup = max(args.warmup, 3)
+    steps = args.steps
+    alpha = 0.5 - 1.0j
+    peak, peak_src = measured_peaks()
+
+    n = args.spins or 28
+    B, H = build_chain(Q, n)
+    nloc = n
+    x = Q.Ket(B)
+    Q.fill_state(x.data, 7, 2.0 ** (-n / 2))
+    y = Q.Ket(B)
+    plan = Q.describe(H)
+
+    def step():
+        Q.mul_(y, H, x, alpha, 0.0)
+    xs, ys = x.data, y.data
+    run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps, peak, peak_src, H, alpha)
+
+
+def run_product_dist(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    import qob200 as Q
+    from qob200.dist import ShardedLazySum
+
+    warmup = max(args.warmup, 3)
+    alpha = 0.5 - 1.0j
+    peak, peak_src = measured_peaks()
+    p = world.bit_length() - 1
+    free, _total = torch.cuda.mem_get_info()
+    n = args.spins or 33
+    while 4 * 16 * (1 << (n - p)) > 0.85 * free and n > 20:
+        n -= 1
+    nloc = n - p
+    B, H = build_chain(Q, n)
+    sh = ShardedLazySum(H, rank, world)
+    x = torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
+    Q.fill_state(x, 7, 2.0 ** (-n / 2), offset=rank << nloc)
+    y = torch.empty_like(x)
+    plan = sh.describe()
+
+    def step():
+        sh.mul_(y, x, alpha, 0.0)
+
+    run_common(args, Q, rank, world, step, x, y, n, nloc, plan, warmup, args.steps, peak, peak_src, H, alpha, sharded=sh)
+
+
+def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps, peak, peak_src, H, alpha, sharded=None):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    nterms = len(H.operators)
+    for _ in range(warmup):
+        step()
+    barrier()
+    # ---- timed region: exactly `steps` steps
+    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+    l0 = Q.launch_count()
+    Q.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    Q.profile_enable(False)
+    prof = Q.profile_read()
+    launches = Q.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    ms_step = ms_total / steps
+    amps = float(1 << n)
+    value = amps / (ms_step * 1e-3)
+
+    # ---- end-to-end through the public host-buffer API: pinned host -> device, mul!, device -> pinned host
+    e2e_steps = max(1, min(3, steps))
+    hx = torch.empty(1 << nloc, dtype=torch.complex128).pin_memory()
+    hy = torch.empty(1 << nloc, dtype=torch.complex128).pin_memory()
+    hx.copy_(xs)
+    torch.cuda.synchronize()
+    t_e2e = []
+    for i in range(e2e_steps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        if sharded is None:
+            Q.apply_host(H, hx.numpy(), alpha=alpha, beta=0.0, y=hy.numpy())
+        else:
+            xs.copy_(hx, non_blocking=True)
+            step()
+            hy.copy_(ys, non_blocking=True)
+        barrier()
+        if i > 0:
+            t_e2e.append(time.perf_counter() - t0)
+    e2e_s = sum(t_e2e) / len(t_e2e)
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    slab_bytes = 16 * (1 << nloc)
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (the tile-pass kernel), from the live per-launch CUDA-event times
+    tot_ms = sum(p[0] for p in prof)
+    tot_bytes = sum(p[2] for p in prof)
+    achieved = (tot_bytes / 1e9) / (tot_ms * 1e-3) if tot_ms > 0 else 0.0
+    by_pass = {}
+    for ms, pi, by in prof:
+        by_pass.setdefault(pi, []).append((ms, by))
+    passes = [{"pass": k, "ms": sum(m for m, _ in v) / len(v), "GBps": (v[0][1] / 1e9) / (sum(m for m, _ in v) / len(v) * 1e-3)}
+              for k, v in sorted(by_pass.items())]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "qtile_kernel (all tile passes of the fused LazySum)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": tot_bytes / max(len(prof), 1),
+                "kernel_share_of_step": tot_ms / ms_total if ms_total > 0 else None, "per_pass": passes,
+                "whole_mul_GBps_at_32B_per_amplitude": 32.0 * (1 << nloc) / 1e9 / (ms_step * 1e-3),
+                "whole_mul_frac_of_peak": 32.0 * (1 << nloc) / 1e9 / (ms_step * 1e-3) / peak}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Heisenberg XYZ spin-1/2 chain N={n} periodic, LazySum of {nterms} LazyTensor terms "
+                               f"(sparse sigma factors), mul!(y,H,x,alpha,0) on Ket of 2^{n} ComplexF64",
+                   "state_bytes": 16 * (1 << n), "l2": "operands (>= 4 GiB per GPU) exceed the 126 MB L2; no flush needed",
+                   "plan": plan, "parallelism": "single GPU" if world == 1 else f"state sharded on top {world.bit_length() - 1} axes, NCCL all-to-all axis swap"},
+        "term_updates_per_s": value * nterms,
+        "hbm_GBps_algorithmic": 32.0 * (1 << nloc) / 1e9 / (ms_step * 1e-3),
+        "clocks": clocks,
+        "e2e": {"value": amps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": slab_bytes * world, "d2h_bytes_per_step": slab_bytes * world,
+                "ms_per_step": 1e3 * e2e_s, "steps": len(t_e2e)},
+        "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample(n, nterms)
+    else:
+        line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "reported at N=1 only"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="qob200", choices=["qob200", "reference"])
+    ap.add_argument("--spins", type=int, default=0, help="override the chain length (testing)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world if world > 1 else args.gpus)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        try:
+            run_product_dist(args, rank, world, local_rank)
+        finally:
+            dist.destroy_process_group()
+    else:
+        if args.gpus > 1:
+            print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun (WORLD_SIZE={world})"}))
+            sys.exit(2)
+        run_product(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

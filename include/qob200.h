@@ -133,6 +133,13 @@ int qob_op_apply_host(qob_op *op, int32_t side, qob_c64 alpha, const qob_c64 *x,
 int64_t qob_launch_count(void);
 int qob_op_describe(qob_op *op, int32_t side, int64_t batch, char *buf, int64_t buflen);
 
+/* Per-kernel timing for the roofline report: while enabled, every tile-pass launch is bracketed by
+ * CUDA events on the launching stream.  qob_profile_read synchronises those events and returns, in
+ * launch order, the duration (ms), the pass index and the algorithmic bytes (32 B/amplitude for a
+ * pass that only writes y, 48 B/amplitude for a read-modify-write pass) of each launch, then clears. */
+int qob_profile_enable(int32_t on);
+int qob_profile_read(int32_t max_entries, float *ms, int32_t *pass_index, double *alg_bytes, int32_t *count);
+
 /* Counter-based synthetic input generator shared with the oracle (oracle/qob_oracle.c:orc_fill_state):
  * x[i] = scale * (u(seed, 2i), u(seed, 2i+1)), u uniform in [-1, 1) from splitmix64. */
 int qob_fill_state(void *x, int64_t offset, int64_t n, uint64_t seed, double scale, void *stream);

@@ -10,7 +10,7 @@ from ._lib import (ArgumentError, CudaError, DimensionMismatch, IncompatibleBase
 from .operators import (Adjoint, Basis, Bra, CompositeBasis, DenseOperator, Eye, FockBasis, GenericBasis, Ket,
                         LazyProduct, LazySum, LazyTensor, NLevelBasis, Operator, SparseOperator, SpinBasis,
                         apply_host, create, dagger, dense, describe, destroy, dot, fill_state, handle,
-                        identityoperator, launch_count, mul_, norm2, number, randstate, sigmam, sigmap, sigmax,
+                        identityoperator, launch_count, mul_, norm2, number, profile_enable, profile_read, randstate, sigmam, sigmap, sigmax,
                         sigmay, sigmaz, sparse, tensor, transition)
 
 mul = mul_  # `mul!`

@@ -101,6 +101,8 @@ _sigs = {
     "qob_fill_state": (C.c_int, [_vp, _i64, _i64, C.c_uint64, C.c_double, _vp]),
     "qob_norm2": (C.c_int, [_vp, _i64, C.POINTER(C.c_double), _vp]),
     "qob_dot": (C.c_int, [_vp, _vp, _i64, C.POINTER(c64), _vp]),
+    "qob_profile_enable": (C.c_int, [_i32]),
+    "qob_profile_read": (C.c_int, [_i32, C.POINTER(C.c_float), C.POINTER(_i32), C.POINTER(C.c_double), C.POINTER(_i32)]),
     "qob_lazysum_term_masks": (C.c_int, [_vp, _i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "qob_layout_plan_create": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.c_uint64, C.POINTER(C.c_uint8), C.POINTER(_i32)]),
     "qob_layout_plan_apply": (C.c_int, [_vp, _i32, c64, _vp, c64, _vp, _vp]),

@@ -15,5 +15,5 @@ for f in qob_api qob_kernels_gather qob_kernels_qtile qob_kernels_axis; do
   OBJS+=("$HERE/../build/$f.o")
 done
 wait
-"$NVCC" -shared -cudart static "${OBJS[@]}" -o "$OUT"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart static "${OBJS[@]}" -o "$OUT"
 echo "built $OUT"

@@ -420,10 +420,52 @@ static int launch_pass(const QTileProgramHost &h, const QPassHost &p, const QPas
   return QOB_STATUS_OK;
 }
 
+// ---- optional per-launch event timing (qob_profile_enable / qob_profile_read)
+struct ProfEntry {
+  cudaEvent_t a, b;
+  int pass;
+  double bytes;
+};
+static bool g_prof_on = false;
+static std::vector<ProfEntry> g_prof;
+extern "C" int qob_profile_enable(int32_t on) {
+  g_prof_on = on != 0;
+  return QOB_STATUS_OK;
+}
+extern "C" int qob_profile_read(int32_t max_entries, float *ms, int32_t *pass_index, double *alg_bytes, int32_t *count) {
+  int n = 0;
+  for (ProfEntry &e : g_prof) {
+    cudaEventSynchronize(e.b);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e.a, e.b);
+    if (n < max_entries) {
+      if (ms) ms[n] = t;
+      if (pass_index) pass_index[n] = e.pass;
+      if (alg_bytes) alg_bytes[n] = e.bytes;
+      ++n;
+    }
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  g_prof.clear();
+  if (count) *count = n;
+  return QOB_STATUS_OK;
+}
+
 int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s) {
   const QTileProgramHost &h = *prog.h;
   bool first = true;
+  int pass_no = 0;
   for (auto &pp : h.passes) {
+    ProfEntry pe;
+    if (g_prof_on) {
+      cudaEventCreate(&pe.a);
+      cudaEventCreate(&pe.b);
+      pe.pass = pass_no;
+      pe.bytes = (double)(1ull << h.nbits) * ((first && beta == cplx(0.0, 0.0)) ? 32.0 : 48.0);
+      cudaEventRecord(pe.a, s);
+    }
+    ++pass_no;
     QPassParams P = pp->params;
     P.alpha = make_double2(alpha.real(), alpha.imag());
     P.beta = make_double2(beta.real(), beta.imag());
@@ -435,6 +477,10 @@ int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta,
       case 12: QOB_TRY((launch_pass<12, 256, 3>(h, *pp, P, x, y, s))); break;
       case 13: QOB_TRY((launch_pass<13, 512, 1>(h, *pp, P, x, y, s))); break;
       default: QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: unsupported tile size %d", h.T);
+    }
+    if (g_prof_on) {
+      cudaEventRecord(pe.b, s);
+      g_prof.push_back(pe);
     }
   }
   return QOB_STATUS_OK;

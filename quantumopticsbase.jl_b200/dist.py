@@ -96,6 +96,8 @@ class ShardedLazySum:
         pos = (C.c_int32 * self.n)(*range(self.n))
         _lib.check(lib.qob_layout_plan_create(self.h, self.nloc, pos, C.c_uint64(rank), local_sel, C.byref(pid)))
         self.plan_local = pid.value
+        # what each plan means (layout + selected terms); used by describe() and by the CPU emulation in tests
+        self.plan_info = {self.plan_local: dict(bitpos=list(range(self.n)), hi_value=rank, select=[bool(v) for v in local_sel][:nterms])}
         self.plan_swapped = None
         self.swap_lo = None
         if self.n_remote:
@@ -104,6 +106,7 @@ class ShardedLazySum:
             pos2 = (C.c_int32 * self.n)(*sp)
             _lib.check(lib.qob_layout_plan_create(self.h, self.nloc, pos2, C.c_uint64(rank), remote_sel, C.byref(pid)))
             self.plan_swapped = pid.value
+            self.plan_info[self.plan_swapped] = dict(bitpos=sp, hi_value=rank, select=[bool(v) for v in remote_sel][:nterms])
         self._buf = None
 
     def describe(self):

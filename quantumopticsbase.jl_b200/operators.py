@@ -708,3 +708,17 @@ def dot(x, y):
 
 def launch_count():
     return int(lib.qob_launch_count())
+
+
+def profile_enable(on=True):
+    _lib.check(lib.qob_profile_enable(1 if on else 0))
+
+
+def profile_read(max_entries=4096):
+    """[(ms, pass_index, algorithmic_bytes)] of every tile-pass launch since profile_enable, in launch order."""
+    ms = (C.c_float * max_entries)()
+    pi = (C.c_int32 * max_entries)()
+    by = (C.c_double * max_entries)()
+    n = C.c_int32()
+    _lib.check(lib.qob_profile_read(max_entries, ms, pi, by, C.byref(n)))
+    return [(float(ms[i]), int(pi[i]), float(by[i])) for i in range(n.value)]

@@ -1,0 +1,200 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/qob200.h declares, fails loudly
+without a GPU (no CPU fallback), validates constructor arguments like the reference, and its planner produces
+the expected pass structure.  No compute calls are made here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def Q():
+    import qob200
+
+    return qob200
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "qob200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qob_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_header_symbol_is_exported(Q):
+    lib = ctypes.CDLL(Q.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/qob200.h but not exported by libqob200.so"
+    assert set(names) == set(Q.EXPORTED), set(names) ^ set(Q.EXPORTED)
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+
+    import qob200
+
+    out = subprocess.run(["cuobjdump", "--list-elf", qob200.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback(Q):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the GPU-less container")
+    h = ctypes.c_void_p()
+    st = Q.lib.qob_ctx_create(0, ctypes.byref(h))
+    assert st == 5 and b"no CPU fallback" in Q.lib.qob_last_error()
+    with pytest.raises(Q.CudaError):
+        Q.context()
+    with pytest.raises(Q.CudaError):
+        Q.Ket(Q.GenericBasis(4))
+    # a planning-only context can build and describe plans but never computes
+    ctx = Q.context(-1)
+    b = Q.SpinBasis(0.5)
+    B = Q.tensor(*[b] * 20)
+    op = Q.LazySum([1.0], [Q.LazyTensor(B, [3, 4], (Q.sigmax(b), Q.sigmax(b)))])
+    hnd = Q.handle(op, ctx)
+    st = Q.lib.qob_op_apply(hnd, 0, Q._lib.c64.of(1), ctypes.c_void_p(4096), Q._lib.c64.of(0), ctypes.c_void_p(1 << 40), 1, None)
+    assert st == 5 and b"no CPU fallback" in Q.lib.qob_last_error()
+
+
+def test_status_strings(Q):
+    assert Q.lib.qob_status_string(0) == b"ok"
+    assert Q.lib.qob_status_string(1) == b"DimensionMismatch"
+    assert Q.lib.qob_version() >= 100
+
+
+def chain(Q, n, kind="heis"):
+    b = Q.SpinBasis(0.5)
+    B = Q.tensor(*[b] * n)
+    sig = (Q.sigmax(b), Q.sigmay(b), Q.sigmaz(b))
+    terms = []
+    for i in range(1, n + 1):
+        j = i % n + 1
+        idx = sorted([i, j])
+        if kind == "heis":
+            terms += [Q.LazyTensor(B, idx, (s, s)) for s in sig]
+        else:
+            terms += [Q.LazyTensor(B, [i], (sig[0],)), Q.LazyTensor(B, idx, (sig[2], sig[2]))]
+    return B, Q.LazySum([1.0] * len(terms), terms)
+
+
+def test_planner_pass_structure(Q):
+    """N=28 Heisenberg chain: 28 bonds need 3 tile passes at T=12/L=3 (11 + 8 + 8 + wrap), 28 distinct flip masks."""
+    ctx = Q.context(-1)
+    _, Hs = chain(Q, 28)
+    d = Q.describe(Hs, ctx=ctx)
+    assert "qtile[bits=28,T=12,L=3,passes=3,components=56]" in d, d
+    assert "{free:0-11" in d and "free:0-2,11-19" in d and "free:0-2,19-27" in d
+    _, Ht = chain(Q, 12, "tfim")
+    assert "gather[terms=24,maxfac=2]" in Q.describe(Ht, ctx=ctx)
+    # density-matrix apply: 2N index bits, left terms on the low N, right terms (transposed) on the high N
+    _, Hd = chain(Q, 10)
+    assert "qtile[bits=20" in Q.describe(Hd, "left", 1 << 10, ctx=ctx)
+    assert "qtile[bits=20" in Q.describe(Hd, "right", 1 << 10, ctx=ctx)
+    assert "gather" in Q.describe(Hd, "left", 3, ctx=ctx)  # non power-of-two batch -> generic kernel
+
+
+def test_planner_routes_dense_factors_to_dmma(Q):
+    ctx = Q.context(-1)
+    f1, f2, f3 = Q.FockBasis(47), Q.FockBasis(47), Q.NLevelBasis(3)
+    B = Q.tensor(f1, f2, f3)
+    rng = np.random.default_rng(0)
+    A1, A2 = Q.Operator(f1, f1, H.rnd(rng, 48, 48)), Q.Operator(f2, f2, H.rnd(rng, 48, 48))
+    op = Q.LazyTensor(B, [1, 2], (A1, A2))
+    d = Q.describe(op, "left", 4096, ctx=ctx)
+    assert d.count("dmma") == 2, d
+    # sparse site operators of the same size stay on the fused gather kernel
+    op2 = Q.LazyTensor(B, [1, 2], (Q.destroy(f1), Q.create(f2)))
+    assert "gather" in Q.describe(op2, ctx=ctx)
+
+
+def test_constructor_validation_mirrors_reference(Q):
+    ctx = Q.context(-1)
+    b2, b3 = Q.GenericBasis(2), Q.GenericBasis(3)
+    B = Q.CompositeBasis([b2, b3])
+    a2, a3 = Q.Operator(b2, b2, np.eye(2)), Q.Operator(b3, b3, np.eye(3))
+    with pytest.raises(AssertionError):
+        Q.LazyTensor(B, [2, 1], (a3, a2))            # issorted(indices), operators_lazytensor.jl:26
+    with pytest.raises(AssertionError):
+        Q.LazyTensor(B, [1], (a3,))                  # basis of the site operator, :30-31
+    with pytest.raises(Q.ArgumentError):
+        Q.LazyTensor(B, [3], (a3,))                  # check_indices
+    with pytest.raises(Q.ArgumentError):
+        Q.LazySum([1.0, 2.0], [Q.LazyTensor(B, [1], (a2,))])   # operators_lazysum.jl:46
+    with pytest.raises(Q.IncompatibleBases):
+        Q.LazySum(B, B, [1.0], [Q.LazyTensor(Q.CompositeBasis([b3, b2]), [1], (a3,))])
+    with pytest.raises(Q.IncompatibleBases):
+        Q.LazyProduct(Q.LazyTensor(B, [1], (a2,)), Q.LazyTensor(Q.CompositeBasis([b3, b2]), [1], (a3,)))
+    with pytest.raises(Q.ArgumentError):
+        Q.LazyProduct()
+    with pytest.raises(Q.DimensionMismatch):
+        Q.Operator(b2, b3, np.zeros((3, 2)))        # operators_dense.jl:16-17
+    # the C ABI validates on its own as well (a Julia caller bypasses the python mirror)
+    dl = (ctypes.c_int64 * 2)(2, 3)
+    sites = (ctypes.c_int32 * 2)(2, 1)
+    keep = []
+    facs = (Q._lib.Factor * 2)(Q.operators._factor_struct(a3.data, keep), Q.operators._factor_struct(a2.data, keep))
+    out = ctypes.c_void_p()
+    st = Q.lib.qob_lazytensor_create(ctx, 2, dl, dl, 2, sites, facs, Q._lib.c64.of(1), ctypes.byref(out))
+    assert st == 3 and b"sorted" in Q.lib.qob_last_error()
+    sites = (ctypes.c_int32 * 1)(1)
+    facs = (Q._lib.Factor * 1)(Q.operators._factor_struct(a3.data, keep))
+    st = Q.lib.qob_lazytensor_create(ctx, 2, dl, dl, 1, sites, facs, Q._lib.c64.of(1), ctypes.byref(out))
+    assert st == 3
+    # unsupported factor type -> MethodError (test_operators_lazytensor.jl:409-415)
+    class Weird(Q.operators.AbstractOperator):
+        basis_l = basis_r = b2
+    with pytest.raises(Q.MethodError):
+        Q.handle(Q.LazyTensor(B, [1], (Weird(),)), ctx)
+    # sparse x sparse is "not implemented" in the reference (sparsematrix.jl:177-188): no method here either
+    with pytest.raises(Q.MethodError):
+        Q.mul_(Q.Operator(b2, b2, sp.eye(2)), Q.Operator(b2, b2, sp.eye(2)), Q.Operator(b2, b2, sp.eye(2)))
+
+
+def test_lazysum_dimension_check_in_c_abi(Q):
+    ctx = Q.context(-1)
+    b2, b3 = Q.GenericBasis(2), Q.GenericBasis(3)
+    t = Q.LazyTensor(Q.CompositeBasis([b2, b3]), [1], (Q.Operator(b2, b2, np.eye(2)),))
+    h = Q.handle(t, ctx)
+    arr = (ctypes.c_void_p * 1)(h.value)
+    cf = (Q._lib.c64 * 1)(Q._lib.c64.of(1))
+    out = ctypes.c_void_p()
+    assert Q.lib.qob_lazysum_create(ctx, 5, 5, 1, cf, arr, ctypes.byref(out)) == 1
+    assert Q.lib.qob_lazysum_create(ctx, 6, 6, 1, cf, arr, ctypes.byref(out)) == 0
+    assert Q.lib.qob_lazysum_set_coefs(out, 2, cf) == 3
+    dl, dr = ctypes.c_int64(), ctypes.c_int64()
+    assert Q.lib.qob_op_dims(out, ctypes.byref(dl), ctypes.byref(dr)) == 0 and (dl.value, dr.value) == (6, 6)
+    Q.lib.qob_op_destroy(out)
+
+
+def test_layout_plans_and_term_masks(Q):
+    """host logic of the sharded apply: which terms are local, where the swap window goes"""
+    from qob200.dist import ShardedLazySum, swap_window, swapped_bitpos
+
+    ctx = Q.context(-1)
+    n = 24
+    _, Hs = chain(Q, n)
+    h = Q.handle(Hs, ctx)
+    od, al = ctypes.c_uint64(), ctypes.c_uint64()
+    Q._lib.check(Q.lib.qob_lazysum_term_masks(h, 0, ctypes.byref(od), ctypes.byref(al)))   # sx sx on sites 1,2
+    assert (od.value, al.value) == (0b11, 0b11)
+    Q._lib.check(Q.lib.qob_lazysum_term_masks(h, 2, ctypes.byref(od), ctypes.byref(al)))   # sz sz on sites 1,2
+    assert (od.value, al.value) == (0, 0b11)
+    sh = ShardedLazySum(Hs, rank=5, world=8, ctx=ctx)
+    # bonds (21,22),(22,23),(23,24),(24,1) have sigma_x/sigma_y on sharded bits 21..23 (0-based) -> 4 bonds x 2 terms
+    assert sh.n_remote == 8 and sh.n_local == 3 * n - 8
+    assert sh.swap_lo == 17 and swap_window(21, 3, (1 << 20) | 1) == 17
+    assert swapped_bitpos(24, 21, 3, 17) == list(range(17)) + [21, 22, 23, 20, 17, 18, 19]
+    d = sh.describe()
+    assert "local[64 terms]" in d and "swapped[8 terms, window bit 17]" in d
