@@ -299,9 +299,9 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
     value = amps / (ms_step * 1e-3)
 
     # ---- end-to-end through the public host-buffer API: pinned host -> device, mul!, device -> pinned host
-    e2e_steps = max(1, min(3, steps))
-    hx = torch.empty(1 << nloc, dtype=torch.complex128).pin_memory()
-    hy = torch.empty(1 << nloc, dtype=torch.complex128).pin_memory()
+    e2e_steps = max(1, min(3, steps)) if world == 1 else 1
+    hx = torch.empty(1 << nloc, dtype=torch.complex128, pin_memory=True)
+    hy = torch.empty(1 << nloc, dtype=torch.complex128, pin_memory=True)
     hx.copy_(xs)
     torch.cuda.synchronize()
     t_e2e = []

@@ -1,0 +1,190 @@
+#!/usr/bin/env python
+"""bench_configs.py — secondary measurements for BASELINE configs 1-3 (the headline, config 4/5, is bench.py).
+
+Prints one JSON line per config: device time per mul! (CUDA events, warm, on torch's current stream = the launching
+stream), the derived throughput against the roofline that bounds it, and the oracle's CPU time on the same inputs
+(restated reference algorithm, see oracle/).  Run on a B200:  python bench_configs.py [--out profiles/configs_rNN.jsonl]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def rnd(rng, *shape):
+    return rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)
+
+
+def gpu_time(fn, iters, warm=5):
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters  # ms
+
+
+def cpu_time(fn, reps=3):
+    fn()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    return sorted(ts)[len(ts) // 2] * 1e3
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm = json.load(open(p))["hbm_gbs"] if os.path.exists(p) else 6650.0
+    return hbm
+
+
+def config1(Q, O, out):
+    """TFIM N=12: LazySum of 2N embedded terms on a random Ket (launch-latency bound: 64 KiB state)."""
+    n = 12
+    rng = np.random.default_rng(1)
+    b = Q.SpinBasis(0.5)
+    B = Q.tensor(*[b] * n)
+    dims = (2,) * n
+    sx = np.array([[0, 1], [1, 0]], dtype=complex)
+    sz = np.array([[1, 0], [0, -1]], dtype=complex)
+    qt, ot, cf = [], [], []
+    for i in range(1, n + 1):
+        j = i % n + 1
+        qt.append(Q.LazyTensor(B, [i], (Q.sigmax(b),)))
+        ot.append(O.LazyTensor(dims, dims, [i], [O.Op((2,), (2,), sp.csc_matrix(sx))]))
+        cf.append(-rng.uniform(0.5, 1.5))
+        qt.append(Q.LazyTensor(B, sorted([i, j]), (Q.sigmaz(b), Q.sigmaz(b))))
+        ot.append(O.LazyTensor(dims, dims, sorted([i, j]), [O.Op((2,), (2,), sp.csc_matrix(sz))] * 2))
+        cf.append(-rng.uniform(0.5, 1.5))
+    Hq, Ho = Q.LazySum(cf, qt), O.LazySum(dims, dims, cf, ot)
+    xh = rnd(rng, 1 << n)
+    x, y = Q.Ket(B, xh), Q.Ket(B)
+    ms = gpu_time(lambda: Q.mul_(y, Hq, x, -1j, 0.0), 500)
+    xo, yo = O.Ket(dims, xh), O.Ket(dims, np.zeros(1 << n, dtype=complex))
+    cms = cpu_time(lambda: O.mul(yo, Ho, xo, -1j, 0.0))
+    err = np.linalg.norm(y.to_host() - yo.data) / np.linalg.norm(yo.data)
+    out({"config": "1: TFIM N=12, LazySum of 24 terms, mul! on Ket", "plan": Q.describe(Hq), "us_per_mul": ms * 1e3,
+         "amplitude_updates_per_s": (1 << n) / (ms * 1e-3), "bound": "launch latency (64 KiB state, one fused launch)",
+         "cpu_ms_oracle_1thread": cms, "speedup_vs_cpu_port": cms / ms, "rel_err_vs_oracle": err})
+
+
+def config2(Q, O, out, cutoffs=(64, 256, 1024, 4096)):
+    """Jaynes-Cummings: SparseOperator H x DenseOperator rho, mul!(drho,H,rho,-i,0) then mul!(drho,rho,H,i,1)."""
+    hbm = peaks()
+    for nc in cutoffs:
+        nf = nc + 1
+        a = O.destroy(nc).data
+        ad = O.create(nc).data
+        num = O.number(nc).data
+        sz, spl, smi = O.sigmaz().data, O.sigmap().data, O.sigmam().data
+        i2, inf = sp.identity(2, format="csc"), sp.identity(nf, format="csc")
+        Hm = (1.0 * sp.kron(i2, num) + 0.45 * sp.kron(sz, inf) + 0.1 * (sp.kron(spl, a) + sp.kron(smi, ad))).tocsc()
+        D = 2 * nf
+        bas = Q.CompositeBasis([Q.FockBasis(nc), Q.SpinBasis(0.5)])
+        Hq = Q.Operator(bas, bas, Hm)
+        rng = np.random.default_rng(2)
+        import torch
+
+        rho = Q.DenseOperator(bas, bas, torch.randn(D, D, dtype=torch.complex128, device="cuda").t())
+        drho = Q.DenseOperator(bas, bas, torch.zeros(D, D, dtype=torch.complex128, device="cuda").t())
+
+        def step():
+            Q.mul_(drho, Hq, rho, -1j, 0.0)
+            Q.mul_(drho, rho, Hq, 1j, 1.0)
+        ms = gpu_time(step, 200 if D < 3000 else 20)
+        alg = 16.0 * D * D * (2 + 3) + 2 * Hm.nnz * 24
+        rec = {"config": f"2: Jaynes-Cummings Fock({nc}) x spin-1/2, dim {D}, H nnz={Hm.nnz}: -i[H,rho] as two sparse gemm!",
+               "us_per_commutator": ms * 1e3, "algorithmic_GB": alg / 1e9, "GBps": alg / 1e9 / (ms * 1e-3),
+               "frac_of_measured_hbm": alg / 1e9 / (ms * 1e-3) / hbm,
+               "bound": "launch latency" if D < 1000 else "HBM"}
+        if D <= 520:
+            rh = np.asfortranarray(rho.to_host())
+            so, ro = O.Op((nf, 2), (nf, 2), rh), O.Op((nf, 2), (nf, 2), np.zeros((D, D), dtype=complex))
+            Ho = O.Op((nf, 2), (nf, 2), Hm)
+
+            def cstep():
+                O.mul(ro, Ho, so, -1j, 0.0)
+                O.mul(ro, so, Ho, 1j, 1.0)
+            rec["cpu_ms_oracle_1thread"] = cpu_time(cstep)
+            rec["speedup_vs_cpu_port"] = rec["cpu_ms_oracle_1thread"] / ms
+            rec["rel_err_vs_oracle"] = float(np.linalg.norm(drho.to_host() - ro.data) / np.linalg.norm(ro.data))
+        out(rec)
+
+
+def config3(Q, O, out, batch=4096):
+    """Two-mode Fock(47) x Fock(47) x NLevel(3): LazyTensor with two dense d=48 factors on a Ket batch (DMMA path)."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    f1, f2, f3 = Q.FockBasis(47), Q.FockBasis(47), Q.NLevelBasis(3)
+    B = Q.tensor(f1, f2, f3)
+    A1, A2 = rnd(rng, 48, 48) / 7, rnd(rng, 48, 48) / 7
+    op = Q.LazyTensor(B, [1, 2], (Q.Operator(f1, f1, A1), Q.Operator(f2, f2, A2)))
+    D = 48 * 48 * 3
+    bb = Q.GenericBasis(batch)
+    X = Q.DenseOperator(B, bb, torch.randn(batch, D, dtype=torch.complex128, device="cuda").t())
+    Y = Q.DenseOperator(B, bb, torch.zeros(batch, D, dtype=torch.complex128, device="cuda").t())
+    ms = gpu_time(lambda: Q.mul_(Y, op, X, 1.0, 0.0), 20)
+    flops = 8.0 * (48 + 48) * D * batch
+    alg = 32.0 * D * batch
+    rec = {"config": f"3: dims (48,48,3), LazyTensor with two dense 48x48 factors, Ket batch {batch} ({16 * D * batch / 2**20:.0f} MiB)",
+           "plan": Q.describe(op, "left", batch), "ms_per_mul": ms, "fp64_TFLOPs": flops / 1e12 / (ms * 1e-3),
+           "frac_of_fp64_peak_40TF": flops / 1e12 / (ms * 1e-3) / 40.0, "algorithmic_GBps": alg / 1e9 / (ms * 1e-3),
+           "amplitude_updates_per_s": D * batch / (ms * 1e-3), "bound": "FP64 tensor (DMMA): 24 flop/B > ridge"}
+    # CPU: the reference's dense-factor path (zgemm + permutes, all host cores through OpenBLAS) on a batch sample
+    sb = 128
+    dims = (48, 48, 3)
+    lt = O.LazyTensor(dims, dims, [1, 2], [O.Op((48,), (48,), A1), O.Op((48,), (48,), A2)])
+    xs = np.asfortranarray(X.data[:, :sb].cpu().numpy())
+    xo, yo = O.Op(dims, (sb,), xs), O.Op(dims, (sb,), np.zeros((D, sb), dtype=complex))
+    cms = cpu_time(lambda: O.mul(yo, lt, xo, 1.0, 0.0))
+    rec["cpu_ms_oracle_numpy_openblas"] = cms * batch / sb
+    rec["cpu_sample"] = f"batch {sb} of {batch}, scaled; threads = {os.cpu_count()} (OpenBLAS)"
+    rec["speedup_vs_cpu_port"] = rec["cpu_ms_oracle_numpy_openblas"] / ms
+    rec["rel_err_vs_oracle"] = float(np.linalg.norm(Y.data[:, :sb].cpu().numpy() - yo.data) / np.linalg.norm(yo.data))
+    out(rec)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="")
+    ap.add_argument("--configs", default="1,2,3")
+    args = ap.parse_args()
+    import qob200 as Q
+    from oracle import qob_oracle as O
+
+    lines = []
+
+    def out(rec):
+        print(json.dumps(rec), flush=True)
+        lines.append(rec)
+    todo = args.configs.split(",")
+    if "1" in todo:
+        config1(Q, O, out)
+    if "2" in todo:
+        config2(Q, O, out)
+    if "3" in todo:
+        config3(Q, O, out)
+    if args.out:
+        with open(args.out, "w") as f:
+            for r in lines:
+                f.write(json.dumps(r) + "\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,214 @@
+# QOB200.jl — thin Julia glue that makes libqob200.so a drop-in for QuantumOpticsBase's `mul!` hot path.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: neither this image nor the GPU boxes have a Julia toolchain
+# (SURVEY.md "Three facts", §8b).  It is written to the reference's method table so that a maintainer can
+# load it next to QuantumOpticsBase + CUDA.jl; the same C ABI is exercised from Python (ctypes) by tests/.
+#
+# What it does
+#   * device-resident states: `Ket{B,<:CuVector{ComplexF64}}`, `Operator{BL,BR,<:CuMatrix{ComplexF64}}`
+#     (made by `Adapt.adapt(CuArray, x)`, reference src/states.jl:315-316, src/operators_dense.jl:47);
+#   * operator definitions (LazyTensor / LazySum / LazyProduct / SparseOperator / dense site operators) stay
+#     host objects; the first `mul!` compiles them into a libqob200 handle cached by `objectid(op)`;
+#   * `mul!(result, op, state, alpha, beta)` methods with the SAME signatures as
+#     src/operators_lazytensor.jl:539-609, src/operators_lazysum.jl:189-238,
+#     src/operators_lazyproduct.jl:103-163, src/operators_sparse.jl:199-202 forward to `qob_op_apply`.
+module QOB200
+
+using LinearAlgebra, SparseArrays
+import LinearAlgebra: mul!
+using CUDA
+using FillArrays: Eye
+using QuantumOpticsBase
+using QuantumOpticsBase: Ket, Bra, Operator, LazyTensor, LazySum, LazyProduct, DataOperator, AbstractOperator,
+                         Basis, CompositeBasis, IncompatibleBases
+
+const libqob200 = get(ENV, "LIBQOB200", joinpath(@__DIR__, "..", "quantumopticsbase.jl_b200", "libqob200.so"))
+
+struct C64
+    re::Float64
+    im::Float64
+end
+C64(z::Number) = (c = ComplexF64(z); C64(real(c), imag(c)))   # Bool/Int/Float/Complex are all promoted
+
+# qob_factor (include/qob200.h)
+struct QobFactor
+    kind::Int32
+    trans::Int32
+    nrows::Int64
+    ncols::Int64
+    dense::Ptr{ComplexF64}
+    colptr::Ptr{Int64}
+    rowval::Ptr{Int64}
+    nzval::Ptr{ComplexF64}
+end
+const FACTOR_DENSE, FACTOR_CSC, FACTOR_EYE = Int32(0), Int32(1), Int32(2)
+const OP_N, OP_T, OP_C = Int32(0), Int32(1), Int32(2)
+const SIDE_LEFT, SIDE_RIGHT = Int32(0), Int32(1)
+
+function check(status::Integer)
+    status == 0 && return nothing
+    msg = unsafe_string(ccall((:qob_last_error, libqob200), Cstring, ()))
+    status == 1 && throw(DimensionMismatch(msg))
+    (status == 2 || status == 3) && throw(ArgumentError(msg))
+    status == 4 && throw(MethodError(mul!, ()))           # unsupported factor / operand types
+    error("libqob200 (status $status): $msg")
+end
+
+# ---------------------------------------------------------------- context (one per device)
+const CONTEXTS = Dict{Int,Ptr{Cvoid}}()
+function context()
+    dev = Int(CUDA.deviceid(CUDA.device()))
+    get!(CONTEXTS, dev) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:qob_ctx_create, libqob200), Cint, (Cint, Ref{Ptr{Cvoid}}), dev, h))
+        h[]
+    end
+end
+
+# the reference's cache controls (src/operators_lazytensor.jl:241-279) map onto the scratch pool
+lazytensor_cachesize() = (b = Ref{Int64}(0); check(ccall((:qob_ctx_scratch_bytes, libqob200), Cint, (Ptr{Cvoid}, Ref{Int64}), context(), b)); b[])
+lazytensor_clear_cache() = check(ccall((:qob_ctx_clear_scratch, libqob200), Cint, (Ptr{Cvoid},), context()))
+
+# ---------------------------------------------------------------- factors
+# returns (QobFactor, objects that must stay alive during the ccall)
+function factor(d::Matrix{ComplexF64}, trans=OP_N)
+    QobFactor(FACTOR_DENSE, trans, size(d, 1), size(d, 2), pointer(d), C_NULL, C_NULL, C_NULL), (d,)
+end
+factor(d::AbstractMatrix{<:Number}, trans=OP_N) = factor(Matrix{ComplexF64}(d), trans)
+function factor(d::SparseMatrixCSC, trans=OP_N)
+    m = SparseMatrixCSC{ComplexF64,Int64}(d)
+    QobFactor(FACTOR_CSC, trans, size(m, 1), size(m, 2), C_NULL, pointer(m.colptr), pointer(m.rowval), pointer(m.nzval)), (m,)
+end
+factor(d::Eye, trans=OP_N) = (QobFactor(FACTOR_EYE, trans, size(d, 1), size(d, 2), C_NULL, C_NULL, C_NULL, C_NULL), ())
+factor(d::Adjoint, trans=OP_N) = factor(parent(d), trans == OP_N ? OP_C : error("nested adjoint"))
+factor(d::Transpose, trans=OP_N) = factor(parent(d), trans == OP_N ? OP_T : error("nested transpose"))
+
+# ---------------------------------------------------------------- handles, cached per operator object
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    children::Vector{Any}
+    function Handle(p, children=Any[])
+        h = new(p, children)
+        finalizer(x -> ccall((:qob_op_destroy, libqob200), Cint, (Ptr{Cvoid},), x.ptr), h)
+        h
+    end
+end
+const HANDLES = IdDict{Any,Handle}()
+
+shape(b::CompositeBasis) = Int64[length(x) for x in b.bases]
+shape(b::Basis) = Int64[length(b)]
+
+function handle(op::LazyTensor)
+    get!(HANDLES, op) do
+        facs = QobFactor[]
+        keep = Any[]
+        for o in op.operators
+            o isa DataOperator || throw(MethodError(mul!, (op,)))
+            f, k = factor(o.data)
+            push!(facs, f); push!(keep, k)
+        end
+        dl, dr = shape(op.basis_l), shape(op.basis_r)
+        sites = Int32[i for i in op.indices]
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve keep facs dl dr sites begin
+            check(ccall((:qob_lazytensor_create, libqob200), Cint,
+                        (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Int64}, Int32, Ptr{Int32}, Ptr{QobFactor}, C64, Ref{Ptr{Cvoid}}),
+                        context(), length(dl), dl, dr, length(sites), sites, facs, C64(op.factor), out))
+        end
+        Handle(out[])
+    end
+end
+
+function handle(op::Operator)   # SparseOperator / dense operator definition
+    get!(HANDLES, op) do
+        f, keep = factor(op.data)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        fn = f.kind == FACTOR_CSC ? :qob_sparse_create : :qob_dense_create
+        GC.@preserve keep begin
+            if f.kind == FACTOR_CSC
+                check(ccall((:qob_sparse_create, libqob200), Cint, (Ptr{Cvoid}, Ref{QobFactor}, Ref{Ptr{Cvoid}}), context(), Ref(f), out))
+            else
+                check(ccall((:qob_dense_create, libqob200), Cint, (Ptr{Cvoid}, Ref{QobFactor}, Ref{Ptr{Cvoid}}), context(), Ref(f), out))
+            end
+        end
+        Handle(out[])
+    end
+end
+
+function handle(op::LazySum)
+    h = get!(HANDLES, op) do
+        hs = [handle(o) for o in op.operators]
+        ptrs = Ptr{Cvoid}[x.ptr for x in hs]
+        coefs = C64[C64(f) for f in op.factors]
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:qob_lazysum_create, libqob200), Cint,
+                    (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{C64}, Ptr{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}),
+                    context(), length(op.basis_l), length(op.basis_r), length(ptrs), coefs, ptrs, out))
+        Handle(out[], hs)
+    end
+    # TimeDependentSum rewrites `factors` at every set_time! (src/time_dependent_operator.jl:279-290): resend, it is cheap
+    coefs = C64[C64(f) for f in op.factors]
+    check(ccall((:qob_lazysum_set_coefs, libqob200), Cint, (Ptr{Cvoid}, Int32, Ptr{C64}), h.ptr, length(coefs), coefs))
+    h
+end
+
+function handle(op::LazyProduct)
+    get!(HANDLES, op) do
+        hs = [handle(o) for o in op.operators]
+        ptrs = Ptr{Cvoid}[x.ptr for x in hs]
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:qob_lazyproduct_create, libqob200), Cint, (Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}, C64, Ref{Ptr{Cvoid}}),
+                    context(), length(ptrs), ptrs, C64(op.factor), out))
+        Handle(out[], hs)
+    end
+end
+
+# ---------------------------------------------------------------- the one call
+function apply!(y::CuArray{ComplexF64}, op, side::Int32, x::CuArray{ComplexF64}, alpha, beta, batch::Integer)
+    h = handle(op)
+    GC.@preserve h check(ccall((:qob_op_apply, libqob200), Cint,
+                               (Ptr{Cvoid}, Int32, C64, CuPtr{Cvoid}, C64, CuPtr{Cvoid}, Int64, Ptr{Cvoid}),
+                               h.ptr, side, C64(alpha), pointer(x), C64(beta), pointer(y), batch, CUDA.stream().handle))
+    y
+end
+
+const DevVec = CuVector{ComplexF64}
+const DevMat = CuMatrix{ComplexF64}
+const DevOp{BL,BR} = Operator{BL,BR,<:DevMat}
+const LazyOps{BL,BR} = Union{LazySum{BL,BR},LazyProduct{BL,BR}}
+const HostSparseOrDense{BL,BR} = Operator{BL,BR,<:Union{SparseMatrixCSC,Adjoint{<:Number,<:SparseMatrixCSC},Matrix,Adjoint{<:Number,<:Matrix}}}
+
+# LazyTensor — same type constraints as src/operators_lazytensor.jl:539,559,576,593 to avoid ambiguities
+mul!(result::Ket{B1,<:DevVec}, a::LazyTensor{B1,B2,F,I,T}, b::Ket{B2,<:DevVec}, alpha, beta) where {B1<:Basis,B2<:Basis,F,I,T<:Tuple{Vararg{DataOperator}}} =
+    (apply!(result.data, a, SIDE_LEFT, b.data, alpha, beta, 1); result)
+mul!(result::Bra{B2,<:DevVec}, a::Bra{B1,<:DevVec}, b::LazyTensor{B1,B2,F,I,T}, alpha, beta) where {B1<:Basis,B2<:Basis,F,I,T<:Tuple{Vararg{DataOperator}}} =
+    (apply!(result.data, b, SIDE_RIGHT, a.data, alpha, beta, 1); result)
+mul!(result::DevOp{B1,B3}, a::LazyTensor{B1,B2,F,I,T}, b::DevOp{B2,B3}, alpha, beta) where {B1<:Basis,B2<:Basis,B3<:Basis,F,I,T<:Tuple{Vararg{DataOperator}}} =
+    (apply!(result.data, a, SIDE_LEFT, b.data, alpha, beta, size(b.data, 2)); result)
+mul!(result::DevOp{B1,B3}, a::DevOp{B1,B2}, b::LazyTensor{B2,B3,F,I,T}, alpha, beta) where {B1<:Basis,B2<:Basis,B3<:Basis,F,I,T<:Tuple{Vararg{DataOperator}}} =
+    (apply!(result.data, b, SIDE_RIGHT, a.data, alpha, beta, size(a.data, 1)); result)
+
+# LazySum / LazyProduct (src/operators_lazysum.jl:189-238, src/operators_lazyproduct.jl:103-163): ONE call, the
+# per-term loop and the LazyProduct buffers live behind the ABI (device temporaries, not the host ket_l/bra_r)
+mul!(result::Ket{B1,<:DevVec}, a::LazyOps{B1,B2}, b::Ket{B2,<:DevVec}, alpha, beta) where {B1,B2} =
+    (apply!(result.data, a, SIDE_LEFT, b.data, alpha, beta, 1); result)
+mul!(result::Bra{B2,<:DevVec}, a::Bra{B1,<:DevVec}, b::LazyOps{B1,B2}, alpha, beta) where {B1,B2} =
+    (apply!(result.data, b, SIDE_RIGHT, a.data, alpha, beta, 1); result)
+mul!(result::DevOp{B1,B3}, a::LazyOps{B1,B2}, b::DevOp{B2,B3}, alpha, beta) where {B1,B2,B3} =
+    (apply!(result.data, a, SIDE_LEFT, b.data, alpha, beta, size(b.data, 2)); result)
+mul!(result::DevOp{B1,B3}, a::DevOp{B1,B2}, b::LazyOps{B2,B3}, alpha, beta) where {B1,B2,B3} =
+    (apply!(result.data, b, SIDE_RIGHT, a.data, alpha, beta, size(a.data, 1)); result)
+
+# SparseOperator / dense operator definitions on the host applied to device states (src/operators_sparse.jl:199-202,
+# src/operators_dense.jl:394-396).  Without these, a device `Operator` falls to the column-by-column fallback
+# (src/operators_dense.jl:400-418).
+mul!(result::DevOp{B1,B3}, M::HostSparseOrDense{B1,B2}, b::DevOp{B2,B3}, alpha, beta) where {B1,B2,B3} =
+    (apply!(result.data, M, SIDE_LEFT, b.data, alpha, beta, size(b.data, 2)); result)
+mul!(result::DevOp{B1,B3}, a::DevOp{B1,B2}, M::HostSparseOrDense{B2,B3}, alpha, beta) where {B1,B2,B3} =
+    (apply!(result.data, M, SIDE_RIGHT, a.data, alpha, beta, size(a.data, 1)); result)
+mul!(result::Ket{B1,<:DevVec}, M::HostSparseOrDense{B1,B2}, b::Ket{B2,<:DevVec}, alpha, beta) where {B1,B2} =
+    (apply!(result.data, M, SIDE_LEFT, b.data, alpha, beta, 1); result)
+mul!(result::Bra{B2,<:DevVec}, b::Bra{B1,<:DevVec}, M::HostSparseOrDense{B1,B2}, alpha, beta) where {B1,B2} =
+    (apply!(result.data, M, SIDE_RIGHT, b.data, alpha, beta, 1); result)
+
+end # module

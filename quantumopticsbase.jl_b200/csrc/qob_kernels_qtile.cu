@@ -27,25 +27,38 @@
 
 #define QT_MAXSEG 8
 #define QT_MAXSEL 3
+#define QT_DIAG_WINDOW 6  // merged diagonal tables span at most this many index bits (64 entries)
 
-struct QCompDev {       // 16 bytes, read as one int4 broadcast from shared memory
-  uint32_t lmask;       // tile-local flip mask
-  uint32_t sel;         // selector bit positions: byte j = global bit of table-index bit j; 0xFF = unused
-  uint32_t tab_off;     // offset of this component's 2^nsel weights in the pass table
-  uint32_t flags;       // bit0: last component of its mask group (do the gather+FMA now)
+// One weight-table lookup + (at the end of a mask group) one gather from the staged tile.
+struct QCompDev {   // 16 bytes, read as one broadcast LDS.128
+  uint32_t xorB;    // tile-local flip mask * 16 (byte offset XOR inside the staged tile)
+  uint32_t sel;     // up to three bit-field runs of the index: run r = bits [9r, 9r+9): shift (6 bits) | width (3 bits)
+  uint32_t tabB;    // byte offset of this table inside the pass table
+  uint32_t flags;   // bit0: last lookup of its mask group (gather + FMA now); bit1: the group has a single lookup
 };
 
+#define QT_MAXCOMP 56  // lookup records carried in the kernel parameters (uniform loads, no shared-memory traffic)
+
 struct QPassParams {
-  const QCompDev *comps;  // device
-  const double2 *tab;     // device
-  int ncomp, ntab;
+  const double2 *tab;     // device: weight tables of this pass (entry 0 is a zero weight)
+  int npre;               // diagonal tables evaluated once per thread (selector bits fixed for the thread)
+  int ndiag;              // diagonal tables evaluated per amplitude
+  int nmulti;             // off-diagonal lookups that share their mask with others (summed before the gather)
+  int nsingle;            // off-diagonal lookups with a mask of their own
+  int ntab;
+  int has_diag;           // some diagonal weight exists: acc starts from (dthread + diag tables) * x[i]
   int nfree_seg, nfixed_seg;
   // segment = (shift in the compact index, length, position in the address)
   unsigned char fs_l[QT_MAXSEG], fs_n[QT_MAXSEG], fs_g[QT_MAXSEG];  // free bits: tile-local index -> address
   unsigned char xs_l[QT_MAXSEG], xs_n[QT_MAXSEG], xs_g[QT_MAXSEG];  // fixed bits: tile id -> address
-  unsigned long long hi_or;  // index bits above the local address (rank), already shifted
+  unsigned long long hi_or;     // index bits above the local address (rank), already shifted
+  unsigned long long eoff[16];  // address part of tile-local index k*THREADS (k < TILE/THREADS), precomputed on the host
   double2 alpha, beta;
   int mode;  // 0: y = a*acc ; 1: y = a*acc + beta*y ; 2: y = a*acc + y
+  QCompDev comps[QT_MAXCOMP];  // [npre | ndiag | nmulti | nsingle]
+  // per (record, k): byte offsets contributed by the warp-uniform part k*THREADS of the tile-local index:
+  // .x -> weight-table offset (selector bits among the thread's varying bits), .y -> gather offset (k*THREADS*16 ^ high mask bits)
+  uint2 ck[QT_MAXCOMP][16];
 };
 
 __device__ __forceinline__ void qcfma(double2 &acc, double2 a, double2 b) {
@@ -64,92 +77,213 @@ __device__ __forceinline__ unsigned long long qexpand(unsigned v, int nseg, cons
   return a;
 }
 
-template <int T, int THREADS, int MINB>
+// value of the index field described by run r of `sel` (shift 6 bits | width 3 bits), shifted left by `pos`
+template <bool IDX64>
+__device__ __forceinline__ unsigned qrun(unsigned sel, int r, unsigned lo, unsigned hi, unsigned pos) {
+  const unsigned sh = (sel >> (9 * r)) & 63u, w = (sel >> (9 * r + 6)) & 7u;
+  unsigned v;
+  if (IDX64)
+    v = sh < 32 ? __funnelshift_r(lo, hi, sh) : (hi >> (sh & 31));
+  else
+    v = lo >> sh;
+  return (v & ((1u << w) - 1u)) << pos;
+}
+// table index (in entries) for up to three runs; runs 1 and 2 are rare (selector bits that are not adjacent).
+// The field is bitwise in the index: qfield(a | b) == qfield(a) | qfield(b).
+template <bool IDX64>
+__device__ __forceinline__ unsigned qfield(unsigned sel, unsigned lo, unsigned hi) {
+  unsigned idx = qrun<IDX64>(sel, 0, lo, hi, 0);
+  if (sel >> 9) {
+    const unsigned w0 = (sel >> 6) & 7u, w1 = (sel >> 15) & 7u;
+    idx |= qrun<IDX64>(sel, 1, lo, hi, w0);
+    if (sel >> 18) idx |= qrun<IDX64>(sel, 2, lo, hi, w0 + w1);
+  }
+  return idx;
+}
+
+// weight load: complex tables hold (re, im); the REALW variant reads only the real part (8 bytes: half the
+// shared-memory wavefronts) and multiplies with 2 DFMA instead of 4
+template <bool REALW>
+struct QW {
+  double2 w;
+  __device__ __forceinline__ void load(const unsigned char *p) {
+    if (REALW) {
+      w.x = *reinterpret_cast<const double *>(p);
+      w.y = 0.0;
+    } else {
+      w = *reinterpret_cast<const double2 *>(p);
+    }
+  }
+  __device__ __forceinline__ void fma_into(double2 &acc, const double2 v) const {
+    if (REALW) {
+      acc.x = fma(w.x, v.x, acc.x);
+      acc.y = fma(w.x, v.y, acc.y);
+    } else {
+      qcfma(acc, w, v);
+    }
+  }
+};
+
+template <int T, int THREADS, int MINB, bool IDX64, bool REALW>
 __global__ void __launch_bounds__(THREADS, MINB)
     qtile_kernel(const __grid_constant__ QPassParams P, const double2 *__restrict__ x, double2 *__restrict__ y) {
   constexpr int TILE = 1 << T;
-  constexpr int U = 4;                    // amplitudes in flight per thread
-  constexpr int ITERS = TILE / (THREADS * U);
-  static_assert(ITERS >= 1, "tile too small for this block size");
+  constexpr int PER = TILE / THREADS;       // amplitudes per thread
+  constexpr int U = PER < 8 ? PER : 8;      // amplitudes in flight per thread
+  constexpr int ITERS = PER / U;
+  constexpr unsigned TMASKB = THREADS * 16u - 1u;  // byte-offset bits that belong to the tid part of the tile-local index
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2 *xs = reinterpret_cast<double2 *>(smem_raw);
-  double2 *tab = xs + TILE;
-  QCompDev *comps = reinterpret_cast<QCompDev *>(tab + P.ntab);
+  unsigned char *xsB = smem_raw;                                    // staged x tile, byte addressed
+  unsigned char *tabB = smem_raw + (size_t)TILE * sizeof(double2);  // weight tables
 
   const unsigned tid = threadIdx.x;
   const unsigned long long base = qexpand(blockIdx.x, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g);
-  const unsigned long long a_tid = qexpand(tid, P.nfree_seg, P.fs_l, P.fs_n, P.fs_g);
+  const unsigned long long at = base | qexpand(tid, P.nfree_seg, P.fs_l, P.fs_n, P.fs_g);  // per-thread address part
 
   // ---- stage the x tile: 16-byte cp.async per amplitude, lanes walk the contiguous low block
-#pragma unroll 4
-  for (int it = 0; it < TILE / THREADS; ++it) {
-    const unsigned l = it * THREADS + tid;
-    const unsigned long long a = base | a_tid | qexpand(it * THREADS, P.nfree_seg, P.fs_l, P.fs_n, P.fs_g);
-    const unsigned saddr = (unsigned)__cvta_generic_to_shared(xs + l);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(x + a));
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const unsigned l = k * THREADS + tid;
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(xsB + (size_t)l * sizeof(double2));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(x + (at | P.eoff[k])));
   }
   asm volatile("cp.async.commit_group;\n" ::);
-  for (int i = tid; i < P.ntab; i += THREADS) tab[i] = P.tab[i];
-  for (int i = tid; i < P.ncomp; i += THREADS) comps[i] = P.comps[i];
+  // read-modify-write passes: pull this tile's y lines into L2 now (no registers held), so that the epilogue's
+  // loads find them there instead of paying the DRAM latency after the compute phase.  The low 3 tile-local bits
+  // are always contiguous address bits (L >= 3): one prefetch per 128-byte line.
+  if (P.mode != 0 && (tid & 7u) == 0u) {
+#pragma unroll
+    for (int k = 0; k < PER; ++k) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(y + (at | P.eoff[k])));
+  }
+  {
+    int4 *t4 = reinterpret_cast<int4 *>(tabB);
+    const int4 *g4 = reinterpret_cast<const int4 *>(P.tab);
+    for (int i = tid; i < P.ntab; i += THREADS) t4[i] = g4[i];
+  }
   asm volatile("cp.async.wait_group 0;\n" ::);
   __syncthreads();
 
-  const int ncomp = P.ncomp;
-  const unsigned long long at = base | a_tid;  // per-thread part of the address
+  // thread part of the logical index (tile id, tid and rank bits); the amplitude-dependent part eoff[k] is warp-uniform
+  const unsigned g_lo = (unsigned)(at | P.hi_or), g_hi = (unsigned)((at | P.hi_or) >> 32);
+  const unsigned lbt = tid * 16u;
+  // ---- diagonal weight that does not depend on which of its amplitudes the thread is working on: once per thread
+  double2 dthread = make_double2(0.0, 0.0);
+  for (int c = 0; c < P.npre; ++c) {
+    const QCompDev cd = P.comps[c];
+    const double2 w = *reinterpret_cast<const double2 *>(tabB + cd.tabB + qfield<IDX64>(cd.sel, g_lo, g_hi) * 16u);
+    dthread.x += w.x;
+    dthread.y += w.y;
+  }
+  const int c_diag = P.npre, c_multi = c_diag + P.ndiag, c_single = c_multi + P.nmulti, c_end = c_single + P.nsingle;
+
+#pragma unroll 1
   for (int it = 0; it < ITERS; ++it) {
-    unsigned glo[U], ghi[U];
-    double2 acc[U], ws[U];
+    double2 acc[U];
+    if (P.has_diag) {  // acc = (sum of diagonal weights) * x[i]
+      double2 d[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      // (it*U+u)*THREADS is warp-uniform: its expansion lives in uniform registers
-      const unsigned long long gg = at | qexpand((it * U + u) * THREADS, P.nfree_seg, P.fs_l, P.fs_n, P.fs_g) | P.hi_or;
-      glo[u] = (unsigned)gg;
-      ghi[u] = (unsigned)(gg >> 32);
-      acc[u] = make_double2(0.0, 0.0);
-      ws[u] = make_double2(0.0, 0.0);
-    }
-    for (int c = 0; c < ncomp; ++c) {
-      const QCompDev cd = comps[c];
-      const unsigned s0 = cd.sel & 0xFF, s1 = (cd.sel >> 8) & 0xFF, s2 = (cd.sel >> 16) & 0xFF;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        unsigned idx = 0;
-        if (s0 != 0xFF) idx |= (((s0 < 32) ? glo[u] : ghi[u]) >> (s0 & 31)) & 1u;
-        if (s1 != 0xFF) idx |= ((((s1 < 32) ? glo[u] : ghi[u]) >> (s1 & 31)) & 1u) << 1;
-        if (s2 != 0xFF) idx |= ((((s2 < 32) ? glo[u] : ghi[u]) >> (s2 & 31)) & 1u) << 2;
-        const double2 w = tab[cd.tab_off + idx];
-        ws[u].x += w.x;
-        ws[u].y += w.y;
-      }
-      if (cd.flags & 1u) {
+      for (int u = 0; u < U; ++u) d[u] = dthread;
+      for (int c = c_diag; c < c_multi; ++c) {
+        const QCompDev cd = P.comps[c];
+        const unsigned char *wt = tabB + cd.tabB + qfield<IDX64>(cd.sel, g_lo, g_hi) * 16u;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const unsigned l = (it * U + u) * THREADS + tid;
-          const double2 v = xs[l ^ cd.lmask];
-          qcfma(acc[u], ws[u], v);
-          ws[u] = make_double2(0.0, 0.0);
+          const double2 w = *reinterpret_cast<const double2 *>(wt + P.ck[c][it * U + u].x);
+          d[u].x += w.x;
+          d[u].y += w.y;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double2 v = *reinterpret_cast<const double2 *>(xsB + lbt + (unsigned)(it * U + u) * (THREADS * 16u));
+        acc[u] = make_double2(d[u].x * v.x - d[u].y * v.y, d[u].x * v.y + d[u].y * v.x);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] = make_double2(0.0, 0.0);
+    }
+    if (P.nmulti) {  // several lookups per mask (terms that share a flip mask but not their selector bits): rare
+      double2 ws[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) ws[u] = make_double2(0.0, 0.0);
+      for (int c = c_multi; c < c_single; ++c) {
+        const QCompDev cd = P.comps[c];
+        const unsigned char *wt = tabB + cd.tabB + qfield<IDX64>(cd.sel, g_lo, g_hi) * 16u;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const double2 w = *reinterpret_cast<const double2 *>(wt + P.ck[c][it * U + u].x);
+          ws[u].x += w.x;
+          ws[u].y += w.y;
+        }
+        if (cd.flags & 1u) {
+          const unsigned xT = lbt ^ (cd.xorB & TMASKB);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const double2 v = *reinterpret_cast<const double2 *>(xsB + xT + P.ck[c][it * U + u].y);
+            qcfma(acc[u], ws[u], v);
+            ws[u] = make_double2(0.0, 0.0);
+          }
         }
       }
     }
+    // hot loop — one record per bond.  Everything that depends only on the record and on (it, u) is warp-uniform
+    // (records and eoff live in the kernel parameters), so per (bond, amplitude) the vector pipes see:
+    //   LDS (weight; skipped when the weight is the same for all of the thread's amplitudes), LDS.128 (gather), DFMAs.
+    for (int c = c_single; c < c_end; ++c) {
+      const QCompDev cd = P.comps[c];
+      const unsigned char *wt = tabB + cd.tabB + qfield<IDX64>(cd.sel, g_lo, g_hi) * 16u;   // thread part of the lookup
+      const unsigned char *xt = xsB + (lbt ^ (cd.xorB & TMASKB));                            // thread part of the gather
+      if (cd.flags & 4u) {  // selector bits do not include any bit that varies between this thread's amplitudes
+        QW<REALW> w;
+        w.load(wt);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned long long a = at | qexpand((it * U + u) * THREADS, P.nfree_seg, P.fs_l, P.fs_n, P.fs_g);
-      double2 o;
-      o.x = P.alpha.x * acc[u].x - P.alpha.y * acc[u].y;
-      o.y = P.alpha.x * acc[u].y + P.alpha.y * acc[u].x;
-      if (P.mode == 1) {
-        qcfma(o, P.beta, y[a]);
-      } else if (P.mode == 2) {
-        const double2 yo = y[a];
-        o.x += yo.x;
-        o.y += yo.y;
+        for (int u = 0; u < U; ++u) {
+          if (u == 4) asm volatile("" ::: "memory");  // two batches of 4 loads in flight: keeps the kernel at 80 registers
+          const double2 v = *reinterpret_cast<const double2 *>(xt + P.ck[c][it * U + u].y);
+          w.fma_into(acc[u], v);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (u == 4) asm volatile("" ::: "memory");
+          const uint2 o = P.ck[c][it * U + u];
+          QW<REALW> w;
+          w.load(wt + o.x);
+          const double2 v = *reinterpret_cast<const double2 *>(xt + o.y);
+          w.fma_into(acc[u], v);
+        }
       }
-      y[a] = o;
+      asm volatile("" ::: "memory");
+    }
+    // ---- epilogue: y read-modify-write in batches of 4 independent 16-byte accesses per thread
+    constexpr int EB = U < 4 ? U : 4;
+#pragma unroll
+    for (int u0 = 0; u0 < U; u0 += EB) {
+      double2 yo[EB];
+      if (P.mode != 0) {
+#pragma unroll
+        for (int u = 0; u < EB; ++u) yo[u] = y[at | P.eoff[it * U + u0 + u]];
+      }
+#pragma unroll
+      for (int u = 0; u < EB; ++u) {
+        double2 o;
+        o.x = P.alpha.x * acc[u0 + u].x - P.alpha.y * acc[u0 + u].y;
+        o.y = P.alpha.x * acc[u0 + u].y + P.alpha.y * acc[u0 + u].x;
+        if (P.mode == 1) {
+          qcfma(o, P.beta, yo[u]);
+        } else if (P.mode == 2) {
+          o.x += yo[u].x;
+          o.y += yo[u].y;
+        }
+        y[at | P.eoff[it * U + u0 + u]] = o;
+      }
+      asm volatile("" ::: "memory");
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------- host
+// A "component" = all terms that share (flip mask, selector bits): weight table of 2^nsel entries.
 struct QCompHost {
   uint64_t mask = 0;
   std::vector<int> sel;  // selector bit positions (global), ascending
@@ -160,23 +294,34 @@ struct QCompHost {
   };
   std::vector<Contrib> contribs;
   int pass = -1;
-  uint32_t tab_off = 0;
+};
+// A device table: either one off-diagonal component, or several diagonal components merged over a bit window.
+struct QTableHost {
+  std::vector<int> bits;  // index bits that form the table index, ascending (index bit j of the table <-> bits[j])
+  struct Member {
+    int comp;
+    std::vector<int> pos;  // for each selector bit of the component: its position inside `bits`
+  };
+  std::vector<Member> members;
+  uint32_t tab_off = 0;  // in double2 units inside the pass table
 };
 struct QPassHost {
   std::vector<int> free_bits;  // ascending, size T
-  std::vector<int> comp_ids;   // sorted by mask
+  std::vector<QTableHost> tables;
   QPassParams params;
-  DevArray<QCompDev> d_comps;
   DevArray<double2> d_tab;
   std::vector<double2> h_tab;
+  bool real_weights = false;  // every off-diagonal weight of this pass has a zero imaginary part (checked per coefficient set)
+  std::vector<std::pair<uint32_t, uint32_t>> offdiag_ranges;  // [begin, end) table ranges of the off-diagonal "single" lookups
 };
 struct QTileProgramHost {
   int nbits = 0, T = 0, L = 0, threads = 256;
+  bool idx64 = false;
   uint64_t hi_value = 0;
   std::vector<QCompHost> comps;
   std::vector<std::unique_ptr<QPassHost>> passes;
   size_t smem_bytes(const QPassHost &p) const {
-    return ((size_t)1 << T) * sizeof(double2) + p.params.ntab * sizeof(double2) + p.params.ncomp * sizeof(QCompDev);
+    return ((size_t)1 << T) * sizeof(double2) + p.params.ntab * sizeof(double2);
   }
 };
 
@@ -194,30 +339,105 @@ static void make_segments(const std::vector<int> &bits, unsigned char *sl, unsig
   while (i < bits.size()) {
     size_t j = i;
     while (j + 1 < bits.size() && bits[j + 1] == bits[j] + 1) ++j;
-    sl[nseg] = (unsigned char)i;
-    sn[nseg] = (unsigned char)(j - i + 1);
-    sg[nseg] = (unsigned char)bits[i];
+    if (nseg < QT_MAXSEG) {
+      sl[nseg] = (unsigned char)i;
+      sn[nseg] = (unsigned char)(j - i + 1);
+      sg[nseg] = (unsigned char)bits[i];
+    }
     ++nseg;
     i = j + 1;
   }
 }
 
+// bit-field runs of an ascending bit list -> packed `sel` word; false when more than 3 runs / run wider than 7
+static bool pack_runs(const std::vector<int> &bits, uint32_t &sel) {
+  sel = 0;
+  int r = 0;
+  size_t i = 0;
+  while (i < bits.size()) {
+    size_t j = i;
+    while (j + 1 < bits.size() && bits[j + 1] == bits[j] + 1) ++j;
+    const int w = (int)(j - i + 1);
+    if (r >= 3 || w > 7 || bits[i] > 63) return false;
+    sel |= ((uint32_t)bits[i] | ((uint32_t)w << 6)) << (9 * r);
+    ++r;
+    i = j + 1;
+  }
+  return true;
+}
+
+static cplx comp_value(const QCompHost &c, const std::vector<cplx> &coefs, size_t r) {
+  cplx w = 0.0;
+  for (const auto &ct : c.contribs) {
+    cplx f = ct.scalar;
+    if (ct.coef_index >= 0) f *= coefs[ct.coef_index];
+    w += f * ct.unit[r];
+  }
+  return w;
+}
+
 static void fill_tables(QTileProgramHost &h, const std::vector<cplx> &coefs) {
   for (auto &pp : h.passes) {
     QPassHost &p = *pp;
-    for (int id : p.comp_ids) {
-      const QCompHost &c = h.comps[id];
-      const size_t n = (size_t)1 << c.sel.size();
-      for (size_t r = 0; r < n; ++r) {
-        cplx w = 0.0;
-        for (const auto &ct : c.contribs) {
-          cplx f = ct.scalar;
-          if (ct.coef_index >= 0) f *= coefs[ct.coef_index];
-          w += f * ct.unit[r];
+    std::fill(p.h_tab.begin(), p.h_tab.end(), make_double2(0.0, 0.0));
+    for (const QTableHost &t : p.tables) {
+      const size_t n = (size_t)1 << t.bits.size();
+      for (const auto &m : t.members) {
+        const QCompHost &c = h.comps[m.comp];
+        // component values once, then scattered over the (possibly wider) merged table
+        std::vector<cplx> cv((size_t)1 << c.sel.size());
+        for (size_t r = 0; r < cv.size(); ++r) cv[r] = comp_value(c, coefs, r);
+        for (size_t r = 0; r < n; ++r) {
+          size_t ci = 0;
+          for (size_t b = 0; b < m.pos.size(); ++b) ci |= ((r >> m.pos[b]) & 1) << b;
+          p.h_tab[t.tab_off + r].x += cv[ci].real();
+          p.h_tab[t.tab_off + r].y += cv[ci].imag();
         }
-        p.h_tab[c.tab_off + r] = make_double2(w.real(), w.imag());
       }
     }
+    p.real_weights = true;
+    for (auto &rg : p.offdiag_ranges)
+      for (uint32_t e = rg.first; e < rg.second; ++e) p.real_weights &= (p.h_tab[e].y == 0.0);
+  }
+}
+
+// merge diagonal components into tables over windows of <= QT_DIAG_WINDOW index bits
+static void merge_diag(const QTileProgramHost &h, std::vector<int> ids, std::vector<QTableHost> &out) {
+  std::sort(ids.begin(), ids.end(), [&](int a, int b) {
+    const auto &sa = h.comps[a].sel, &sb = h.comps[b].sel;
+    int la = sa.empty() ? -1 : sa.front(), lb = sb.empty() ? -1 : sb.front();
+    if (la != lb) return la < lb;
+    return sa < sb;
+  });
+  std::vector<bool> used(ids.size(), false);
+  for (size_t i = 0; i < ids.size(); ++i) {
+    if (used[i]) continue;
+    QTableHost t;
+    std::vector<int> bits = h.comps[ids[i]].sel;
+    std::vector<size_t> mem = {i};
+    used[i] = true;
+    for (size_t j = i + 1; j < ids.size(); ++j) {
+      if (used[j]) continue;
+      std::vector<int> u = bits;
+      for (int b : h.comps[ids[j]].sel)
+        if (std::find(u.begin(), u.end(), b) == u.end()) u.push_back(b);
+      std::sort(u.begin(), u.end());
+      uint32_t dummy;
+      if ((int)u.size() <= QT_DIAG_WINDOW && pack_runs(u, dummy)) {
+        bits = u;
+        mem.push_back(j);
+        used[j] = true;
+      }
+    }
+    t.bits = bits;
+    for (size_t m : mem) {
+      QTableHost::Member mm;
+      mm.comp = ids[m];
+      for (int b : h.comps[ids[m]].sel)
+        mm.pos.push_back((int)(std::find(bits.begin(), bits.end(), b) - bits.begin()));
+      t.members.push_back(mm);
+    }
+    out.push_back(std::move(t));
   }
 }
 
@@ -231,17 +451,20 @@ int qtile_build(QTileProgram &prog, int nbits, uint64_t hi_value, const std::vec
   if (T > nbits) T = nbits;
   if (T < 10) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile needs at least 10 index bits (got %d)", nbits);
   int L = env_int("QOB_QTILE_L", 3);
-  if (L < 1) L = 1;
+  if (L < 3) L = 3;  // the kernel prefetches y by 128-byte lines: at least 8 contiguous amplitudes per run
   if (L > T - 3) L = T - 3;
   h->T = T;
   h->L = L;
   h->threads = (T == 13) ? 512 : 256;
+  const int tid_bits = (T == 13) ? 9 : 8;  // log2(threads): tile-local bits below this are fixed per thread
 
   // ---- expand every term into flip/no-flip components, merged by (mask, selector bits)
   std::map<std::pair<uint64_t, std::vector<int>>, int> index;
+  int max_bit = nbits - 1;
   for (const QTerm &t : terms) {
     const int k = (int)t.bits.size();
     if (k > QT_MAXSEL) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: term on %d sites (max %d)", k, QT_MAXSEL);
+    for (int b : t.bits) max_bit = std::max(max_bit, b);
     for (int S = 0; S < (1 << k); ++S) {
       std::vector<cplx> unit((size_t)1 << k);
       bool any = false;
@@ -278,13 +501,14 @@ int qtile_build(QTileProgram &prog, int nbits, uint64_t hi_value, const std::vec
       h->comps[id].contribs.push_back({t.coef_index, t.scalar, unit});
     }
   }
+  h->idx64 = max_bit >= 32;
 
   // ---- cover the distinct non-zero masks with passes of T free bits
   std::vector<uint64_t> masks;
   for (auto &c : h->comps)
     if (c.mask && std::find(masks.begin(), masks.end(), c.mask) == masks.end()) masks.push_back(c.mask);
   std::vector<uint64_t> free_sets;
-  free_sets.push_back((T >= 64) ? ~0ull : ((1ull << T) - 1));  // pass 0: the lowest T bits (fully contiguous tiles)
+  free_sets.push_back((1ull << T) - 1);  // pass 0: the lowest T bits (fully contiguous tiles)
   std::vector<uint64_t> remaining;
   for (uint64_t m : masks)
     if (m & ~free_sets[0]) remaining.push_back(m);
@@ -303,8 +527,7 @@ int qtile_build(QTileProgram &prog, int nbits, uint64_t hi_value, const std::vec
       else rest.push_back(m);
     }
     if (fr == lowL) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: a term does not fit one tile");
-    // a second sweep: masks that became coverable because their bits were added meanwhile
-    for (int b = 0; b < nbits && __builtin_popcountll(fr) < T; ++b) fr |= 1ull << b;  // spend spare bits on the low block
+    for (int b = 0; b < nbits && __builtin_popcountll(fr) < T; ++b) fr |= 1ull << b;  // spare bits widen the low block
     std::vector<uint64_t> rest2;
     for (uint64_t m : rest)
       if (m & ~fr) rest2.push_back(m);
@@ -323,55 +546,156 @@ int qtile_build(QTileProgram &prog, int nbits, uint64_t hi_value, const std::vec
     if (c.pass < 0) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: internal planner error (uncovered mask)");
   }
   for (size_t p = 0; p < free_sets.size(); ++p) {
-    auto ph = std::make_unique<QPassHost>();
+    std::vector<int> free_bits;
     for (int b = 0; b < nbits; ++b)
-      if (free_sets[p] >> b & 1) ph->free_bits.push_back(b);
-    for (size_t id = 0; id < h->comps.size(); ++id)
-      if (h->comps[id].pass == (int)p) ph->comp_ids.push_back((int)id);
-    if (p > 0 && ph->comp_ids.empty()) continue;
-    std::stable_sort(ph->comp_ids.begin(), ph->comp_ids.end(),
-                     [&](int a, int b) { return h->comps[a].mask < h->comps[b].mask; });
-    // device records
-    std::vector<QCompDev> dc;
-    uint32_t tab_off = 0;
-    for (size_t i = 0; i < ph->comp_ids.size(); ++i) {
-      QCompHost &c = h->comps[ph->comp_ids[i]];
-      QCompDev d;
-      uint32_t lmask = 0;
-      for (size_t j = 0; j < ph->free_bits.size(); ++j)
-        if (c.mask >> ph->free_bits[j] & 1) lmask |= 1u << j;
-      d.lmask = lmask;
-      d.sel = 0xFFFFFFFFu;
-      for (size_t j = 0; j < c.sel.size(); ++j) d.sel = (d.sel & ~(0xFFu << (8 * j))) | ((uint32_t)c.sel[j] << (8 * j));
-      d.tab_off = tab_off;
-      c.tab_off = tab_off;
-      tab_off += 1u << c.sel.size();
-      bool last = (i + 1 == ph->comp_ids.size()) || h->comps[ph->comp_ids[i + 1]].mask != c.mask;
-      d.flags = last ? 1u : 0u;
-      dc.push_back(d);
+      if (free_sets[p] >> b & 1) free_bits.push_back(b);
+    // index bits that change between the amplitudes one thread owns: tile-local bits >= tid_bits
+    uint64_t varying = 0;
+    for (size_t j = tid_bits; j < free_bits.size(); ++j) varying |= 1ull << free_bits[j];
+    std::vector<int> diag_pre, diag_amp, flips;
+    for (size_t id = 0; id < h->comps.size(); ++id) {
+      const QCompHost &c = h->comps[id];
+      if (c.pass != (int)p) continue;
+      if (c.mask) {
+        flips.push_back((int)id);
+      } else {
+        uint64_t sb = 0;
+        for (int b : c.sel) sb |= 1ull << b;
+        ((sb & varying) ? diag_amp : diag_pre).push_back((int)id);
+      }
     }
-    if (dc.empty()) {  // a sum with no term at all in pass 0: keep one zero-weight component so y is still written
-      QCompDev d = {0u, 0xFFFFFFFFu, 0u, 1u};
-      dc.push_back(d);
-      tab_off = 1;
+    if (p > 0 && flips.empty() && diag_pre.empty() && diag_amp.empty()) continue;
+    std::stable_sort(flips.begin(), flips.end(), [&](int a, int b) { return h->comps[a].mask < h->comps[b].mask; });
+    std::vector<QTableHost> pre_tabs, amp_tabs;
+    merge_diag(*h, diag_pre, pre_tabs);
+    merge_diag(*h, diag_amp, amp_tabs);
+    // off-diagonal lookups: groups that share a mask ("multi", summed before the gather) and singles
+    std::vector<int> multis, singles;
+    for (size_t i = 0; i < flips.size(); ++i) {
+      const uint64_t m = h->comps[flips[i]].mask;
+      const bool first = (i == 0) || h->comps[flips[i - 1]].mask != m;
+      const bool last = (i + 1 == flips.size()) || h->comps[flips[i + 1]].mask != m;
+      ((first && last) ? singles : multis).push_back(flips[i]);
     }
-    ph->h_tab.assign(std::max<uint32_t>(tab_off, 1), make_double2(0.0, 0.0));
-    QPassParams &P = ph->params;
-    memset(&P, 0, sizeof(P));
-    P.ncomp = (int)dc.size();
-    P.ntab = (int)ph->h_tab.size();
-    make_segments(ph->free_bits, P.fs_l, P.fs_n, P.fs_g, P.nfree_seg);
-    std::vector<int> fixed;
-    for (int b = 0; b < nbits; ++b)
-      if (!(free_sets[p] >> b & 1)) fixed.push_back(b);
-    make_segments(fixed, P.xs_l, P.xs_n, P.xs_g, P.nfixed_seg);
-    if (P.nfree_seg > QT_MAXSEG || P.nfixed_seg > QT_MAXSEG) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: too many index segments");
-    P.hi_or = (nbits >= 64) ? 0ull : (hi_value << nbits);
-    QOB_TRY(ph->d_comps.upload(dc));
-    QOB_TRY(ph->d_tab.upload(ph->h_tab));
-    P.comps = ph->d_comps.ptr;
-    P.tab = ph->d_tab.ptr;
-    h->passes.push_back(std::move(ph));
+    if (pre_tabs.size() + amp_tabs.size() + multis.size() > QT_MAXCOMP - 8)
+      QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: too many diagonal / shared-mask lookups for one pass");
+
+    // the records live in the kernel parameters: if the singles do not fit, the overflow runs as extra passes over
+    // the same tiles (each a read-modify-write of y)
+    size_t s_begin = 0;
+    bool first_chunk = true;
+    do {
+      auto ph = std::make_unique<QPassHost>();
+      ph->free_bits = free_bits;
+      std::vector<QCompDev> dc;
+      uint32_t tab_off = 1;  // entry 0 is a zero weight
+      auto emit = [&](QTableHost &t, uint32_t xorB, uint32_t flags) -> int {
+        QCompDev d;
+        d.xorB = xorB;
+        if (!pack_runs(t.bits, d.sel)) return QOB_STATUS_UNSUPPORTED;
+        d.tabB = tab_off * (uint32_t)sizeof(double2);
+        d.flags = flags;
+        t.tab_off = tab_off;
+        tab_off += 1u << t.bits.size();
+        dc.push_back(d);
+        ph->tables.push_back(t);
+        return QOB_STATUS_OK;
+      };
+      auto flip_table = [&](int id, QTableHost &t, uint32_t &lmask, bool &invariant) {
+        const QCompHost &c = h->comps[id];
+        lmask = 0;
+        for (size_t j = 0; j < free_bits.size(); ++j)
+          if (c.mask >> free_bits[j] & 1) lmask |= 1u << j;
+        t.bits = c.sel;
+        QTableHost::Member m;
+        m.comp = id;
+        uint64_t sb = 0;
+        for (size_t b = 0; b < c.sel.size(); ++b) {
+          m.pos.push_back((int)b);
+          sb |= 1ull << c.sel[b];
+        }
+        t.members.push_back(m);
+        invariant = !(sb & varying);
+      };
+      int npre = 0, ndiag = 0, nmulti = 0, nsingle = 0;
+      bool has_diag = false;
+      if (first_chunk) {
+        for (auto &t : pre_tabs)
+          if (emit(t, 0, 0) != QOB_STATUS_OK) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: selector bits too scattered");
+        npre = (int)dc.size();
+        for (auto &t : amp_tabs)
+          if (emit(t, 0, 0) != QOB_STATUS_OK) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: selector bits too scattered");
+        ndiag = (int)dc.size() - npre;
+        has_diag = npre + ndiag > 0;
+        for (size_t i = 0; i < multis.size(); ++i) {
+          QTableHost t;
+          uint32_t lmask;
+          bool inv;
+          flip_table(multis[i], t, lmask, inv);
+          const bool last = (i + 1 == multis.size()) || h->comps[multis[i + 1]].mask != h->comps[multis[i]].mask;
+          if (emit(t, lmask * 16u, last ? 1u : 0u) != QOB_STATUS_OK)
+            QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: selector bits too scattered");
+          ++nmulti;
+        }
+      }
+      while (s_begin < singles.size() && dc.size() < QT_MAXCOMP) {
+        QTableHost t;
+        uint32_t lmask;
+        bool inv;
+        flip_table(singles[s_begin], t, lmask, inv);
+        const uint32_t t0 = tab_off;
+        if (emit(t, lmask * 16u, 1u | 2u | (inv ? 4u : 0u)) != QOB_STATUS_OK)
+          QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: selector bits too scattered");
+        ph->offdiag_ranges.push_back({t0, tab_off});
+        ++nsingle;
+        ++s_begin;
+      }
+      ph->h_tab.assign(tab_off, make_double2(0.0, 0.0));
+      QPassParams &P = ph->params;
+      memset(&P, 0, sizeof(P));
+      P.npre = npre;
+      P.ndiag = ndiag;
+      P.nmulti = nmulti;
+      P.nsingle = nsingle;
+      P.ntab = (int)ph->h_tab.size();
+      P.has_diag = has_diag ? 1 : 0;
+      for (size_t i = 0; i < dc.size(); ++i) P.comps[i] = dc[i];
+      {
+        const unsigned tmaskb = (unsigned)h->threads * 16u - 1u;
+        for (size_t i = 0; i < dc.size(); ++i)
+          for (int k = 0; k < (1 << T) / h->threads && k < 16; ++k) {
+            // address part of tile-local index k*threads, then the table field of that part (bitwise in the index)
+            unsigned long long e = 0;
+            const unsigned v = (unsigned)k * (unsigned)h->threads;
+            for (size_t j = 0; j < free_bits.size(); ++j) e |= (unsigned long long)((v >> j) & 1u) << free_bits[j];
+            unsigned idx = 0, pos = 0;
+            for (int r = 0; r < 3; ++r) {
+              const unsigned sh = (dc[i].sel >> (9 * r)) & 63u, w = (dc[i].sel >> (9 * r + 6)) & 7u;
+              idx |= (unsigned)((e >> sh) & ((1ull << w) - 1ull)) << pos;
+              pos += w;
+            }
+            P.ck[i][k].x = idx * 16u;
+            P.ck[i][k].y = (v * 16u) ^ (dc[i].xorB & ~tmaskb);
+          }
+      }
+      make_segments(free_bits, P.fs_l, P.fs_n, P.fs_g, P.nfree_seg);
+      std::vector<int> fixed;
+      for (int b = 0; b < nbits; ++b)
+        if (!(free_sets[p] >> b & 1)) fixed.push_back(b);
+      make_segments(fixed, P.xs_l, P.xs_n, P.xs_g, P.nfixed_seg);
+      if (P.nfree_seg > QT_MAXSEG || P.nfixed_seg > QT_MAXSEG) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: too many index segments");
+      P.hi_or = (nbits >= 64) ? 0ull : (hi_value << nbits);
+      for (int k = 0; k < (1 << T) / h->threads && k < 16; ++k) {
+        unsigned long long e = 0;
+        const unsigned v = (unsigned)k * (unsigned)h->threads;
+        for (size_t j = 0; j < free_bits.size(); ++j) e |= (unsigned long long)((v >> j) & 1u) << free_bits[j];
+        P.eoff[k] = e;
+      }
+      QOB_TRY(ph->d_tab.upload(ph->h_tab));
+      P.tab = ph->d_tab.ptr;
+      h->passes.push_back(std::move(ph));
+      first_chunk = false;
+    } while (s_begin < singles.size());
   }
   prog.h = h;
   prog.npasses = (int)h->passes.size();
@@ -386,7 +710,12 @@ int qtile_build(QTileProgram &prog, int nbits, uint64_t hi_value, const std::vec
       snprintf(buf, sizeof buf, "%s%d-%d", s ? "," : "", pp->params.fs_g[s], pp->params.fs_g[s] + pp->params.fs_n[s] - 1);
       prog.describe += buf;
     }
-    snprintf(buf, sizeof buf, " comps:%d}", pp->params.ncomp);
+    int ninv = 0;
+    for (int c = 0; c < pp->params.npre + pp->params.ndiag + pp->params.nmulti + pp->params.nsingle; ++c)
+      ninv += (pp->params.comps[c].flags & 4u) ? 1 : 0;
+    snprintf(buf, sizeof buf, " lookups:%d diag+%d multi+%d single(%d thread-invariant) per amplitude, %d per thread; tables:%dB}",
+             pp->params.ndiag, pp->params.nmulti, pp->params.nsingle, ninv, pp->params.npre,
+             (int)(pp->params.ntab * sizeof(double2)));
     prog.describe += buf;
   }
   (void)sm_count;
@@ -403,18 +732,18 @@ int qtile_set_coefs(QTileProgram &prog, const std::vector<cplx> &coefs, cudaStre
   return QOB_STATUS_OK;
 }
 
-template <int T, int THREADS, int MINB>
+template <int T, int THREADS, int MINB, bool IDX64, bool REALW>
 static int launch_pass(const QTileProgramHost &h, const QPassHost &p, const QPassParams &P, const void *x, void *y,
                        cudaStream_t s) {
   size_t smem = h.smem_bytes(p);
   static size_t configured = 0;
   if (smem > configured) {
-    QOB_CUDA(cudaFuncSetAttribute(qtile_kernel<T, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QOB_CUDA(cudaFuncSetAttribute(qtile_kernel<T, THREADS, MINB, IDX64, REALW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const uint64_t ntiles = 1ull << (h.nbits - T);
   if (ntiles > 0x7FFFFFFFull) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: too many tiles");
-  qtile_kernel<T, THREADS, MINB><<<(unsigned)ntiles, THREADS, smem, s>>>(P, (const double2 *)x, (double2 *)y);
+  qtile_kernel<T, THREADS, MINB, IDX64, REALW><<<(unsigned)ntiles, THREADS, smem, s>>>(P, (const double2 *)x, (double2 *)y);
   QOB_LAUNCHED();
   QOB_CUDA(cudaGetLastError());
   return QOB_STATUS_OK;
@@ -457,6 +786,15 @@ int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta,
   bool first = true;
   int pass_no = 0;
   for (auto &pp : h.passes) {
+    {
+      const QPassParams &q = pp->params;
+      const bool empty = q.npre + q.ndiag + q.nmulti + q.nsingle == 0;
+      // a pass without any lookup only has to perform the beta update; with beta == 1 that is a no-op
+      if (empty && ((first && beta == cplx(1.0, 0.0)) || !first)) {
+        first = false;
+        continue;
+      }
+    }
     ProfEntry pe;
     if (g_prof_on) {
       cudaEventCreate(&pe.a);
@@ -471,13 +809,22 @@ int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta,
     P.beta = make_double2(beta.real(), beta.imag());
     P.mode = first ? (beta == cplx(0.0, 0.0) ? 0 : 1) : 2;
     first = false;
+#define QT_CASE(TT, TH, MB)                                                                  \
+  case TT:                                                                                   \
+    if (h.idx64 && rw) QOB_TRY((launch_pass<TT, TH, MB, true, true>(h, *pp, P, x, y, s)));   \
+    else if (h.idx64) QOB_TRY((launch_pass<TT, TH, MB, true, false>(h, *pp, P, x, y, s)));   \
+    else if (rw) QOB_TRY((launch_pass<TT, TH, MB, false, true>(h, *pp, P, x, y, s)));        \
+    else QOB_TRY((launch_pass<TT, TH, MB, false, false>(h, *pp, P, x, y, s)));               \
+    break;
+    const bool rw = pp->real_weights && !getenv("QOB_QTILE_NO_REALW");
     switch (h.T) {
-      case 10: QOB_TRY((launch_pass<10, 256, 3>(h, *pp, P, x, y, s))); break;
-      case 11: QOB_TRY((launch_pass<11, 256, 3>(h, *pp, P, x, y, s))); break;
-      case 12: QOB_TRY((launch_pass<12, 256, 3>(h, *pp, P, x, y, s))); break;
-      case 13: QOB_TRY((launch_pass<13, 512, 1>(h, *pp, P, x, y, s))); break;
+      QT_CASE(10, 256, 3)
+      QT_CASE(11, 256, 3)
+      QT_CASE(12, 256, 3)
+      QT_CASE(13, 512, 1)
       default: QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: unsupported tile size %d", h.T);
     }
+#undef QT_CASE
     if (g_prof_on) {
       cudaEventRecord(pe.b, s);
       g_prof.push_back(pe);

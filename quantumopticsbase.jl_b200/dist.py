@@ -43,11 +43,13 @@ def swapped_bitpos(n: int, nloc: int, p: int, s: int):
     return pos
 
 
-def axis_swap(t, s: int, p: int, out, group=None):
+def axis_swap(t, s: int, p: int, out, group=None, async_op=False):
     """All-to-all axis swap of a local slab `t` (2^nloc complex128): local bits [s, s+p) <-> rank bits.
 
     Viewed as (hi, P, lo) with lo = 2^s, block [h, d, :] goes to rank d and lands at [h, src, :].
-    Works on CUDA tensors (NCCL) and on CPU tensors (gloo, used by the world_size-2 tests)."""
+    Works on CUDA tensors (NCCL) and on CPU tensors (gloo, used by the world_size-2 tests).
+    async_op=True returns the list of work handles (the collectives run on NCCL's stream, ordered after the
+    work already queued on the current stream); call `.wait()` on each before consuming `out`."""
     import torch
     import torch.distributed as dist
 
@@ -59,63 +61,89 @@ def axis_swap(t, s: int, p: int, out, group=None):
     tout = torch.view_as_real(out).view(hi, P * lo * 2)
     if P == 1:
         tout.copy_(tin)
-        return out
+        return [] if async_op else out
+    works = []
     for h in range(hi):
-        dist.all_to_all_single(tout[h], tin[h], group=group)
-    return out
+        w = dist.all_to_all_single(tout[h], tin[h], group=group, async_op=async_op)
+        if async_op:
+            works.append(w)
+    return works if async_op else out
 
 
 class ShardedLazySum:
-    """`mul!(y, H, x, alpha, beta)` for a Ket sharded over the ranks of a torch.distributed group."""
+    """`mul!(y, H, x, alpha, beta)` for a Ket sharded over the ranks of a torch.distributed group.
 
-    def __init__(self, H: LazySum, rank: int, world: int, group=None, ctx=None):
+    Schedule of one apply (the two all-to-alls overlap the local tile passes):
+        comm:     x' = swap(x) ...................           y'' = swap(y') ...................
+        compute:  y = alpha*H_A x + beta*y            y' = alpha*H_remote x'   y += alpha*H_B x        y += y''
+    H_A / H_B: the communication-free terms, split at an index bit so that both halves cover a swap."""
+
+    def __init__(self, H: LazySum, rank: int, world: int, group=None, ctx=None, overlap=True):
         assert world & (world - 1) == 0, "world size must be a power of two"
         self.H, self.rank, self.world, self.group = H, rank, world, group
         self.n = len(H.basis_l.shape)
         self.p = world.bit_length() - 1
         self.nloc = self.n - self.p
         self.ctx = ctx
+        self.overlap = overlap
         self.h = handle(H, ctx)
         nterms = len(H.operators)
         od, al = C.c_uint64(), C.c_uint64()
-        local_sel = (C.c_uint8 * max(nterms, 1))()
-        remote_sel = (C.c_uint8 * max(nterms, 1))()
-        touched = 0
         lowmask = (1 << self.nloc) - 1
+        split_bit = self.nloc // 2 + 3          # off-diagonal terms entirely below this bit -> group A
+        sel = {k: (C.c_uint8 * max(nterms, 1))() for k in ("A", "B", "R")}
+        touched = 0
         self.n_local = self.n_remote = 0
+        counts = {"A": 0, "B": 0, "R": 0}
         for i in range(nterms):
             _lib.check(lib.qob_lazysum_term_masks(self.h, i, C.byref(od), C.byref(al)))
             if od.value & ~lowmask:
-                remote_sel[i] = 1
+                k = "R"
                 touched |= al.value
-                self.n_remote += 1
+            elif od.value == 0 or (od.value >> split_bit) == 0:
+                k = "A"          # diagonal terms cost no pass of their own: keep them with the first group
             else:
-                local_sel[i] = 1
-                self.n_local += 1
-        pid = C.c_int32()
-        pos = (C.c_int32 * self.n)(*range(self.n))
-        _lib.check(lib.qob_layout_plan_create(self.h, self.nloc, pos, C.c_uint64(rank), local_sel, C.byref(pid)))
-        self.plan_local = pid.value
-        # what each plan means (layout + selected terms); used by describe() and by the CPU emulation in tests
-        self.plan_info = {self.plan_local: dict(bitpos=list(range(self.n)), hi_value=rank, select=[bool(v) for v in local_sel][:nterms])}
+                k = "B"
+            sel[k][i] = 1
+            counts[k] += 1
+        self.n_remote = counts["R"]
+        self.n_local = counts["A"] + counts["B"]
+        if not self.n_remote or not overlap:   # nothing to overlap with: one local plan
+            for i in range(nterms):
+                if sel["B"][i]:
+                    sel["A"][i], sel["B"][i] = 1, 0
+            counts["A"] += counts["B"]
+            counts["B"] = 0
+        self.plan_info = {}
+        ident = list(range(self.n))
+
+        def make(select, bitpos):
+            pid = C.c_int32()
+            pos = (C.c_int32 * self.n)(*bitpos)
+            _lib.check(lib.qob_layout_plan_create(self.h, self.nloc, pos, C.c_uint64(rank), select, C.byref(pid)))
+            self.plan_info[pid.value] = dict(bitpos=list(bitpos), hi_value=rank, select=[bool(v) for v in select][:nterms])
+            return pid.value
+
+        self.plan_local = make(sel["A"], ident)          # always exists: it also carries the beta update
+        self.plan_local_b = make(sel["B"], ident) if counts["B"] else None
         self.plan_swapped = None
         self.swap_lo = None
         if self.n_remote:
             self.swap_lo = swap_window(self.nloc, self.p, touched & lowmask)
-            sp = swapped_bitpos(self.n, self.nloc, self.p, self.swap_lo)
-            pos2 = (C.c_int32 * self.n)(*sp)
-            _lib.check(lib.qob_layout_plan_create(self.h, self.nloc, pos2, C.c_uint64(rank), remote_sel, C.byref(pid)))
-            self.plan_swapped = pid.value
-            self.plan_info[self.plan_swapped] = dict(bitpos=sp, hi_value=rank, select=[bool(v) for v in remote_sel][:nterms])
+            self.plan_swapped = make(sel["R"], swapped_bitpos(self.n, self.nloc, self.p, self.swap_lo))
         self._buf = None
 
     def describe(self):
         buf = C.create_string_buffer(1 << 14)
-        _lib.check(lib.qob_layout_plan_describe(self.h, self.plan_local, buf, len(buf)))
-        out = f"local[{self.n_local} terms]: {buf.value.decode()}"
+
+        def d(pid):
+            _lib.check(lib.qob_layout_plan_describe(self.h, pid, buf, len(buf)))
+            return buf.value.decode()
+        out = f"local[{self.n_local} terms]: {d(self.plan_local)}"
+        if self.plan_local_b is not None:
+            out += f" + {d(self.plan_local_b)}"
         if self.plan_swapped is not None:
-            _lib.check(lib.qob_layout_plan_describe(self.h, self.plan_swapped, buf, len(buf)))
-            out += f" | swapped[{self.n_remote} terms, window bit {self.swap_lo}]: {buf.value.decode()}"
+            out += f" | swapped[{self.n_remote} terms, window bit {self.swap_lo}]: {d(self.plan_swapped)}"
         return out
 
     def _apply(self, plan, alpha, x, beta, y):
@@ -127,24 +155,29 @@ class ShardedLazySum:
                                              C.c_void_p(y.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
     def mul_(self, y, x, alpha=1.0, beta=0.0):
-        """y_local = alpha * (H x)_local + beta * y_local;  x, y: torch complex128 CUDA slabs of 2^nloc."""
+        """y_local = alpha * (H x)_local + beta * y_local;  x, y: torch complex128 slabs of 2^nloc amplitudes."""
         import torch
 
         assert x.numel() == 1 << self.nloc and y.numel() == 1 << self.nloc
         alpha, beta = complex(alpha), complex(beta)
         if self.plan_swapped is None or alpha == 0:
             self._apply(self.plan_local, alpha, x, beta, y)
+            if self.plan_local_b is not None and alpha != 0:
+                self._apply(self.plan_local_b, alpha, x, 1.0, y)
             return y
-        if self._buf is None or self._buf[0].numel() != x.numel():
+        if self._buf is None or self._buf[0].numel() != x.numel() or self._buf[0].device != x.device:
             self._buf = (torch.empty_like(x), torch.empty_like(x))
         b1, b2 = self._buf
-        axis_swap(x, self.swap_lo, self.p, b1, self.group)        # x in the swapped layout
-        self._apply(self.plan_swapped, alpha, b1, 0.0, b2)         # partial result, swapped layout
-        if beta == 0:
-            axis_swap(b2, self.swap_lo, self.p, y, self.group)     # lands directly in y
-            self._apply(self.plan_local, alpha, x, 1.0, y)
-        else:
-            self._apply(self.plan_local, alpha, x, beta, y)
-            axis_swap(b2, self.swap_lo, self.p, b1, self.group)
-            y.add_(b1)
+        use_async = self.overlap and x.is_cuda
+        works = axis_swap(x, self.swap_lo, self.p, b1, self.group, async_op=use_async)     # x in the swapped layout
+        self._apply(self.plan_local, alpha, x, beta, y)                                     # overlaps the swap
+        for w in (works if use_async else []):
+            w.wait()
+        self._apply(self.plan_swapped, alpha, b1, 0.0, b2)                                  # partial result, swapped layout
+        works = axis_swap(b2, self.swap_lo, self.p, b1, self.group, async_op=use_async)     # back to the slab layout
+        if self.plan_local_b is not None:
+            self._apply(self.plan_local_b, alpha, x, 1.0, y)                                # overlaps the swap back
+        for w in (works if use_async else []):
+            w.wait()
+        y.add_(b1)
         return y
