@@ -241,18 +241,32 @@ def run_product_dist(args, rank, world, local_rank):
     p = world.bit_length() - 1
     free, _total = torch.cuda.mem_get_info()
     n = args.spins or 33
-    while 4 * 16 * (1 << (n - p)) > 0.85 * free and n > 20:
+    nbuf = 3 if os.environ.get("QOB_DIST_EXCHANGE", "fused") == "fused" else 4   # x, y, contributions (+ staging for NCCL)
+    while nbuf * 16 * (1 << (n - p)) > 0.85 * free and n > 20:
         n -= 1
     nloc = n - p
     B, H = build_chain(Q, n)
     sh = ShardedLazySum(H, rank, world)
-    x = torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
+    exchange = os.environ.get("QOB_DIST_EXCHANGE", "fused")
+    x = None
+    if exchange == "fused":
+        try:
+            x = sh.empty_state()   # symmetric memory: peers load their tiles straight from this slab over NVLink
+        except Exception as e:     # no symmetric-memory support on this box: NCCL all-to-all axis swaps instead
+            if rank == 0:
+                print(f"[bench] symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL exchange", file=sys.stderr)
+            exchange = "nccl"
+    if x is None:
+        x = torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
     Q.fill_state(x, 7, 2.0 ** (-n / 2), offset=rank << nloc)
-    y = torch.empty_like(x)
-    plan = sh.describe()
+    y = torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
+    plan = f"exchange={exchange}: " + sh.describe()
 
     def step():
-        sh.mul_(y, x, alpha, 0.0)
+        if exchange == "fused":
+            sh.mul_fused_(y, x, alpha, 0.0)
+        else:
+            sh.mul_(y, x, alpha, 0.0)
 
     run_common(args, Q, rank, world, step, x, y, n, nloc, plan, warmup, args.steps, peak, peak_src, H, alpha, sharded=sh)
 

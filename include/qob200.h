@@ -165,6 +165,18 @@ int qob_layout_plan_create(qob_op *sum, int32_t nbits_local, const int32_t *bitp
 int qob_layout_plan_apply(qob_op *sum, int32_t plan_id, qob_c64 alpha, const void *x, qob_c64 beta, void *y,
                           void *stream);
 int qob_layout_plan_describe(qob_op *sum, int32_t plan_id, char *buf, int64_t buflen);
+/* Extended form used by the fused exchange (compute + NVLink peer memory in ONE kernel, no staging copy, no NCCL):
+ *   zadd     (optional) extra addend in the local layout: y = alpha*(terms)x + beta*y + zadd, folded into the last pass;
+ *   npeers>0 the plan's buffer is the SWAPPED layout of the ranks' slabs: index bits [peer_shift, peer_shift+log2 npeers)
+ *            of an address select the owning rank; the tile kernel loads x straight from x_peers[owner] and stores its
+ *            result straight into y_peers[owner] (device pointers into every rank's symmetric / IPC-mapped memory).
+ *            x and y are ignored in that case.
+ *   sm_budget>0 limits the persistent tile kernel to that many SMs so that another kernel (the local passes) runs beside it. */
+int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const void *x, qob_c64 beta, void *y,
+                             const void *zadd, int32_t npeers, const void *const *x_peers, void *const *y_peers,
+                             int32_t peer_shift, int32_t sm_budget, void *stream);
+/* SMs the persistent tile kernels may occupy by default (0 = all). */
+int qob_set_sm_budget(int32_t sms);
 
 #ifdef __cplusplus
 }

@@ -985,6 +985,46 @@ int qob_layout_plan_apply(qob_op *sum, int32_t plan_id, qob_c64 alpha, const voi
   return qtile_launch(lp.prog, C(alpha), x, C(beta), y, s);
 }
 
+int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const void *x, qob_c64 beta, void *y,
+                             const void *zadd, int32_t npeers, const void *const *x_peers, void *const *y_peers,
+                             int32_t peer_shift, int32_t sm_budget, void *stream) {
+  LazySumOp *S = nullptr;
+  QOB_TRY(qubit_sum(sum, &S));
+  if (plan_id < 0 || plan_id >= (int)S->layouts.size()) QOB_FAIL(QOB_STATUS_INVALID_ARG, "bad layout plan id");
+  if (S->ctx->device < 0) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
+  LazySumOp::LayoutPlan &lp = *S->layouts[plan_id];
+  const int64_t n = 1ll << lp.nloc;
+  cudaStream_t s = (cudaStream_t)stream;
+  QLaunchOpts o;
+  o.sm_budget = sm_budget;
+  o.zadd = zadd;
+  if (npeers > 0) {
+    if (!is_pow2(npeers) || !x_peers || !y_peers) QOB_FAIL(QOB_STATUS_INVALID_ARG, "npeers must be a power of two with pointer tables");
+    const int pb = ilog2(npeers);
+    if (peer_shift < 0 || peer_shift + pb > lp.nloc) QOB_FAIL(QOB_STATUS_INVALID_ARG, "peer window outside the local index bits");
+    if (zadd) QOB_FAIL(QOB_STATUS_INVALID_ARG, "zadd is not available in the peer-addressed form");
+    for (int q = 0; q < npeers; ++q)
+      if (!x_peers[q] || !y_peers[q]) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null peer pointer");
+    o.npeers = npeers;
+    o.peer_shift = peer_shift;
+    o.peer_rank = (int)(lp.prog.h_hi_value() & (uint64_t)(npeers - 1));
+    o.xpeer = x_peers;
+    o.ypeer = y_peers;
+  } else {
+    if (!x || !y) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null data pointer");
+    QOB_TRY(check_alias(x, n, y, n));
+    if (zadd) QOB_TRY(check_alias(zadd, n, y, n));
+  }
+  QOB_CUDA(cudaSetDevice(S->ctx->device));
+  if (C(alpha) == ZERO) {
+    if (npeers > 0) QOB_FAIL(QOB_STATUS_INVALID_ARG, "alpha == 0 in the peer-addressed form");
+    if (zadd) return launch_axpby(zadd, y, n, ONE, C(beta), s);
+    return launch_scale(y, n, C(beta), s);
+  }
+  QOB_TRY(qtile_set_coefs(lp.prog, S->coefs, s));
+  return qtile_launch(lp.prog, C(alpha), x, C(beta), y, s, &o);
+}
+
 int qob_layout_plan_describe(qob_op *sum, int32_t plan_id, char *buf, int64_t buflen) {
   LazySumOp *S = nullptr;
   QOB_TRY(qubit_sum(sum, &S));

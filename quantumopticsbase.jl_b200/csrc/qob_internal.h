@@ -191,11 +191,22 @@ struct QTileProgram {
   std::shared_ptr<QTileProgramHost> h;
   std::string describe;
   int npasses = 0;
+  uint64_t hi_value = 0;
+  uint64_t h_hi_value() const { return hi_value; }
 };
 // nbits: bits of the local flat index; hi_value: value of index bits >= nbits (rank offset for sharded states)
 int qtile_build(QTileProgram &p, int nbits, uint64_t hi_value, const std::vector<QTerm> &terms, int sm_count);
 int qtile_set_coefs(QTileProgram &p, const std::vector<cplx> &coefs, cudaStream_t s);
-int qtile_launch(const QTileProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s);
+struct QLaunchOpts {
+  int sm_budget = 0;              // SMs this launch may occupy (0: library default, see qob_set_sm_budget)
+  const void *zadd = nullptr;     // extra addend (local layout), applied by the last pass
+  int npeers = 0;                 // > 0: x and y are addressed across ranks (swapped layout over peer memory)
+  int peer_shift = 0, peer_rank = 0;
+  const void *const *xpeer = nullptr;
+  void *const *ypeer = nullptr;
+};
+int qtile_launch(const QTileProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s,
+                 const QLaunchOpts *opts = nullptr);
 bool qtile_supported_term(const QTerm &t);
 
 // misc device helpers

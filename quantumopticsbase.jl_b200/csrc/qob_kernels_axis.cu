@@ -12,6 +12,7 @@
 // tensor path on sm_100a).  Used for genuinely dense factors (d >= 16, BASELINE config 3, d = 48).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "qob_internal.h"
 
@@ -134,6 +135,134 @@ __global__ void __launch_bounds__(32 * MW * NW)
   }
 }
 
+// ---- whole-K variant (dl, dr <= 64: every Fock/NLevel site factor of the BASELINE configs) ----------------
+// The factor A stays in shared memory for the lifetime of a persistent CTA, a full (K x 64) slab of x is staged per
+// tile, so there is ONE barrier pair per 64 output columns instead of two per 16-deep K slice; 12 warps (MW=3) with
+// 16x16 warp tiles and 2 CTAs/SM keep the DMMA pipe fed while the other CTA loads.
+template <int MW>
+__global__ void __launch_bounds__(MW * 128, 2)
+    axis_dmma_wk_kernel(const __grid_constant__ AxisParams P, const double2 *__restrict__ x, double2 *__restrict__ y,
+                        int kpad, int ldk) {
+  constexpr int TM = 16 * MW, TN = 64, NT = MW * 128;
+  extern __shared__ __align__(16) double smem_d[];
+  double *As_re = smem_d, *As_im = As_re + TM * ldk;
+  double *Xs_re = As_im + TM * ldk, *Xs_im = Xs_re + TN * ldk;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp % MW, wn = warp / MW;  // wn in 0..3: 16 columns each
+  const int g = lane >> 2, t = lane & 3;
+  const bool n_fast = P.L >= 8;
+
+  for (int e = tid; e < TM * kpad; e += NT) {
+    int i = e / kpad, k = e - i * kpad;
+    double re = 0.0, im = 0.0;
+    if (i < P.dl_pad && k < P.dr_pad) {
+      re = P.a_re[(long long)i * P.dr_pad + k];
+      im = P.a_im[(long long)i * P.dr_pad + k];
+    }
+    As_re[i * ldk + k] = re;
+    As_im[i * ldk + k] = im;
+  }
+  const long long ntiles = (P.N + TN - 1) / TN;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long n0 = tile * TN;
+    __syncthreads();  // previous tile's fragments are no longer read (first iteration: orders the A stores)
+    for (int e = tid; e < TN * kpad; e += NT) {
+      int n, k;
+      if (n_fast) {
+        k = e / TN;
+        n = e - k * TN;
+      } else {
+        n = e / kpad;
+        k = e - n * kpad;
+      }
+      double2 v = make_double2(0.0, 0.0);
+      const long long nn = n0 + n;
+      if (nn < P.N && k < P.dr) {
+        const long long r = nn / P.L, l = nn - r * P.L;
+        v = x[l + P.L * ((long long)k + (long long)P.dr * r)];
+      }
+      Xs_re[n * ldk + k] = v.x;
+      Xs_im[n * ldk + k] = v.y;
+    }
+    __syncthreads();
+    double cre[2][2][2], cim[2][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
+    for (int kk = 0; kk < kpad; kk += 4) {
+      double are[2], aim[2], naim[2], bre[2], bim[2];
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb) {
+        const int row = wm * 16 + mb * 8 + g;
+        are[mb] = As_re[row * ldk + kk + t];
+        aim[mb] = As_im[row * ldk + kk + t];
+        naim[mb] = -aim[mb];
+      }
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        const int col = wn * 16 + nb * 8 + g;
+        bre[nb] = Xs_re[col * ldk + kk + t];
+        bim[nb] = Xs_im[col * ldk + kk + t];
+      }
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          dmma884(cre[mb][nb][0], cre[mb][nb][1], are[mb], bre[nb]);
+          dmma884(cre[mb][nb][0], cre[mb][nb][1], naim[mb], bim[nb]);
+          dmma884(cim[mb][nb][0], cim[mb][nb][1], are[mb], bim[nb]);
+          dmma884(cim[mb][nb][0], cim[mb][nb][1], aim[mb], bre[nb]);
+        }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+      const int i = wm * 16 + mb * 8 + g;
+      if (i >= P.dl) continue;
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const long long nn = n0 + wn * 16 + nb * 8 + 2 * t + e;
+          if (nn >= P.N) continue;
+          const long long r = nn / P.L, l = nn - r * P.L;
+          const long long addr = l + P.L * ((long long)i + (long long)P.dl * r);
+          const double ar = cre[mb][nb][e], ai = cim[mb][nb][e];
+          double2 o = make_double2(P.alpha.x * ar - P.alpha.y * ai, P.alpha.x * ai + P.alpha.y * ar);
+          if (!P.beta_zero) {
+            const double2 yo = y[addr];
+            o.x += P.beta.x * yo.x - P.beta.y * yo.y;
+            o.y += P.beta.x * yo.y + P.beta.y * yo.x;
+          }
+          y[addr] = o;
+        }
+    }
+  }
+}
+
+template <int MW>
+static int launch_axis_wk(const AxisParams &P, const double2 *xp, double2 *yp, cudaStream_t s) {
+  const int kpad = (P.dr + 3) / 4 * 4;
+  int ldk = kpad;
+  while (ldk % 16 != 4) ++ldk;  // conflict-free 64-bit fragment loads
+  const size_t smem = (size_t)2 * (16 * MW + 64) * ldk * sizeof(double);
+  static size_t configured = 0;
+  if (smem > configured) {
+    QOB_CUDA(cudaFuncSetAttribute(axis_dmma_wk_kernel<MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const long long ntiles = (P.N + 63) / 64;
+  const long long grid = std::min<long long>(ntiles, 2ll * sms);
+  axis_dmma_wk_kernel<MW><<<(unsigned)grid, MW * 128, smem, s>>>(P, xp, yp, kpad, ldk);
+  return QOB_STATUS_OK;
+}
+
 int prepare_axis_matrix(const HostMat &m, AxisMatrixDev &out) {
   out.dl = (int)m.rows;
   out.dr = (int)m.cols;
@@ -176,6 +305,15 @@ int launch_axis_dense(const AxisMatrixDev &A, int64_t L, int64_t R, cplx alpha, 
     dim3 grid((unsigned)gx, (unsigned)((A.dl + TM - 1) / TM));                       \
     axis_dmma_kernel<MW, NW><<<grid, 32 * MW * NW, 0, s>>>(P, xp, yp);               \
   } while (0)
+  if (A.dl <= 64 && A.dr <= 64 && !getenv("QOB_AXIS_V1")) {
+    if (A.dl <= 16) QOB_TRY(launch_axis_wk<1>(P, xp, yp, s));
+    else if (A.dl <= 32) QOB_TRY(launch_axis_wk<2>(P, xp, yp, s));
+    else if (A.dl <= 48) QOB_TRY(launch_axis_wk<3>(P, xp, yp, s));
+    else QOB_TRY(launch_axis_wk<4>(P, xp, yp, s));
+    QOB_LAUNCHED();
+    QOB_CUDA(cudaGetLastError());
+    return QOB_STATUS_OK;
+  }
   // static shared memory must stay under 48 KiB: (TM + TN) * AX_LD * 16 B
   if (A.dl <= 16)
     AX_LAUNCH(1, 4);

@@ -37,6 +37,7 @@ struct QCompDev {   // 16 bytes, read as one broadcast LDS.128
   uint32_t flags;   // bit0: last lookup of its mask group (gather + FMA now); bit1: the group has a single lookup
 };
 
+#define QT_MAXPEER 16
 #define QT_MAXCOMP 56  // lookup records carried in the kernel parameters (uniform loads, no shared-memory traffic)
 
 struct QPassParams {
@@ -54,7 +55,15 @@ struct QPassParams {
   unsigned long long hi_or;     // index bits above the local address (rank), already shifted
   unsigned long long eoff[16];  // address part of tile-local index k*THREADS (k < TILE/THREADS), precomputed on the host
   double2 alpha, beta;
-  int mode;  // 0: y = a*acc ; 1: y = a*acc + beta*y ; 2: y = a*acc + y
+  int mode;  // 0: y = a*acc ; 1: y = a*acc + beta*y ; 2: y = a*acc + y      (+ zadd[i] when zadd != nullptr)
+  unsigned ntiles;          // tiles of this pass; the CTAs are persistent and stride over them
+  const double2 *zadd;      // optional extra addend in the local layout (contributions received from other ranks)
+  // PEER variant (sharded states): the buffer addressed by this pass is the SWAPPED layout of the ranks' slabs.  Index bits
+  // [peer_shift, peer_shift+peer_bits) of an address name the rank that holds the element; there it sits at the same
+  // address with those bits replaced by this rank's number.  Loads/stores go straight to that rank's memory (NVLink P2P).
+  int peer_shift, peer_bits, peer_rank;
+  const double2 *xpeer[QT_MAXPEER];
+  double2 *ypeer[QT_MAXPEER];
   QCompDev comps[QT_MAXCOMP];  // [npre | ndiag | nmulti | nsingle]
   // per (record, k): byte offsets contributed by the warp-uniform part k*THREADS of the tile-local index:
   // .x -> weight-table offset (selector bits among the thread's varying bits), .y -> gather offset (k*THREADS*16 ^ high mask bits)
@@ -124,7 +133,16 @@ struct QW {
   }
 };
 
-template <int T, int THREADS, int MINB, bool IDX64, bool REALW>
+// address of element `a` of the buffer a pass works on: local memory, or (PEER) the owning rank's slab
+template <bool PEER, typename PT>
+__device__ __forceinline__ PT *qaddr(const QPassParams &P, PT *local, PT *const *peers, unsigned long long a) {
+  if (!PEER) return local + a;
+  const unsigned long long m = ((1ull << P.peer_bits) - 1ull) << P.peer_shift;
+  const unsigned q = (unsigned)((a & m) >> P.peer_shift);
+  return peers[q] + ((a & ~m) | ((unsigned long long)P.peer_rank << P.peer_shift));
+}
+
+template <int T, int THREADS, int MINB, bool IDX64, bool REALW, bool PEER>
 __global__ void __launch_bounds__(THREADS, MINB)
     qtile_kernel(const __grid_constant__ QPassParams P, const double2 *__restrict__ x, double2 *__restrict__ y) {
   constexpr int TILE = 1 << T;
@@ -137,35 +155,47 @@ __global__ void __launch_bounds__(THREADS, MINB)
   unsigned char *tabB = smem_raw + (size_t)TILE * sizeof(double2);  // weight tables
 
   const unsigned tid = threadIdx.x;
-  const unsigned long long base = qexpand(blockIdx.x, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g);
-  const unsigned long long at = base | qexpand(tid, P.nfree_seg, P.fs_l, P.fs_n, P.fs_g);  // per-thread address part
+  const unsigned long long at_tid = qexpand(tid, P.nfree_seg, P.fs_l, P.fs_n, P.fs_g);
+  {
+    int4 *t4 = reinterpret_cast<int4 *>(tabB);
+    const int4 *g4 = reinterpret_cast<const int4 *>(P.tab);
+    for (int i = tid; i < P.ntab; i += THREADS) t4[i] = g4[i];
+  }
+  const unsigned lbt = tid * 16u;
+  const int c_diag = P.npre, c_multi = c_diag + P.ndiag, c_single = c_multi + P.nmulti, c_end = c_single + P.nsingle;
+
+  // persistent CTAs: the grid is sized by the host (occupancy x SMs granted to this kernel) and strides over the tiles
+#pragma unroll 1
+  for (unsigned tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+  const unsigned long long at = qexpand(tile, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g) | at_tid;  // per-thread address part
+  __syncthreads();  // the previous tile is no longer read (first trip: orders the table stores)
 
   // ---- stage the x tile: 16-byte cp.async per amplitude, lanes walk the contiguous low block
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
     const unsigned l = k * THREADS + tid;
     const unsigned saddr = (unsigned)__cvta_generic_to_shared(xsB + (size_t)l * sizeof(double2));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(x + (at | P.eoff[k])));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(qaddr<PEER>(P, x, P.xpeer, at | P.eoff[k])));
   }
   asm volatile("cp.async.commit_group;\n" ::);
-  // read-modify-write passes: pull this tile's y lines into L2 now (no registers held), so that the epilogue's
-  // loads find them there instead of paying the DRAM latency after the compute phase.  The low 3 tile-local bits
-  // are always contiguous address bits (L >= 3): one prefetch per 128-byte line.
-  if (P.mode != 0 && (tid & 7u) == 0u) {
+  // read-modify-write passes: pull this tile's y (and z) lines into L2 now (no registers held), so that the
+  // epilogue's loads find them there instead of paying the DRAM latency after the compute phase.  The low 3
+  // tile-local bits are always contiguous address bits (L >= 3): one prefetch per 128-byte line.
+  if (!PEER && (tid & 7u) == 0u) {
+    if (P.mode != 0) {
 #pragma unroll
-    for (int k = 0; k < PER; ++k) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(y + (at | P.eoff[k])));
-  }
-  {
-    int4 *t4 = reinterpret_cast<int4 *>(tabB);
-    const int4 *g4 = reinterpret_cast<const int4 *>(P.tab);
-    for (int i = tid; i < P.ntab; i += THREADS) t4[i] = g4[i];
+      for (int k = 0; k < PER; ++k) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(y + (at | P.eoff[k])));
+    }
+    if (P.zadd != nullptr) {
+#pragma unroll
+      for (int k = 0; k < PER; ++k) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(P.zadd + (at | P.eoff[k])));
+    }
   }
   asm volatile("cp.async.wait_group 0;\n" ::);
   __syncthreads();
 
   // thread part of the logical index (tile id, tid and rank bits); the amplitude-dependent part eoff[k] is warp-uniform
   const unsigned g_lo = (unsigned)(at | P.hi_or), g_hi = (unsigned)((at | P.hi_or) >> 32);
-  const unsigned lbt = tid * 16u;
   // ---- diagonal weight that does not depend on which of its amplitudes the thread is working on: once per thread
   double2 dthread = make_double2(0.0, 0.0);
   for (int c = 0; c < P.npre; ++c) {
@@ -174,7 +204,6 @@ __global__ void __launch_bounds__(THREADS, MINB)
     dthread.x += w.x;
     dthread.y += w.y;
   }
-  const int c_diag = P.npre, c_multi = c_diag + P.ndiag, c_single = c_multi + P.nmulti, c_end = c_single + P.nsingle;
 
 #pragma unroll 1
   for (int it = 0; it < ITERS; ++it) {
@@ -259,27 +288,37 @@ __global__ void __launch_bounds__(THREADS, MINB)
     constexpr int EB = U < 4 ? U : 4;
 #pragma unroll
     for (int u0 = 0; u0 < U; u0 += EB) {
-      double2 yo[EB];
+      double2 t[EB];  // beta*y (+ z): everything that is added to alpha*acc
+#pragma unroll
+      for (int u = 0; u < EB; ++u) t[u] = make_double2(0.0, 0.0);
       if (P.mode != 0) {
 #pragma unroll
-        for (int u = 0; u < EB; ++u) yo[u] = y[at | P.eoff[it * U + u0 + u]];
+        for (int u = 0; u < EB; ++u) t[u] = *qaddr<PEER>(P, y, P.ypeer, at | P.eoff[it * U + u0 + u]);
+        if (P.mode == 1) {
+#pragma unroll
+          for (int u = 0; u < EB; ++u)
+            t[u] = make_double2(P.beta.x * t[u].x - P.beta.y * t[u].y, P.beta.x * t[u].y + P.beta.y * t[u].x);
+        }
+      }
+      if (!PEER && P.zadd != nullptr) {
+#pragma unroll
+        for (int u = 0; u < EB; ++u) {
+          const double2 z = P.zadd[at | P.eoff[it * U + u0 + u]];
+          t[u].x += z.x;
+          t[u].y += z.y;
+        }
       }
 #pragma unroll
       for (int u = 0; u < EB; ++u) {
         double2 o;
-        o.x = P.alpha.x * acc[u0 + u].x - P.alpha.y * acc[u0 + u].y;
-        o.y = P.alpha.x * acc[u0 + u].y + P.alpha.y * acc[u0 + u].x;
-        if (P.mode == 1) {
-          qcfma(o, P.beta, yo[u]);
-        } else if (P.mode == 2) {
-          o.x += yo[u].x;
-          o.y += yo[u].y;
-        }
-        y[at | P.eoff[it * U + u0 + u]] = o;
+        o.x = fma(P.alpha.x, acc[u0 + u].x, fma(-P.alpha.y, acc[u0 + u].y, t[u].x));
+        o.y = fma(P.alpha.x, acc[u0 + u].y, fma(P.alpha.y, acc[u0 + u].x, t[u].y));
+        *qaddr<PEER>(P, y, P.ypeer, at | P.eoff[it * U + u0 + u]) = o;
       }
       asm volatile("" ::: "memory");
     }
   }
+  }  // tile loop
 }
 
 // ---------------------------------------------------------------------------------------- host
@@ -698,6 +737,7 @@ int qtile_build(QTileProgram &prog, int nbits, uint64_t hi_value, const std::vec
     } while (s_begin < singles.size());
   }
   prog.h = h;
+  prog.hi_value = hi_value;
   prog.npasses = (int)h->passes.size();
   char buf[256];
   snprintf(buf, sizeof buf, "qtile[bits=%d,T=%d,L=%d,passes=%d,components=%d]", nbits, T, L, prog.npasses,
@@ -732,18 +772,19 @@ int qtile_set_coefs(QTileProgram &prog, const std::vector<cplx> &coefs, cudaStre
   return QOB_STATUS_OK;
 }
 
-template <int T, int THREADS, int MINB, bool IDX64, bool REALW>
+template <int T, int THREADS, int MINB, bool IDX64, bool REALW, bool PEER>
 static int launch_pass(const QTileProgramHost &h, const QPassHost &p, const QPassParams &P, const void *x, void *y,
-                       cudaStream_t s) {
+                       int max_ctas, cudaStream_t s) {
   size_t smem = h.smem_bytes(p);
   static size_t configured = 0;
   if (smem > configured) {
-    QOB_CUDA(cudaFuncSetAttribute(qtile_kernel<T, THREADS, MINB, IDX64, REALW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QOB_CUDA(cudaFuncSetAttribute(qtile_kernel<T, THREADS, MINB, IDX64, REALW, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const uint64_t ntiles = 1ull << (h.nbits - T);
   if (ntiles > 0x7FFFFFFFull) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: too many tiles");
-  qtile_kernel<T, THREADS, MINB, IDX64, REALW><<<(unsigned)ntiles, THREADS, smem, s>>>(P, (const double2 *)x, (double2 *)y);
+  uint64_t grid = std::min<uint64_t>(ntiles, (uint64_t)std::max(1, max_ctas));
+  qtile_kernel<T, THREADS, MINB, IDX64, REALW, PEER><<<(unsigned)grid, THREADS, smem, s>>>(P, (const double2 *)x, (double2 *)y);
   QOB_LAUNCHED();
   QOB_CUDA(cudaGetLastError());
   return QOB_STATUS_OK;
@@ -781,42 +822,78 @@ extern "C" int qob_profile_read(int32_t max_entries, float *ms, int32_t *pass_in
   return QOB_STATUS_OK;
 }
 
-int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s) {
+static int g_sm_budget = 0;  // SMs the persistent tile kernels may occupy (0 = all of them)
+extern "C" int qob_set_sm_budget(int32_t sms) {
+  g_sm_budget = sms < 0 ? 0 : sms;
+  return QOB_STATUS_OK;
+}
+
+int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s,
+                 const QLaunchOpts *opts) {
   const QTileProgramHost &h = *prog.h;
-  bool first = true;
-  int pass_no = 0;
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  QLaunchOpts none;
+  const QLaunchOpts &o = opts ? *opts : none;
+  if (o.npeers > QT_MAXPEER) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "more than %d peers", QT_MAXPEER);
+  int sms = o.sm_budget > 0 ? o.sm_budget : (g_sm_budget > 0 ? g_sm_budget : sm_count);
+  sms = std::min(sms, sm_count);
+  // passes that hold no lookup at all only matter for the beta update
+  std::vector<const QPassHost *> run;
   for (auto &pp : h.passes) {
-    {
-      const QPassParams &q = pp->params;
-      const bool empty = q.npre + q.ndiag + q.nmulti + q.nsingle == 0;
-      // a pass without any lookup only has to perform the beta update; with beta == 1 that is a no-op
-      if (empty && ((first && beta == cplx(1.0, 0.0)) || !first)) {
-        first = false;
-        continue;
-      }
-    }
+    const QPassParams &q = pp->params;
+    if (q.npre + q.ndiag + q.nmulti + q.nsingle > 0) run.push_back(pp.get());
+  }
+  const int64_t n = (int64_t)1 << h.nbits;
+  if (run.empty()) {
+    if (o.npeers) QOB_FAIL(QOB_STATUS_INVALID_ARG, "peer-addressed apply of a plan without terms");
+    if (o.zadd) return launch_axpby(o.zadd, y, n, cplx(1.0, 0.0), beta, s);
+    return launch_scale(y, n, beta, s);
+  }
+  for (size_t pi = 0; pi < run.size(); ++pi) {
+    const QPassHost *pp = run[pi];
+    const bool first = pi == 0;
     ProfEntry pe;
     if (g_prof_on) {
       cudaEventCreate(&pe.a);
       cudaEventCreate(&pe.b);
-      pe.pass = pass_no;
-      pe.bytes = (double)(1ull << h.nbits) * ((first && beta == cplx(0.0, 0.0)) ? 32.0 : 48.0);
+      pe.pass = (int)pi;
+      pe.bytes = (double)(1ull << h.nbits) * ((first && beta == cplx(0.0, 0.0)) ? 32.0 : 48.0) +
+                 ((o.zadd && pi + 1 == run.size()) ? 16.0 * (double)(1ull << h.nbits) : 0.0);
       cudaEventRecord(pe.a, s);
     }
-    ++pass_no;
     QPassParams P = pp->params;
     P.alpha = make_double2(alpha.real(), alpha.imag());
     P.beta = make_double2(beta.real(), beta.imag());
     P.mode = first ? (beta == cplx(0.0, 0.0) ? 0 : 1) : 2;
-    first = false;
-#define QT_CASE(TT, TH, MB)                                                                  \
-  case TT:                                                                                   \
-    if (h.idx64 && rw) QOB_TRY((launch_pass<TT, TH, MB, true, true>(h, *pp, P, x, y, s)));   \
-    else if (h.idx64) QOB_TRY((launch_pass<TT, TH, MB, true, false>(h, *pp, P, x, y, s)));   \
-    else if (rw) QOB_TRY((launch_pass<TT, TH, MB, false, true>(h, *pp, P, x, y, s)));        \
-    else QOB_TRY((launch_pass<TT, TH, MB, false, false>(h, *pp, P, x, y, s)));               \
-    break;
+    P.ntiles = (unsigned)(1ull << (h.nbits - h.T));
+    P.zadd = (pi + 1 == run.size()) ? (const double2 *)o.zadd : nullptr;
+    P.peer_shift = o.peer_shift;
+    P.peer_rank = o.peer_rank;
+    P.peer_bits = 0;
+    while ((1 << P.peer_bits) < o.npeers) ++P.peer_bits;
+    for (int q = 0; q < o.npeers; ++q) {
+      P.xpeer[q] = (const double2 *)o.xpeer[q];
+      P.ypeer[q] = (double2 *)o.ypeer[q];
+    }
     const bool rw = pp->real_weights && !getenv("QOB_QTILE_NO_REALW");
+    const bool peer = o.npeers > 0;
+#define QT_CASE(TT, TH, MB)                                                                                     \
+  case TT: {                                                                                                    \
+    const int ctas = sms * MB;                                                                                  \
+    if (peer) {                                                                                                 \
+      if (rw) QOB_TRY((launch_pass<TT, TH, MB, true, true, true>(h, *pp, P, x, y, ctas, s)));                  \
+      else QOB_TRY((launch_pass<TT, TH, MB, true, false, true>(h, *pp, P, x, y, ctas, s)));                    \
+    } else if (h.idx64 && rw) QOB_TRY((launch_pass<TT, TH, MB, true, true, false>(h, *pp, P, x, y, ctas, s))); \
+    else if (h.idx64) QOB_TRY((launch_pass<TT, TH, MB, true, false, false>(h, *pp, P, x, y, ctas, s)));        \
+    else if (rw) QOB_TRY((launch_pass<TT, TH, MB, false, true, false>(h, *pp, P, x, y, ctas, s)));             \
+    else QOB_TRY((launch_pass<TT, TH, MB, false, false, false>(h, *pp, P, x, y, ctas, s)));                    \
+  } break;
     switch (h.T) {
       QT_CASE(10, 256, 3)
       QT_CASE(11, 256, 3)

@@ -17,6 +17,7 @@ and moves data.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 from . import _lib
 from ._lib import c64, lib
@@ -78,7 +79,7 @@ class ShardedLazySum:
         compute:  y = alpha*H_A x + beta*y            y' = alpha*H_remote x'   y += alpha*H_B x        y += y''
     H_A / H_B: the communication-free terms, split at an index bit so that both halves cover a swap."""
 
-    def __init__(self, H: LazySum, rank: int, world: int, group=None, ctx=None, overlap=True):
+    def __init__(self, H: LazySum, rank: int, world: int, group=None, ctx=None, overlap=True, swap_sms=None):
         assert world & (world - 1) == 0, "world size must be a power of two"
         self.H, self.rank, self.world, self.group = H, rank, world, group
         self.n = len(H.basis_l.shape)
@@ -132,6 +133,84 @@ class ShardedLazySum:
             self.swap_lo = swap_window(self.nloc, self.p, touched & lowmask)
             self.plan_swapped = make(sel["R"], swapped_bitpos(self.n, self.nloc, self.p, self.swap_lo))
         self._buf = None
+        # fused exchange (symmetric memory): peers' pointer tables, keyed by the local tensor's data_ptr
+        self._symm = {}
+        self._zbuf = None
+        self.swap_sms = int(os.environ.get("QOB_DIST_SWAP_SMS", "32")) if swap_sms is None else int(swap_sms)
+
+    # ------------------------------------------------------------------ fused exchange over NVLink peer memory
+    def empty_state(self, device=None):
+        """A slab of 2^nloc ComplexF64 in SYMMETRIC memory (torch.distributed._symmetric_memory): every rank can address
+        every other rank's slab, which is what lets the remote-term pass load its tiles straight from the owners' HBM.
+        Collective: all ranks must call it in the same order."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        raw = symm_mem.empty((1 << self.nloc) * 2, dtype=torch.float64, device=dev)
+        hdl = symm_mem.rendezvous(raw, self.group if self.group is not None else dist.group.WORLD)
+        t = torch.view_as_complex(raw.view(1 << self.nloc, 2))
+        self._symm[t.data_ptr()] = (hdl, [int(p) for p in hdl.buffer_ptrs], raw)
+        return t
+
+    def _peer_table(self, ptrs):
+        return (C.c_void_p * len(ptrs))(*ptrs)
+
+    def _apply_ex(self, plan, alpha, x, beta, y, zadd=None, peers=None, sm_budget=0):
+        import torch
+
+        handle(self.H, self.ctx)
+        npeers, xp, yp, shift = 0, None, None, 0
+        if peers is not None:
+            xp, yp = self._peer_table(peers[0]), self._peer_table(peers[1])
+            npeers, shift = len(peers[0]), self.swap_lo
+        _lib.check(lib.qob_layout_plan_apply_ex(
+            self.h, plan, c64.of(alpha), C.c_void_p(x.data_ptr() if x is not None else 0), c64.of(beta),
+            C.c_void_p(y.data_ptr() if y is not None else 0), C.c_void_p(zadd.data_ptr() if zadd is not None else 0),
+            npeers, xp, yp, shift, int(sm_budget), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def mul_fused_(self, y, x, alpha=1.0, beta=0.0):
+        """Same result as mul_, with the exchange fused into the compute kernel: the remote-term pass reads x tiles from
+        the peers' slabs and writes its results into the owners' contribution buffers in ONE kernel over NVLink
+        (no staging copy, no NCCL), running beside the first group of local passes on its own share of the SMs; the last
+        local pass folds the received contributions in (zadd).  `x` must come from `empty_state()`."""
+        import torch
+
+        alpha, beta = complex(alpha), complex(beta)
+        if self.plan_swapped is None or alpha == 0:
+            return self.mul_(y, x, alpha, beta)
+        if x.data_ptr() not in self._symm:
+            raise _lib.ArgumentError("mul_fused_ needs a state allocated with empty_state() (symmetric memory)")
+        if self._zbuf is None:
+            self._zbuf = self.empty_state()
+            self._side = torch.cuda.Stream()
+        zh, zptrs, _ = self._symm[self._zbuf.data_ptr()]
+        _, xptrs, _ = self._symm[x.data_ptr()]
+        main = torch.cuda.current_stream()
+        total = torch.cuda.get_device_properties(x.device).multi_processor_count
+        k = max(4, min(self.swap_sms, total // 2))
+        two_groups = self.plan_local_b is not None
+        if self.overlap and two_groups:
+            side = self._side
+            side.wait_stream(main)                     # x is ready on this rank
+            with torch.cuda.stream(side):
+                zh.barrier(channel=0)                  # ... and on every rank; last call's contributions are consumed
+                self._apply_ex(self.plan_swapped, alpha, None, 0.0, None, peers=(xptrs, zptrs), sm_budget=k)
+                zh.barrier(channel=1)                  # every rank's contributions have landed
+            self._apply_ex(self.plan_local, alpha, x, beta, y, sm_budget=total - k)       # beside the exchange
+            main.wait_stream(side)
+            self._apply_ex(self.plan_local_b, alpha, x, 1.0, y, zadd=self._zbuf)
+        else:
+            zh.barrier(channel=0)
+            self._apply_ex(self.plan_swapped, alpha, None, 0.0, None, peers=(xptrs, zptrs))
+            zh.barrier(channel=1)
+            if two_groups:
+                self._apply_ex(self.plan_local, alpha, x, beta, y)
+                self._apply_ex(self.plan_local_b, alpha, x, 1.0, y, zadd=self._zbuf)
+            else:
+                self._apply_ex(self.plan_local, alpha, x, beta, y, zadd=self._zbuf)
+        return y
 
     def describe(self):
         buf = C.create_string_buffer(1 << 14)

@@ -81,6 +81,43 @@ def test_sharded_apply_all_ranks_on_one_gpu(world, n, beta):
     assert H.rel_err(got, oracle_result(n, spec, alpha, beta, xfull, yfull0)) <= 1e-12
 
 
+@pytest.mark.parametrize("world,n", [(2, 14), (4, 16), (8, 17)])
+@pytest.mark.parametrize("beta", [0.0, 0.5 + 0.25j])
+def test_fused_peer_exchange_all_ranks_on_one_gpu(world, n, beta):
+    """The PEER variant of the tile kernel (loads x tiles from the owners' slabs, stores contributions into the owners'
+    buffers) with every rank's slab living on ONE GPU: same addresses and kernels as over NVLink."""
+    import ctypes as C
+
+    import torch
+
+    import qob200 as Q
+    from qob200.dist import ShardedLazySum
+
+    p = world.bit_length() - 1
+    nloc = n - p
+    spec = chain_spec(n, 23)
+    xfull = O.fill_state(1 << n, 5, 2.0 ** (-n / 2))
+    yfull0 = O.fill_state(1 << n, 6, 1.0)
+    alpha = -0.3 + 0.9j
+    ranks = [ShardedLazySum(build_q(Q, n, spec), r, world) for r in range(world)]
+    xs = [torch.from_numpy(xfull[r << nloc:(r + 1) << nloc].copy()).cuda() for r in range(world)]
+    ys = [torch.from_numpy(yfull0[r << nloc:(r + 1) << nloc].copy()).cuda() for r in range(world)]
+    zs = [torch.full((1 << nloc,), float("nan"), dtype=torch.complex128, device="cuda") for _ in range(world)]
+    xptrs, zptrs = [t.data_ptr() for t in xs], [t.data_ptr() for t in zs]
+    for r, sh in enumerate(ranks):
+        sh._apply_ex(sh.plan_swapped, alpha, None, 0.0, None, peers=(xptrs, zptrs), sm_budget=8 + r)
+    torch.cuda.synchronize()
+    for r, sh in enumerate(ranks):
+        assert torch.isfinite(torch.view_as_real(zs[r])).all()   # every element written exactly once
+        if sh.plan_local_b is not None:
+            sh._apply_ex(sh.plan_local, alpha, xs[r], beta, ys[r], sm_budget=100)
+            sh._apply_ex(sh.plan_local_b, alpha, xs[r], 1.0, ys[r], zadd=zs[r])
+        else:
+            sh._apply_ex(sh.plan_local, alpha, xs[r], beta, ys[r], zadd=zs[r])
+    got = np.concatenate([y.cpu().numpy() for y in ys])
+    assert H.rel_err(got, oracle_result(n, spec, alpha, beta, xfull, yfull0)) <= 1e-12
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -89,7 +126,7 @@ def _free_port():
     return p
 
 
-def _nccl_worker(rank, world, port, n, beta, out_dir):
+def _nccl_worker(rank, world, port, n, beta, out_dir, fused):
     import torch
     import torch.distributed as dist
 
@@ -104,19 +141,22 @@ def _nccl_worker(rank, world, port, n, beta, out_dir):
         nloc = n - p
         spec = chain_spec(n, 21)
         sh = ShardedLazySum(build_q(Q, n, spec), rank, world)
-        x = torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
+        x = sh.empty_state() if fused else torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
         Q.fill_state(x, 3, 2.0 ** (-n / 2), offset=rank << nloc)
-        y = torch.empty_like(x)
+        y = torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
         Q.fill_state(y, 4, 1.0, offset=rank << nloc)
-        sh.mul_(y, x, 0.7 - 0.2j, beta)
+        for _ in range(2):   # twice: the second call reuses the contribution buffer
+            Q.fill_state(y, 4, 1.0, offset=rank << nloc)
+            (sh.mul_fused_ if fused else sh.mul_)(y, x, 0.7 - 0.2j, beta)
         torch.cuda.synchronize()
         np.save(os.path.join(out_dir, f"y{rank}.npy"), y.cpu().numpy())
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("beta", [0.0, 0.5 + 0.25j])
-def test_sharded_apply_nccl(tmp_path, beta):
+def test_sharded_apply_nccl(tmp_path, beta, fused):
     import torch
     import torch.multiprocessing as mp
 
@@ -126,7 +166,7 @@ def test_sharded_apply_nccl(tmp_path, beta):
     if world < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
     n = 18
-    mp.spawn(_nccl_worker, args=(world, _free_port(), n, beta, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, _free_port(), n, beta, str(tmp_path), fused), nprocs=world, join=True)
     got = np.concatenate([np.load(tmp_path / f"y{r}.npy") for r in range(world)])
     spec = chain_spec(n, 21)
     ref = oracle_result(n, spec, 0.7 - 0.2j, beta, O.fill_state(1 << n, 3, 2.0 ** (-n / 2)), O.fill_state(1 << n, 4, 1.0))
