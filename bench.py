@@ -268,10 +268,31 @@ def run_product_dist(args, rank, world, local_rank):
         else:
             sh.mul_(y, x, alpha, 0.0)
 
-    run_common(args, Q, rank, world, step, x, y, n, nloc, plan, warmup, args.steps, peak, peak_src, H, alpha, sharded=sh)
+    extra = {}
+    if rank == 0 and free > 5.5 * 16 * (1 << nloc):
+        # "1 GPU scaled": the same chain at the per-GPU slab size (N = nloc spins) on ONE GPU, timed in this run
+        B1, H1 = build_chain(Q, nloc)
+        x1, y1 = Q.Ket(B1), Q.Ket(B1)
+        Q.fill_state(x1.data, 7, 2.0 ** (-nloc / 2))
+        for _ in range(2):
+            Q.mul_(y1, H1, x1, alpha, 0.0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            Q.mul_(y1, H1, x1, alpha, 0.0)
+        e1.record()
+        torch.cuda.synchronize()
+        ms1 = e0.elapsed_time(e1) / 3
+        extra["single_gpu_same_slab"] = {"spins": nloc, "ms_per_step": ms1, "value": (1 << nloc) / (ms1 * 1e-3), "unit": UNIT,
+                                         "note": "one GPU working on a chain of the per-GPU slab size; weak-scaling efficiency = value / (n_gpus * this)"}
+        del x1, y1, H1
+        torch.cuda.empty_cache()
+    dist.barrier()
+    run_common(args, Q, rank, world, step, x, y, n, nloc, plan, warmup, args.steps, peak, peak_src, H, alpha, sharded=sh, extra=extra)
 
 
-def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps, peak, peak_src, H, alpha, sharded=None):
+def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps, peak, peak_src, H, alpha, sharded=None, extra=None):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -378,6 +399,10 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
         "gpu_launches": launches,
         "roofline": roofline,
     }
+    if extra:
+        line.update(extra)
+        if "single_gpu_same_slab" in extra:
+            line["weak_scaling_efficiency_vs_same_slab"] = value / (world * extra["single_gpu_same_slab"]["value"])
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(n, nterms)
     else:

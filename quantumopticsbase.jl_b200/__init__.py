@@ -9,8 +9,8 @@ from ._lib import (ArgumentError, CudaError, DimensionMismatch, IncompatibleBase
                    context, lib)
 from .operators import (Adjoint, Basis, Bra, CompositeBasis, DenseOperator, Eye, FockBasis, GenericBasis, Ket,
                         LazyProduct, LazySum, LazyTensor, NLevelBasis, Operator, SparseOperator, SpinBasis,
-                        apply_host, create, dagger, dense, describe, destroy, dot, fill_state, handle,
+                        apply_host, create, dagger, dense, describe, destroy, dot, expect, fill_state, handle,
                         identityoperator, launch_count, mul_, norm2, number, profile_enable, profile_read, randstate, sigmam, sigmap, sigmax,
-                        sigmay, sigmaz, sparse, tensor, transition)
+                        sigmay, sigmaz, sparse, tensor, transition, variance)
 
 mul = mul_  # `mul!`

@@ -102,8 +102,11 @@ __global__ void __launch_bounds__(32 * MW * NW)
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
           dmma884(cre[mb][nb][0], cre[mb][nb][1], are[mb], bre);
-          dmma884(cre[mb][nb][0], cre[mb][nb][1], naim[mb], bim);
           dmma884(cim[mb][nb][0], cim[mb][nb][1], are[mb], bim);
+        }
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          dmma884(cre[mb][nb][0], cre[mb][nb][1], naim[mb], bim);
           dmma884(cim[mb][nb][0], cim[mb][nb][1], aim[mb], bre);
         }
       }
@@ -135,37 +138,40 @@ __global__ void __launch_bounds__(32 * MW * NW)
   }
 }
 
-// ---- whole-K variant (dl, dr <= 64: every Fock/NLevel site factor of the BASELINE configs) ----------------
-// The factor A stays in shared memory for the lifetime of a persistent CTA, a full (K x 64) slab of x is staged per
-// tile, so there is ONE barrier pair per 64 output columns instead of two per 16-deep K slice; 12 warps (MW=3) with
-// 16x16 warp tiles and 2 CTAs/SM keep the DMMA pipe fed while the other CTA loads.
+// ---- whole-K, software-pipelined variant (dl, dr <= 64: every Fock/NLevel site factor of the BASELINE configs) ----
+// Persistent CTA, one per SM.  The factor A (interleaved re/im, row stride == 4 mod 8 complex -> conflict-free LDS.128
+// fragment loads that deliver re and im together) stays in shared memory; the (K x 64) slabs of x are double-buffered
+// with 16-byte cp.async (zero-fill for the ragged edges), so the DMMA pipe works on tile i while tile i+1 streams in.
+// Warp tile 16x16 (MW*4 warps), four real DMMA.8x8x4 per complex 8x8x4 block.
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, bool valid) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(gmem), "r"(sz));
+}
+
 template <int MW>
-__global__ void __launch_bounds__(MW * 128, 2)
-    axis_dmma_wk_kernel(const __grid_constant__ AxisParams P, const double2 *__restrict__ x, double2 *__restrict__ y,
-                        int kpad, int ldk) {
+__global__ void __launch_bounds__(MW * 128, 1)
+    axis_dmma_pipe_kernel(const __grid_constant__ AxisParams P, const double2 *__restrict__ x, double2 *__restrict__ y,
+                          int kpad, int ldx) {
   constexpr int TM = 16 * MW, TN = 64, NT = MW * 128;
-  extern __shared__ __align__(16) double smem_d[];
-  double *As_re = smem_d, *As_im = As_re + TM * ldk;
-  double *Xs_re = As_im + TM * ldk, *Xs_im = Xs_re + TN * ldk;
+  extern __shared__ __align__(16) double2 smem_c[];
+  double2 *As = smem_c;               // [TM][ldx]
+  double2 *Xs0 = As + TM * ldx;       // [2][TN][ldx]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp % MW, wn = warp / MW;  // wn in 0..3: 16 columns each
   const int g = lane >> 2, t = lane & 3;
   const bool n_fast = P.L >= 8;
 
   for (int e = tid; e < TM * kpad; e += NT) {
-    int i = e / kpad, k = e - i * kpad;
-    double re = 0.0, im = 0.0;
-    if (i < P.dl_pad && k < P.dr_pad) {
-      re = P.a_re[(long long)i * P.dr_pad + k];
-      im = P.a_im[(long long)i * P.dr_pad + k];
-    }
-    As_re[i * ldk + k] = re;
-    As_im[i * ldk + k] = im;
+    const int i = e / kpad, k = e - i * kpad;
+    double2 v = make_double2(0.0, 0.0);
+    if (i < P.dl_pad && k < P.dr_pad) v = make_double2(P.a_re[(long long)i * P.dr_pad + k], P.a_im[(long long)i * P.dr_pad + k]);
+    As[i * ldx + k] = v;
   }
   const long long ntiles = (P.N + TN - 1) / TN;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  auto issue = [&](long long tile, int buf) {
+    double2 *Xs = Xs0 + (size_t)buf * TN * ldx;
     const long long n0 = tile * TN;
-    __syncthreads();  // previous tile's fragments are no longer read (first iteration: orders the A stores)
     for (int e = tid; e < TN * kpad; e += NT) {
       int n, k;
       if (n_fast) {
@@ -175,44 +181,53 @@ __global__ void __launch_bounds__(MW * 128, 2)
         n = e / kpad;
         k = e - n * kpad;
       }
-      double2 v = make_double2(0.0, 0.0);
       const long long nn = n0 + n;
-      if (nn < P.N && k < P.dr) {
+      const bool valid = tile < ntiles && nn < P.N && k < P.dr;
+      long long src = 0;
+      if (valid) {
         const long long r = nn / P.L, l = nn - r * P.L;
-        v = x[l + P.L * ((long long)k + (long long)P.dr * r)];
+        src = l + P.L * ((long long)k + (long long)P.dr * r);
       }
-      Xs_re[n * ldk + k] = v.x;
-      Xs_im[n * ldk + k] = v.y;
+      cp_async16_zfill(Xs + n * ldx + k, x + src, valid);
     }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  long long tile = blockIdx.x;
+  int buf = 0;
+  issue(tile, 0);
+  for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    issue(tile + gridDim.x, buf ^ 1);                      // prefetch the next slab (an empty group past the end)
+    asm volatile("cp.async.wait_group 1;\n" ::);           // this tile's slab has landed
     __syncthreads();
+    const double2 *Xs = Xs0 + (size_t)buf * TN * ldx;
+    const long long n0 = tile * TN;
     double cre[2][2][2], cim[2][2][2];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < 2; ++b) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
+#pragma unroll 2
     for (int kk = 0; kk < kpad; kk += 4) {
-      double are[2], aim[2], naim[2], bre[2], bim[2];
+      double2 a[2], b[2];
 #pragma unroll
-      for (int mb = 0; mb < 2; ++mb) {
-        const int row = wm * 16 + mb * 8 + g;
-        are[mb] = As_re[row * ldk + kk + t];
-        aim[mb] = As_im[row * ldk + kk + t];
-        naim[mb] = -aim[mb];
-      }
+      for (int mb = 0; mb < 2; ++mb) a[mb] = As[(wm * 16 + mb * 8 + g) * ldx + kk + t];
 #pragma unroll
-      for (int nb = 0; nb < 2; ++nb) {
-        const int col = wn * 16 + nb * 8 + g;
-        bre[nb] = Xs_re[col * ldk + kk + t];
-        bim[nb] = Xs_im[col * ldk + kk + t];
-      }
+      for (int nb = 0; nb < 2; ++nb) b[nb] = Xs[(wn * 16 + nb * 8 + g) * ldx + kk + t];
+      // two sweeps over the 8 accumulators: the two updates of one accumulator are 8 DMMAs apart, so no DMMA waits
+      // for its predecessor (back-to-back dependent DMMAs halved the pipe utilisation: ncu 50 % -> see profiles/)
 #pragma unroll
       for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
-          dmma884(cre[mb][nb][0], cre[mb][nb][1], are[mb], bre[nb]);
-          dmma884(cre[mb][nb][0], cre[mb][nb][1], naim[mb], bim[nb]);
-          dmma884(cim[mb][nb][0], cim[mb][nb][1], are[mb], bim[nb]);
-          dmma884(cim[mb][nb][0], cim[mb][nb][1], aim[mb], bre[nb]);
+          dmma884(cre[mb][nb][0], cre[mb][nb][1], a[mb].x, b[nb].x);
+          dmma884(cim[mb][nb][0], cim[mb][nb][1], a[mb].x, b[nb].y);
+        }
+#pragma unroll
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          dmma884(cre[mb][nb][0], cre[mb][nb][1], -a[mb].y, b[nb].y);
+          dmma884(cim[mb][nb][0], cim[mb][nb][1], a[mb].y, b[nb].x);
         }
     }
 #pragma unroll
@@ -237,18 +252,20 @@ __global__ void __launch_bounds__(MW * 128, 2)
           y[addr] = o;
         }
     }
+    __syncthreads();  // everyone is done with this buffer before the next prefetch overwrites it
   }
+  asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
 template <int MW>
 static int launch_axis_wk(const AxisParams &P, const double2 *xp, double2 *yp, cudaStream_t s) {
   const int kpad = (P.dr + 3) / 4 * 4;
-  int ldk = kpad;
-  while (ldk % 16 != 4) ++ldk;  // conflict-free 64-bit fragment loads
-  const size_t smem = (size_t)2 * (16 * MW + 64) * ldk * sizeof(double);
+  int ldx = kpad;
+  while (ldx % 8 != 4) ++ldx;  // conflict-free LDS.128 fragment loads
+  const size_t smem = (size_t)(16 * MW + 2 * 64) * ldx * sizeof(double2);
   static size_t configured = 0;
   if (smem > configured) {
-    QOB_CUDA(cudaFuncSetAttribute(axis_dmma_wk_kernel<MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QOB_CUDA(cudaFuncSetAttribute(axis_dmma_pipe_kernel<MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   static int sms = 0;
@@ -258,8 +275,8 @@ static int launch_axis_wk(const AxisParams &P, const double2 *xp, double2 *yp, c
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const long long ntiles = (P.N + 63) / 64;
-  const long long grid = std::min<long long>(ntiles, 2ll * sms);
-  axis_dmma_wk_kernel<MW><<<(unsigned)grid, MW * 128, smem, s>>>(P, xp, yp, kpad, ldk);
+  const long long grid = std::min<long long>(ntiles, (long long)sms);
+  axis_dmma_pipe_kernel<MW><<<(unsigned)grid, MW * 128, smem, s>>>(P, xp, yp, kpad, ldx);
   return QOB_STATUS_OK;
 }
 

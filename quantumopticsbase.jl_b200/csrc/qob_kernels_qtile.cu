@@ -546,43 +546,102 @@ int qtile_build(QTileProgram &prog, int nbits, uint64_t hi_value, const std::vec
   std::vector<uint64_t> masks;
   for (auto &c : h->comps)
     if (c.mask && std::find(masks.begin(), masks.end(), c.mask) == masks.end()) masks.push_back(c.mask);
-  std::vector<uint64_t> free_sets;
-  free_sets.push_back((1ull << T) - 1);  // pass 0: the lowest T bits (fully contiguous tiles)
-  std::vector<uint64_t> remaining;
-  for (uint64_t m : masks)
-    if (m & ~free_sets[0]) remaining.push_back(m);
-  const uint64_t lowL = (1ull << L) - 1;
-  auto min_high = [&](uint64_t m) { uint64_t hgh = m & ~lowL; return hgh ? __builtin_ctzll(hgh) : 64; };
-  std::sort(remaining.begin(), remaining.end(), [&](uint64_t a, uint64_t b) {
-    int ha = min_high(a), hb = min_high(b);
-    if (ha != hb) return ha < hb;
-    return a < b;
-  });
-  while (!remaining.empty()) {
-    uint64_t fr = lowL;
-    std::vector<uint64_t> rest;
-    for (uint64_t m : remaining) {
-      if (__builtin_popcountll(fr | m) <= T) fr |= m;
-      else rest.push_back(m);
+  // Greedy cover for a given low-block width L and a cap on the number of free bits whose stride is >= one 2 MiB page
+  // (bit 17 and above): every such bit doubles the number of pages a tile touches (measured: 512 pages per operand
+  // cost ~25 % of a pass to TLB misses).  A small cost model picks the cheapest (L, cap) combination.
+  const int page_bit = 17;
+  auto cover = [&](int Lc, int cap, std::vector<uint64_t> &out) -> bool {
+    out.clear();
+    out.push_back((1ull << T) - 1);  // pass 0: the lowest T bits (fully contiguous tiles)
+    std::vector<uint64_t> remaining;
+    for (uint64_t m : masks)
+      if (m & ~out[0]) remaining.push_back(m);
+    const uint64_t lowL = (1ull << Lc) - 1, hiMask = ~((1ull << page_bit) - 1);
+    auto min_high = [&](uint64_t m) { uint64_t hgh = m & ~lowL; return hgh ? __builtin_ctzll(hgh) : 64; };
+    std::sort(remaining.begin(), remaining.end(), [&](uint64_t a, uint64_t b) {
+      int ha = min_high(a), hb = min_high(b);
+      if (ha != hb) return ha < hb;
+      return a < b;
+    });
+    while (!remaining.empty()) {
+      uint64_t fr = lowL;
+      std::vector<uint64_t> rest;
+      for (uint64_t m : remaining) {
+        const uint64_t u = fr | m;
+        if (__builtin_popcountll(u) <= T && __builtin_popcountll(u & hiMask) <= cap) fr = u;
+        else rest.push_back(m);
+      }
+      if (fr == lowL) return false;
+      for (int b = 0; b < nbits && __builtin_popcountll(fr) < T; ++b) fr |= 1ull << b;  // spare bits widen the low block
+      std::vector<uint64_t> rest2;
+      for (uint64_t m : rest)
+        if (m & ~fr) rest2.push_back(m);
+      remaining.swap(rest2);
+      out.push_back(fr);
     }
-    if (fr == lowL) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: a term does not fit one tile");
-    for (int b = 0; b < nbits && __builtin_popcountll(fr) < T; ++b) fr |= 1ull << b;  // spare bits widen the low block
-    std::vector<uint64_t> rest2;
-    for (uint64_t m : rest)
-      if (m & ~fr) rest2.push_back(m);
-    remaining.swap(rest2);
-    free_sets.push_back(fr);
+    return true;
+  };
+  auto plan_cost = [&](const std::vector<uint64_t> &fs) {
+    double cost = 32.0 / 4.1;  // pass 0 is bound by the shared-memory pipe, not by HBM
+    for (size_t p = 1; p < fs.size(); ++p) {
+      int low = 0;
+      while (low < nbits && (fs[p] >> low & 1)) ++low;
+      const double bw = low <= 3 ? 5.4 : (low == 4 ? 6.0 : 6.6);  // TB/s measured for 128 / 256 / >= 512-byte runs
+      const int hb = __builtin_popcountll(fs[p] & ~((1ull << page_bit) - 1));
+      const double tlb = hb <= 7 ? 1.0 : (hb == 8 ? 0.92 : 0.78);
+      cost += 48.0 / (bw * tlb);
+    }
+    return cost;
+  };
+  std::vector<uint64_t> free_sets;
+  {
+    double best = 1e300;
+    const bool forced = getenv("QOB_QTILE_L") != nullptr;
+    for (int Lc = forced ? L : 3; Lc <= (forced ? L : 5) && Lc <= T - 3; ++Lc)
+      for (int cap = 7; cap <= 9; ++cap) {
+        std::vector<uint64_t> fs;
+        if (!cover(Lc, cap, fs)) continue;
+        const double c = plan_cost(fs);
+        if (c < best - 1e-9) {
+          best = c;
+          free_sets = fs;
+          h->L = Lc;
+        }
+      }
+    if (free_sets.empty()) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: a term does not fit one tile");
+    L = h->L;
   }
 
-  // ---- assign components to passes (diagonal -> pass 0; others -> first pass containing the mask)
-  for (auto &c : h->comps) {
-    c.pass = -1;
-    for (size_t p = 0; p < free_sets.size(); ++p)
-      if ((c.mask & ~free_sets[p]) == 0) {
-        c.pass = (int)p;
-        break;
+  // ---- assign components to passes.  Diagonal weights go to pass 0.  An off-diagonal mask that fits several passes
+  // (bonds inside the low block, which every pass carries) goes to the least loaded one: pass 0 is bound by the
+  // shared-memory pipe (one gather per bond and amplitude) while the window passes have slack under their HBM time.
+  {
+    std::vector<int> load(free_sets.size(), 0);
+    std::map<uint64_t, int> mask_pass;
+    // masks with a single candidate first (they fix the loads), then the movable ones
+    for (int movable = 0; movable < 2; ++movable)
+      for (auto &c : h->comps) {
+        if (!c.mask) {
+          c.pass = 0;
+          continue;
+        }
+        std::vector<int> cand;
+        for (size_t p = 0; p < free_sets.size(); ++p)
+          if ((c.mask & ~free_sets[p]) == 0) cand.push_back((int)p);
+        if (cand.empty()) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: internal planner error (uncovered mask)");
+        if ((cand.size() > 1) != (movable == 1)) continue;
+        auto it = mask_pass.find(c.mask);
+        if (it != mask_pass.end()) {  // components that share a mask must share the gather
+          c.pass = it->second;
+          continue;
+        }
+        int best = cand[0];
+        for (int p : cand)
+          if (load[p] < load[best] || (load[p] == load[best] && p > best)) best = p;
+        c.pass = best;
+        mask_pass[c.mask] = best;
+        load[best]++;
       }
-    if (c.pass < 0) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: internal planner error (uncovered mask)");
   }
   for (size_t p = 0; p < free_sets.size(); ++p) {
     std::vector<int> free_bits;
@@ -883,9 +942,14 @@ int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta,
     }
     const bool rw = pp->real_weights && !getenv("QOB_QTILE_NO_REALW");
     const bool peer = o.npeers > 0;
+    // persistent CTAs (grid = SM budget x occupancy) unless a full grid is requested and no SM budget is in force
+    // (measured on N=28/30: one CTA per tile is ~15 % faster than grid-strided persistent CTAs, whose three resident CTAs
+    // per SM fall into lockstep; persistence is only used to confine the kernel to an SM budget)
+    static const bool env_persist = getenv("QOB_QTILE_PERSIST") && atoi(getenv("QOB_QTILE_PERSIST")) != 0;
+    const bool persist = env_persist || sms < sm_count;
 #define QT_CASE(TT, TH, MB)                                                                                     \
   case TT: {                                                                                                    \
-    const int ctas = sms * MB;                                                                                  \
+    const int ctas = persist ? sms * MB : 0x7FFFFFFF;                                                           \
     if (peer) {                                                                                                 \
       if (rw) QOB_TRY((launch_pass<TT, TH, MB, true, true, true>(h, *pp, P, x, y, ctas, s)));                  \
       else QOB_TRY((launch_pass<TT, TH, MB, true, false, true>(h, *pp, P, x, y, ctas, s)));                    \

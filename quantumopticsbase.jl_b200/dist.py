@@ -91,7 +91,9 @@ class ShardedLazySum:
         nterms = len(H.operators)
         od, al = C.c_uint64(), C.c_uint64()
         lowmask = (1 << self.nloc) - 1
-        split_bit = self.nloc // 2 + 3          # off-diagonal terms entirely below this bit -> group A
+        # off-diagonal terms entirely below split_bit -> group A (runs beside the exchange); the rest (one window pass
+        # over the top local bits) -> group B, which also folds the received contributions in
+        split_bit = int(os.environ.get("QOB_DIST_SPLIT_BIT", self.nloc - 6))
         sel = {k: (C.c_uint8 * max(nterms, 1))() for k in ("A", "B", "R")}
         touched = 0
         self.n_local = self.n_remote = 0

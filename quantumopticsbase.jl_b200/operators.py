@@ -710,6 +710,38 @@ def launch_count():
     return int(lib.qob_launch_count())
 
 
+def expect(op, state):
+    """expect(op, state) (src/operators.jl:119-142): <psi|op|psi> for a Ket, tr(op*rho) for a dense device Operator —
+    `mul!` into scratch followed by one device reduction (only the result crosses to the host)."""
+    import torch
+
+    if isinstance(state, Ket):
+        tmp = getattr(op, "_expect_tmp", None)
+        if tmp is None or tmp.basis != op.basis_l:
+            tmp = Ket(op.basis_l)
+            op._expect_tmp = tmp
+        mul_(tmp, op, state, 1.0, 0.0)
+        return dot(state.data, tmp.data)
+    if _is_state_op(state):
+        tmp = DenseOperator(op.basis_l, state.basis_r)
+        mul_(tmp, op, state, 1.0, 0.0)
+        return complex(torch.diagonal(tmp.data).sum().item())
+    raise MethodError(f"expect: unsupported state type {type(state).__name__}")
+
+
+def variance(op, state):
+    """variance(op, state) = <op^2> - <op>^2 (src/operators.jl:139-150), as ||op psi||^2 - |<op>|^2 ... for a Ket
+    computed with two mul! applications like the reference (op*(op*state))."""
+    if not isinstance(state, Ket):
+        raise MethodError("variance: only Ket states are supported on the device path")
+    t1, t2 = Ket(op.basis_l), Ket(op.basis_l)
+    mul_(t1, op, state, 1.0, 0.0)
+    mul_(t2, op, t1, 1.0, 0.0)
+    e1 = dot(state.data, t1.data)
+    e2 = dot(state.data, t2.data)
+    return e2 - e1 * e1
+
+
 def profile_enable(on=True):
     _lib.check(lib.qob_profile_enable(1 if on else 0))
 

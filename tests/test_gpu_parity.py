@@ -361,3 +361,23 @@ def test_apply_host_end_to_end(Q):
     O.mul(ref.o, s.o, H.ket(dims, x).o, 1.0, 0.0)
     y = Q.apply_host(s.q, x)
     assert H.rel_err(y, ref.o.data) <= TOL
+
+
+def test_expect_and_variance(Q):
+    """expect / variance built on mul! + a device reduction (src/operators.jl:119-150)."""
+    rng = np.random.default_rng(95)
+    dims, coefs, terms = _chain_terms(11, "heis", False, rng)
+    s = H.lazysum(dims, dims, coefs, terms)
+    x = H.rnd(rng, 1 << 11)
+    x /= np.linalg.norm(x)
+    Dm = O.dense(s.o)
+    k = H.ket(dims, x).q
+    e = Q.expect(s.q, k)
+    ref = np.vdot(x, Dm @ x)
+    assert abs(e - ref) <= 1e-12 * max(1.0, abs(ref))
+    v = Q.variance(s.q, k)
+    refv = np.vdot(x, Dm @ (Dm @ x)) - ref * ref
+    assert abs(v - refv) <= 1e-11 * max(1.0, abs(refv))
+    rho = np.outer(x, x.conj())
+    er = Q.expect(s.q, H.denseop(dims, dims, rho).q)
+    assert abs(er - ref) <= 1e-12 * max(1.0, abs(ref))
