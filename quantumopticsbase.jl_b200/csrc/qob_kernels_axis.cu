@@ -143,6 +143,22 @@ __global__ void __launch_bounds__(32 * MW * NW)
 // fragment loads that deliver re and im together) stays in shared memory; the (K x 64) slabs of x are double-buffered
 // with 16-byte cp.async (zero-fill for the ragged edges), so the DMMA pipe works on tile i while tile i+1 streams in.
 // Warp tile 16x16 (MW*4 warps), four real DMMA.8x8x4 per complex 8x8x4 block.
+// (l, r) of GEMM column n0 + j (j < 64) given (l0, r0) of column n0: no 64-bit division in the inner loops
+// (the per-element `nn / L` divisions cost ~40 % of the kernel: ~120 instructions each on the integer pipe)
+__device__ __forceinline__ void split_col(unsigned j, unsigned l0, long long r0, long long L, unsigned &l, long long &r) {
+  if (L >= 64) {  // at most one wrap
+    const unsigned long long t = (unsigned long long)l0 + j;
+    const bool w = t >= (unsigned long long)L;
+    l = (unsigned)(w ? t - (unsigned long long)L : t);
+    r = r0 + (w ? 1 : 0);
+  } else {        // small L: 32-bit division of a number < 128
+    const unsigned t = l0 + j, Ls = (unsigned)L;
+    const unsigned q = t / Ls;
+    l = t - q * Ls;
+    r = r0 + q;
+  }
+}
+
 __device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, bool valid) {
   const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem);
   const int sz = valid ? 16 : 0;
@@ -172,6 +188,8 @@ __global__ void __launch_bounds__(MW * 128, 1)
   auto issue = [&](long long tile, int buf) {
     double2 *Xs = Xs0 + (size_t)buf * TN * ldx;
     const long long n0 = tile * TN;
+    const long long r0 = n0 / P.L;                       // one 64-bit division per tile (warp-uniform)
+    const unsigned l0 = (unsigned)(n0 - r0 * P.L);
     for (int e = tid; e < TN * kpad; e += NT) {
       int n, k;
       if (n_fast) {
@@ -185,8 +203,10 @@ __global__ void __launch_bounds__(MW * 128, 1)
       const bool valid = tile < ntiles && nn < P.N && k < P.dr;
       long long src = 0;
       if (valid) {
-        const long long r = nn / P.L, l = nn - r * P.L;
-        src = l + P.L * ((long long)k + (long long)P.dr * r);
+        unsigned l;
+        long long r;
+        split_col((unsigned)n, l0, r0, P.L, l, r);
+        src = (long long)l + P.L * ((long long)k + (long long)P.dr * r);
       }
       cp_async16_zfill(Xs + n * ldx + k, x + src, valid);
     }
@@ -201,6 +221,8 @@ __global__ void __launch_bounds__(MW * 128, 1)
     __syncthreads();
     const double2 *Xs = Xs0 + (size_t)buf * TN * ldx;
     const long long n0 = tile * TN;
+    const long long er0 = n0 / P.L;
+    const unsigned el0 = (unsigned)(n0 - er0 * P.L);
     double cre[2][2][2], cim[2][2][2];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -238,10 +260,12 @@ __global__ void __launch_bounds__(MW * 128, 1)
       for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const long long nn = n0 + wn * 16 + nb * 8 + 2 * t + e;
-          if (nn >= P.N) continue;
-          const long long r = nn / P.L, l = nn - r * P.L;
-          const long long addr = l + P.L * ((long long)i + (long long)P.dl * r);
+          const unsigned j = wn * 16 + nb * 8 + 2 * t + e;
+          if (n0 + j >= P.N) continue;
+          unsigned l;
+          long long r;
+          split_col(j, el0, er0, P.L, l, r);
+          const long long addr = (long long)l + P.L * ((long long)i + (long long)P.dl * r);
           const double ar = cre[mb][nb][e], ai = cim[mb][nb][e];
           double2 o = make_double2(P.alpha.x * ar - P.alpha.y * ai, P.alpha.x * ai + P.alpha.y * ar);
           if (!P.beta_zero) {

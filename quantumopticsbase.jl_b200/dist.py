@@ -139,6 +139,7 @@ class ShardedLazySum:
         self._symm = {}
         self._zbuf = None
         self.swap_sms = int(os.environ.get("QOB_DIST_SWAP_SMS", "32")) if swap_sms is None else int(swap_sms)
+        self.local_budget = int(os.environ.get("QOB_DIST_LOCAL_SMS", "0"))   # 0: full grid (one CTA per tile)
 
     # ------------------------------------------------------------------ fused exchange over NVLink peer memory
     def empty_state(self, device=None):
@@ -186,7 +187,7 @@ class ShardedLazySum:
             raise _lib.ArgumentError("mul_fused_ needs a state allocated with empty_state() (symmetric memory)")
         if self._zbuf is None:
             self._zbuf = self.empty_state()
-            self._side = torch.cuda.Stream()
+            self._side = torch.cuda.Stream(priority=-1)   # the exchange kernel's CTAs get free SM slots first
         zh, zptrs, _ = self._symm[self._zbuf.data_ptr()]
         _, xptrs, _ = self._symm[x.data_ptr()]
         main = torch.cuda.current_stream()
@@ -200,7 +201,9 @@ class ShardedLazySum:
                 zh.barrier(channel=0)                  # ... and on every rank; last call's contributions are consumed
                 self._apply_ex(self.plan_swapped, alpha, None, 0.0, None, peers=(xptrs, zptrs), sm_budget=k)
                 zh.barrier(channel=1)                  # every rank's contributions have landed
-            self._apply_ex(self.plan_local, alpha, x, beta, y, sm_budget=total - k)       # beside the exchange
+            # beside the exchange: the local passes use a full grid; the exchange kernel is persistent with k*occupancy
+            # CTAs on a high-priority stream, so it keeps its share of the slots while local CTAs come and go
+            self._apply_ex(self.plan_local, alpha, x, beta, y, sm_budget=self.local_budget)
             main.wait_stream(side)
             self._apply_ex(self.plan_local_b, alpha, x, 1.0, y, zadd=self._zbuf)
         else:
