@@ -309,7 +309,7 @@ int TensorGroup::compile(int side, int64_t batch, Compiled **out) {
   const bool qt_ok = all2 && qt_batch_ok && nbits >= qt_min_bits && nbits <= 62 && !env_i("QOB_DISABLE_QTILE", 0);
 
   std::vector<QTerm> qterms;
-  std::vector<OrientedTerm> gterms;
+  std::vector<OrientedTerm> gterms, q_as_g;
   for (const GroupTerm &t : terms) {
     OrientedTerm o;
     o.coef_index = t.coef_index;
@@ -391,13 +391,21 @@ int TensorGroup::compile(int side, int64_t batch, Compiled **out) {
           for (int j = 0; j < 2; ++j) q.m.push_back(o.mats[f].at(i, j));
       }
       qterms.push_back(std::move(q));
+      q_as_g.push_back(std::move(o));
     } else {
       gterms.push_back(std::move(o));
     }
   }
   if (!qterms.empty()) {
-    QOB_TRY(qtile_build(c.qtile, nbits, 0, qterms, ctx->sm_count));
-    c.has_qtile = true;
+    const int st = qtile_build(c.qtile, nbits, 0, qterms, ctx->sm_count);
+    if (st == QOB_STATUS_UNSUPPORTED) {
+      // the tile planner declined (selector bits too scattered, too many shared-mask lookups, ...): the generic fused
+      // kernel computes the same map
+      for (auto &o : q_as_g) gterms.push_back(std::move(o));
+    } else {
+      QOB_TRY(st);
+      c.has_qtile = true;
+    }
   }
   if (!gterms.empty()) {
     QOB_TRY(gather_program_build(c.gather, c.dims_out, c.dims_in, gterms));

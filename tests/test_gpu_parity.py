@@ -381,3 +381,22 @@ def test_expect_and_variance(Q):
     rho = np.outer(x, x.conj())
     er = Q.expect(s.q, H.denseop(dims, dims, rho).q)
     assert abs(er - ref) <= 1e-12 * max(1.0, abs(ref))
+
+
+def test_tile_planner_declines_and_generic_kernel_takes_over(Q, monkeypatch):
+    """78 terms X_1 Z_j Z_k share one flip mask with 78 different selector sets: more shared-mask lookups than one tile pass
+    carries -> the planner declines and the generic fused kernel computes the same map."""
+    monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    rng = np.random.default_rng(96)
+    n = 14
+    dims = (2,) * n
+    sx, _, sz = _pauli()
+    terms, coefs = [], []
+    for j in range(2, n + 1):
+        for k in range(j + 1, n + 1):
+            terms.append(H.lazytensor(dims, dims, [1, j, k], [sp.csc_matrix(sx), sp.csc_matrix(sz), sp.csc_matrix(sz)]))
+            coefs.append(rng.uniform(-1, 1))
+    s = H.lazysum(dims, dims, coefs, terms)
+    d = Q.describe(s.q)
+    assert "qtile" not in d and "gather" in d, d
+    H.check_mul(s, dims, dims, rng, tol=TOL, kinds=("ket",), scalars=((1, 0), (1.5, 2.1)))
