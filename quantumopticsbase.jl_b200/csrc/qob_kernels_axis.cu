@@ -165,16 +165,18 @@ __device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, b
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(gmem), "r"(sz));
 }
 
-template <int MW>
-__global__ void __launch_bounds__(MW * 128, 1)
+template <int MW, int NB>
+__global__ void __launch_bounds__(MW * 128, (NB == 1 && MW <= 3) ? 2 : 1)
     axis_dmma_pipe_kernel(const __grid_constant__ AxisParams P, const double2 *__restrict__ x, double2 *__restrict__ y,
                           int kpad, int ldx) {
-  constexpr int TM = 16 * MW, TN = 64, NT = MW * 128;
+  // NB = 8-column blocks per warp: NB = 2 -> 64-column slabs, one CTA per SM; NB = 1 -> 32-column slabs, half the
+  // shared memory and registers, TWO CTAs per SM so that one CTA's epilogue / barrier waits overlap the other's DMMAs
+  constexpr int TM = 16 * MW, TN = 32 * NB, NT = MW * 128;
   extern __shared__ __align__(16) double2 smem_c[];
   double2 *As = smem_c;               // [TM][ldx]
   double2 *Xs0 = As + TM * ldx;       // [2][TN][ldx]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = warp % MW, wn = warp / MW;  // wn in 0..3: 16 columns each
+  const int wm = warp % MW, wn = warp / MW;  // wn in 0..3: 8*NB columns each
   const int g = lane >> 2, t = lane & 3;
   const bool n_fast = P.L >= 8;
 
@@ -185,13 +187,14 @@ __global__ void __launch_bounds__(MW * 128, 1)
     As[i * ldx + k] = v;
   }
   const long long ntiles = (P.N + TN - 1) / TN;
-  auto issue = [&](long long tile, int buf) {
-    double2 *Xs = Xs0 + (size_t)buf * TN * ldx;
-    const long long n0 = tile * TN;
-    const long long r0 = n0 / P.L;                       // one 64-bit division per tile (warp-uniform)
-    const unsigned l0 = (unsigned)(n0 - r0 * P.L);
-    for (int e = tid; e < TN * kpad; e += NT) {
-      int n, k;
+  // which (column n, row k) elements of a slab this thread stages: independent of the tile, so the divisions happen once
+  constexpr int MAXE = (TN * 64 + NT - 1) / NT;
+  unsigned short en[MAXE], ek[MAXE];
+#pragma unroll
+  for (int i = 0; i < MAXE; ++i) {
+    const int e = tid + i * NT;
+    int n = 0, k = 0x7fff;  // k out of range -> zero fill
+    if (e < TN * kpad) {
       if (n_fast) {
         k = e / TN;
         n = e - k * TN;
@@ -199,16 +202,35 @@ __global__ void __launch_bounds__(MW * 128, 1)
         n = e / kpad;
         k = e - n * kpad;
       }
-      const long long nn = n0 + n;
-      const bool valid = tile < ntiles && nn < P.N && k < P.dr;
-      long long src = 0;
-      if (valid) {
-        unsigned l;
-        long long r;
-        split_col((unsigned)n, l0, r0, P.L, l, r);
-        src = (long long)l + P.L * ((long long)k + (long long)P.dr * r);
+    }
+    en[i] = (unsigned short)n;
+    ek[i] = (unsigned short)k;
+  }
+  const int nelem = (TN * kpad + NT - 1) / NT;
+  auto issue = [&](long long tile, int buf) {
+    double2 *Xs = Xs0 + (size_t)buf * TN * ldx;
+    const long long n0 = tile * TN;
+    const long long r0 = n0 / P.L;                       // one 64-bit division per tile (warp-uniform)
+    const unsigned l0 = (unsigned)(n0 - r0 * P.L);
+#pragma unroll
+    for (int i = 0; i < MAXE; ++i) {
+      if (i < nelem && ek[i] != 0x7fff) {
+        const int n = en[i], k = ek[i];
+        const bool valid = tile < ntiles && n0 + n < P.N && k < P.dr;
+        long long src = 0;
+        if (valid) {
+          unsigned l;
+          long long r;
+          if (P.L == 1) {
+            l = 0;
+            r = n0 + n;
+          } else {
+            split_col((unsigned)n, l0, r0, P.L, l, r);
+          }
+          src = (long long)l + P.L * ((long long)k + (long long)P.dr * r);
+        }
+        cp_async16_zfill(Xs + n * ldx + k, x + src, valid);
       }
-      cp_async16_zfill(Xs + n * ldx + k, x + src, valid);
     }
     asm volatile("cp.async.commit_group;\n" ::);
   };
@@ -223,31 +245,31 @@ __global__ void __launch_bounds__(MW * 128, 1)
     const long long n0 = tile * TN;
     const long long er0 = n0 / P.L;
     const unsigned el0 = (unsigned)(n0 - er0 * P.L);
-    double cre[2][2][2], cim[2][2][2];
+    double cre[2][NB][2], cim[2][NB][2];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int b = 0; b < 2; ++b) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
+      for (int b = 0; b < NB; ++b) cre[a][b][0] = cre[a][b][1] = cim[a][b][0] = cim[a][b][1] = 0.0;
 #pragma unroll 2
     for (int kk = 0; kk < kpad; kk += 4) {
-      double2 a[2], b[2];
+      double2 a[2], b[NB];
 #pragma unroll
       for (int mb = 0; mb < 2; ++mb) a[mb] = As[(wm * 16 + mb * 8 + g) * ldx + kk + t];
 #pragma unroll
-      for (int nb = 0; nb < 2; ++nb) b[nb] = Xs[(wn * 16 + nb * 8 + g) * ldx + kk + t];
+      for (int nb = 0; nb < NB; ++nb) b[nb] = Xs[(wn * 8 * NB + nb * 8 + g) * ldx + kk + t];
       // two sweeps over the 8 accumulators: the two updates of one accumulator are 8 DMMAs apart, so no DMMA waits
       // for its predecessor (back-to-back dependent DMMAs halved the pipe utilisation: ncu 50 % -> see profiles/)
 #pragma unroll
       for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
+        for (int nb = 0; nb < NB; ++nb) {
           dmma884(cre[mb][nb][0], cre[mb][nb][1], a[mb].x, b[nb].x);
           dmma884(cim[mb][nb][0], cim[mb][nb][1], a[mb].x, b[nb].y);
         }
 #pragma unroll
       for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-        for (int nb = 0; nb < 2; ++nb) {
+        for (int nb = 0; nb < NB; ++nb) {
           dmma884(cre[mb][nb][0], cre[mb][nb][1], -a[mb].y, b[nb].y);
           dmma884(cim[mb][nb][0], cim[mb][nb][1], a[mb].y, b[nb].x);
         }
@@ -257,10 +279,10 @@ __global__ void __launch_bounds__(MW * 128, 1)
       const int i = wm * 16 + mb * 8 + g;
       if (i >= P.dl) continue;
 #pragma unroll
-      for (int nb = 0; nb < 2; ++nb)
+      for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const unsigned j = wn * 16 + nb * 8 + 2 * t + e;
+          const unsigned j = wn * 8 * NB + nb * 8 + 2 * t + e;
           if (n0 + j >= P.N) continue;
           unsigned l;
           long long r;
@@ -281,27 +303,36 @@ __global__ void __launch_bounds__(MW * 128, 1)
   asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
-template <int MW>
-static int launch_axis_wk(const AxisParams &P, const double2 *xp, double2 *yp, cudaStream_t s) {
+template <int MW, int NB>
+static int launch_axis_pipe(const AxisParams &P, const double2 *xp, double2 *yp, int sms, cudaStream_t s) {
+  constexpr int TN = 32 * NB;
   const int kpad = (P.dr + 3) / 4 * 4;
   int ldx = kpad;
   while (ldx % 8 != 4) ++ldx;  // conflict-free LDS.128 fragment loads
-  const size_t smem = (size_t)(16 * MW + 2 * 64) * ldx * sizeof(double2);
+  const size_t smem = (size_t)(16 * MW + 2 * TN) * ldx * sizeof(double2);
   static size_t configured = 0;
   if (smem > configured) {
-    QOB_CUDA(cudaFuncSetAttribute(axis_dmma_pipe_kernel<MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QOB_CUDA(cudaFuncSetAttribute(axis_dmma_pipe_kernel<MW, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  const int per_sm = (NB == 1 && MW <= 3 && 2 * (smem + 1024) <= 227 * 1024) ? 2 : 1;
+  const long long ntiles = (P.N + TN - 1) / TN;
+  const long long grid = std::min<long long>(ntiles, (long long)sms * per_sm);
+  axis_dmma_pipe_kernel<MW, NB><<<(unsigned)grid, MW * 128, smem, s>>>(P, xp, yp, kpad, ldx);
+  return QOB_STATUS_OK;
+}
+
+template <int MW>
+static int launch_axis_wk(const AxisParams &P, const double2 *xp, double2 *yp, cudaStream_t s) {
   static int sms = 0;
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const long long ntiles = (P.N + 63) / 64;
-  const long long grid = std::min<long long>(ntiles, (long long)sms);
-  axis_dmma_pipe_kernel<MW><<<(unsigned)grid, MW * 128, smem, s>>>(P, xp, yp, kpad, ldx);
-  return QOB_STATUS_OK;
+  static const int nb_env = getenv("QOB_AXIS_NB") ? atoi(getenv("QOB_AXIS_NB")) : 1;
+  if (nb_env == 2) return launch_axis_pipe<MW, 2>(P, xp, yp, sms, s);
+  return launch_axis_pipe<MW, 1>(P, xp, yp, sms, s);
 }
 
 int prepare_axis_matrix(const HostMat &m, AxisMatrixDev &out) {

@@ -39,11 +39,18 @@ class Basis:
     def _key(self):
         return (type(self).__name__, self.shape)
 
+    def _ckey(self):
+        k = getattr(self, "_cached_key", None)   # bases are immutable: the key is computed once
+        if k is None:
+            k = self._key()
+            self._cached_key = k
+        return k
+
     def __eq__(self, other):
-        return isinstance(other, Basis) and self._key() == other._key()
+        return self is other or (isinstance(other, Basis) and self._ckey() == other._ckey())
 
     def __hash__(self):
-        return hash(self._key())
+        return hash(self._ckey())
 
     def __repr__(self):
         return f"{type(self).__name__}{self._key()[1:]}"
@@ -86,7 +93,7 @@ class CompositeBasis(Basis):
         super().__init__(tuple(len(b) for b in self.bases))
 
     def _key(self):
-        return ("CompositeBasis", tuple(b._key() for b in self.bases))
+        return ("CompositeBasis", tuple(b._ckey() for b in self.bases))
 
 
 def tensor(*xs):
@@ -500,11 +507,11 @@ def handle(op, ctx=None):
 def _refresh_coefs(op: LazySum):
     if len(op.factors) != len(op.operators):
         raise ArgumentError("LazySum `operators` and `factors` have different lengths.")
-    if getattr(op, "_sent_factors", None) != [complex(f) for f in op.factors]:
+    if getattr(op, "_sent_factors", None) != op.factors:
         n = len(op.factors)
         cf = (c64 * max(n, 1))(*[c64.of(f) for f in op.factors])
         _lib.check(lib.qob_lazysum_set_coefs(op._handle, n, cf))
-        op._sent_factors = [complex(f) for f in op.factors]
+        op._sent_factors = list(op.factors)
     for o in op.operators:
         if isinstance(o, LazySum) and getattr(o, "_handle", None):
             _refresh_coefs(o)
@@ -539,6 +546,8 @@ def mul_(result, a, b, alpha=1.0, beta=0.0):
       Op   <- DenseOp * op                 (:593, :227, :148, sparse:200)
     alpha/beta: any Python number (bool/int/float/complex), promoted to ComplexF64."""
     alpha, beta = complex(alpha), complex(beta)
+    if _is_state_op(a) and (_is_state_op(b) or isinstance(b, Ket)) or (isinstance(a, Bra) and _is_state_op(b)):
+        return _dense_device_mul(result, a, b, alpha, beta)
     if isinstance(b, Ket) and isinstance(a, AbstractOperator):
         if not isinstance(result, Ket):
             raise MethodError("result must be a Ket")
@@ -574,6 +583,29 @@ def mul_(result, a, b, alpha=1.0, beta=0.0):
     h = handle(op)
     _lib.check(lib.qob_op_apply(h, side, c64.of(alpha), C.c_void_p(state.data.data_ptr()), c64.of(beta),
                                 C.c_void_p(result.data.data_ptr()), int(batch), _stream()))
+    return result
+
+
+def _dense_device_mul(result, a, b, alpha, beta):
+    """Dense x dense on device data: the reference forwards `.data` to BLAS (src/operators_dense.jl:394-396), and so does
+    this: a plain library GEMM/GEMV (cuBLAS zgemm/zgemv through torch), not one of this repository's kernels.  With
+    CuArray-backed data the Julia side needs no glue at all for these three methods (CUDA.jl's mul! is cuBLAS)."""
+    import torch
+
+    if _is_state_op(a) and _is_state_op(b):
+        if a.basis_r != b.basis_l or result.basis_l != a.basis_l or result.basis_r != b.basis_r:
+            raise IncompatibleBases() if a.data.shape[1] == b.data.shape[0] else DimensionMismatch("A and B dimensions do not match")
+        if result.data.data_ptr() in (a.data.data_ptr(), b.data.data_ptr()):
+            raise ArgumentError("output matrix must not be aliased with input matrix")
+        torch.addmm(result.data, a.data, b.data, beta=beta, alpha=alpha, out=result.data)
+    elif _is_state_op(a):   # Ket <- dense Operator * Ket
+        if a.basis_r != b.basis or result.basis != a.basis_l:
+            raise IncompatibleBases() if a.data.shape[1] == b.data.numel() else DimensionMismatch("A and B dimensions do not match")
+        torch.addmv(result.data, a.data, b.data, beta=beta, alpha=alpha, out=result.data)
+    else:                   # Bra <- Bra * dense Operator: mul!(result.data, transpose(b.data), a.data, alpha, beta)
+        if a.basis != b.basis_l or result.basis != b.basis_r:
+            raise IncompatibleBases() if a.data.numel() == b.data.shape[0] else DimensionMismatch("A and B dimensions do not match")
+        torch.addmv(result.data, b.data.t(), a.data, beta=beta, alpha=alpha, out=result.data)
     return result
 
 

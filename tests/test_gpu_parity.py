@@ -400,3 +400,78 @@ def test_tile_planner_declines_and_generic_kernel_takes_over(Q, monkeypatch):
     d = Q.describe(s.q)
     assert "qtile" not in d and "gather" in d, d
     H.check_mul(s, dims, dims, rng, tol=TOL, kinds=("ket",), scalars=((1, 0), (1.5, 2.1)))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_qtile_random_term_sets_vs_oracle(Q, monkeypatch, seed):
+    """Property-style sweep over the tile planner's corner cases: random chain lengths, tile sizes, 1-3-site terms on
+    random sites with random dense / sparse / diagonal / adjoint 2x2 factors, repeated site sets (shared masks)."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(12, 17))
+    T = int(rng.integers(10, min(n, 13) + 1))
+    monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    monkeypatch.setenv("QOB_QTILE_T", str(T))
+    dims = (2,) * n
+    terms, coefs = [], []
+    site_sets = []
+    for _ in range(int(rng.integers(5, 30))):
+        k = int(rng.integers(1, 4))
+        if site_sets and rng.uniform() < 0.3:
+            idx = site_sets[int(rng.integers(len(site_sets)))]   # same sites again -> shared masks / selector sets
+        else:
+            idx = sorted(int(v) for v in rng.choice(np.arange(1, n + 1), size=k, replace=False))
+            site_sets.append(idx)
+        datas = []
+        for _s in idx:
+            kind = rng.integers(4)
+            m = H.rnd(rng, 2, 2)
+            if kind == 0:
+                datas.append(m)
+            elif kind == 1:
+                datas.append(sp.csc_matrix(m * (rng.uniform(0, 1, (2, 2)) < 0.6)))
+            elif kind == 2:
+                datas.append(sp.csc_matrix(np.diag(np.diag(m))))
+            else:
+                datas.append(("adj", m))
+        terms.append(H.lazytensor(dims, dims, idx, datas, H.rnd(rng, 1)[0]))
+        coefs.append(H.rnd(rng, 1)[0])
+    s = H.lazysum(dims, dims, coefs, terms)
+    H.check_mul(s, dims, dims, rng, tol=TOL, kinds=("ket", "bra"), scalars=((1, 0), (0.3 - 0.2j, 1.7)))
+
+
+@pytest.mark.parametrize("n", [9, 10])
+def test_qtile_density_matrix_commutator(Q, monkeypatch, n):
+    """-i[H, rho] on a full 2^n x 2^n density matrix: left and right application run as tile passes over 2n index bits."""
+    monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    rng = np.random.default_rng(77 + n)
+    dims, coefs, terms = _chain_terms(n, "heis", False, rng)
+    s = H.lazysum(dims, dims, coefs, terms)
+    D = 1 << n
+    assert "qtile[bits=%d" % (2 * n) in Q.describe(s.q, "left", D) and "qtile[bits=%d" % (2 * n) in Q.describe(s.q, "right", D)
+    rho = H.rnd(rng, D, D)
+    st, r = H.denseop(dims, dims, rho), H.denseop(dims, dims, np.zeros((D, D), dtype=complex))
+    O.mul(r.o, s.o, st.o, -1j, 0)
+    O.mul(r.o, st.o, s.o, 1j, 1)
+    Q.mul_(r.q, s.q, st.q, -1j, 0)
+    Q.mul_(r.q, st.q, s.q, 1j, 1)
+    assert H.rel_err(r.q.to_host(), r.o.data) <= TOL
+
+
+def test_dense_device_times_dense_device_is_library_gemm(Q):
+    """operators_dense.jl:394-396: dense x dense goes to BLAS in the reference, to cuBLAS (through torch) here."""
+    rng = np.random.default_rng(97)
+    a, b, r0 = H.rnd(rng, 6, 5), H.rnd(rng, 5, 7), H.rnd(rng, 6, 7)
+    A, B_, R = H.denseop((6,), (5,), a), H.denseop((5,), (7,), b), H.denseop((6,), (7,), r0)
+    Q.mul_(R.q, A.q, B_.q, 1.5, 2.1)
+    assert H.rel_err(R.q.to_host(), 1.5 * a @ b + 2.1 * r0) <= TOL
+    R = H.denseop((6,), (7,), r0 * np.nan)
+    Q.mul_(R.q, A.q, B_.q, 1.0, 0.0)
+    assert H.rel_err(R.q.to_host(), a @ b) <= TOL
+    x, y0 = H.rnd(rng, 5), H.rnd(rng, 6)
+    k, out = H.ket((5,), x), H.ket((6,), y0)
+    Q.mul_(out.q, A.q, k.q, -1j, 0.5)
+    assert H.rel_err(out.q.to_host(), -1j * a @ x + 0.5 * y0) <= TOL
+    xb, yb0 = H.rnd(rng, 6), H.rnd(rng, 5)
+    bb, outb = H.bra((6,), xb), H.bra((5,), yb0)
+    Q.mul_(outb.q, bb.q, A.q, 2.0, 1.0)
+    assert H.rel_err(outb.q.to_host(), 2.0 * xb @ a + yb0) <= TOL
