@@ -31,6 +31,8 @@ struct GatherParams {
   long long d_out, d_in, pre, post;
   double2 alpha, beta;
   int beta_zero;
+  int tpo;  // threads per output element (power of two <= 32): small states split the TERMS of the sum over the lanes of a
+            // group and reduce with shuffles, which shortens the per-thread chain of dependent loads (launch-latency regime)
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -48,12 +50,14 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherParams p, const doubl
                                                      double2 *__restrict__ y) {
   const IdxT total = (IdxT)(p.pre * p.d_out * p.post);
   const IdxT pre = (IdxT)p.pre, d_out = (IdxT)p.d_out;
-  for (IdxT idx = (IdxT)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IdxT)gridDim.x * blockDim.x) {
+  const unsigned tpo = (unsigned)p.tpo, sub = threadIdx.x & (tpo - 1);
+  const unsigned gmask = tpo >= 32 ? 0xffffffffu : (((1u << tpo) - 1u) << ((threadIdx.x & 31u) & ~(tpo - 1)));
+  for (IdxT idx = ((IdxT)blockIdx.x * blockDim.x + threadIdx.x) / tpo; idx < total; idx += ((IdxT)gridDim.x * blockDim.x) / tpo) {
     IdxT r = idx % pre, t1 = idx / pre;
     IdxT I = t1 % d_out, c = t1 / d_out;
     const double2 *xb = x + (long long)r + (long long)pre * p.d_in * (long long)c;
     double2 acc = make_double2(0.0, 0.0);
-    for (int t = 0; t < p.nterms; ++t) {
+    for (int t = (int)sub; t < p.nterms; t += (int)tpo) {
       const int4 T = p.terms[t];
       IdxT J0;
       const bool uniform = T.z < 0;
@@ -125,9 +129,15 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherParams p, const doubl
       }
       cfma(acc, p.coef[t], tacc);
     }
-    double2 out = cmul(p.alpha, acc);
-    if (!p.beta_zero) cfma(out, p.beta, y[idx]);
-    y[idx] = out;
+    for (unsigned o = tpo >> 1; o > 0; o >>= 1) {
+      acc.x += __shfl_xor_sync(gmask, acc.x, o);
+      acc.y += __shfl_xor_sync(gmask, acc.y, o);
+    }
+    if (sub == 0) {
+      double2 out = cmul(p.alpha, acc);
+      if (!p.beta_zero) cfma(out, p.beta, y[idx]);
+      y[idx] = out;
+    }
   }
 }
 
@@ -297,7 +307,10 @@ int gather_program_launch(const GatherProgram &p, int64_t pre, int64_t post, cpl
   const int64_t total_out = pre * p.d_out * post, total_in = pre * p.d_in * post;
   if (total_out == 0) return QOB_STATUS_OK;
   const int threads = 256;
-  int64_t blocks = (total_out + threads - 1) / threads;
+  int tpo = 1;
+  while (tpo < 32 && tpo < p.nterms && total_out * tpo * 2 <= (int64_t)148 * 1024) tpo <<= 1;
+  g.tpo = tpo;
+  int64_t blocks = (total_out * tpo + threads - 1) / threads;
   if (blocks > (int64_t)1 << 30) blocks = (int64_t)1 << 30;
   if (total_out < ((int64_t)1 << 31) && total_in < ((int64_t)1 << 31))
     gather_kernel<uint32_t><<<(unsigned)blocks, threads, 0, s>>>(g, (const double2 *)x, (double2 *)y);

@@ -32,9 +32,10 @@ class Basis:
 
     def __init__(self, shape):
         self.shape = tuple(int(s) for s in shape)
+        self._len = int(np.prod(self.shape)) if self.shape else 1
 
     def __len__(self):
-        return int(np.prod(self.shape)) if self.shape else 1
+        return self._len
 
     def _key(self):
         return (type(self).__name__, self.shape)
