@@ -475,3 +475,24 @@ def test_dense_device_times_dense_device_is_library_gemm(Q):
     bb, outb = H.bra((6,), xb), H.bra((5,), yb0)
     Q.mul_(outb.q, bb.q, A.q, 2.0, 1.0)
     assert H.rel_err(outb.q.to_host(), 2.0 * xb @ a + yb0) <= TOL
+
+
+@pytest.mark.parametrize("n", [12, 14])
+def test_qtile_more_masks_than_records_per_pass(Q, monkeypatch, n):
+    """All-to-all sigma_x sigma_x couplings: 91 distinct flip masks, more than the 56 lookup records a pass carries in its
+    kernel parameters -> the planner chunks them into extra passes over the same tiles."""
+    monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    rng = np.random.default_rng(98)
+    dims = (2,) * n
+    sx, sy, sz = _pauli()
+    terms, coefs = [], []
+    for i in range(1, n + 1):
+        for j in range(i + 1, n + 1):
+            terms.append(H.lazytensor(dims, dims, [i, j], [sp.csc_matrix(sx), sp.csc_matrix(sx)]))
+            coefs.append(rng.uniform(-1, 1) / abs(i - j) ** 3)
+    terms.append(H.lazytensor(dims, dims, [1, 7, n], [sy, sz, sy]))   # three separate selector runs
+    coefs.append(0.37)
+    s = H.lazysum(dims, dims, coefs, terms)
+    d = Q.describe(s.q)
+    assert "qtile" in d and d.count("{free:") >= (2 if n == 12 else 3), d
+    H.check_mul(s, dims, dims, rng, tol=TOL, kinds=("ket", "bra"), scalars=((1, 0), (1.5, 2.1)))
