@@ -335,29 +335,35 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
 
     # ---- end-to-end through the public host-buffer API: pinned host -> device, mul!, device -> pinned host
     e2e_steps = max(1, min(3, steps)) if world == 1 else 1
-    hx = torch.empty(1 << nloc, dtype=torch.complex128, pin_memory=True)
-    hy = torch.empty(1 << nloc, dtype=torch.complex128, pin_memory=True)
-    hx.copy_(xs)
-    torch.cuda.synchronize()
-    t_e2e = []
-    for i in range(e2e_steps + 1):
-        barrier()
-        t0 = time.perf_counter()
-        if sharded is None:
-            Q.apply_host(H, hx.numpy(), alpha=alpha, beta=0.0, y=hy.numpy())
-        else:
-            xs.copy_(hx, non_blocking=True)
-            step()
-            hy.copy_(ys, non_blocking=True)
-        barrier()
-        if i > 0:
-            t_e2e.append(time.perf_counter() - t0)
-    e2e_s = sum(t_e2e) / len(t_e2e)
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
     slab_bytes = 16 * (1 << nloc)
+    e2e_s, e2e_err, t_e2e = None, None, []
+    try:
+        hx = torch.empty(1 << nloc, dtype=torch.complex128, pin_memory=True)
+        hy = torch.empty(1 << nloc, dtype=torch.complex128, pin_memory=True)
+        hx.copy_(xs)
+        torch.cuda.synchronize()
+        for i in range(e2e_steps + 1):
+            barrier()
+            t0 = time.perf_counter()
+            if sharded is None:
+                Q.apply_host(H, hx.numpy(), alpha=alpha, beta=0.0, y=hy.numpy())
+            else:
+                xs.copy_(hx, non_blocking=True)
+                step()
+                hy.copy_(ys, non_blocking=True)
+            barrier()
+            if i > 0:
+                t_e2e.append(time.perf_counter() - t0)
+        e2e_s = sum(t_e2e) / len(t_e2e)
+        del hx, hy
+    except Exception as e:  # e.g. the host cannot pin two slabs per rank
+        e2e_err = f"{type(e).__name__}: {e}"
+    if world > 1:
+        t = torch.tensor([e2e_s if e2e_s is not None else -1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mn = torch.tensor([e2e_s if e2e_s is not None else -1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        e2e_s = float(t.item()) if float(mn.item()) > 0 else None
 
     if rank != 0:
         return
@@ -394,8 +400,9 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
         "term_updates_per_s": value * nterms,
         "hbm_GBps_algorithmic": 32.0 * (1 << nloc) / 1e9 / (ms_step * 1e-3),
         "clocks": clocks,
-        "e2e": {"value": amps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": slab_bytes * world, "d2h_bytes_per_step": slab_bytes * world,
-                "ms_per_step": 1e3 * e2e_s, "steps": len(t_e2e)},
+        "e2e": {"value": (amps / e2e_s) if e2e_s else None, "unit": UNIT, "h2d_bytes_per_step": slab_bytes * world,
+                "d2h_bytes_per_step": slab_bytes * world, "ms_per_step": (1e3 * e2e_s) if e2e_s else None,
+                "steps": len(t_e2e), **({"error": e2e_err} if e2e_err else {})},
         "gpu_launches": launches,
         "roofline": roofline,
     }

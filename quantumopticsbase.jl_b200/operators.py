@@ -419,6 +419,34 @@ class LazyProduct(AbstractOperator):
         self.basis_l, self.basis_r = operators[0].basis_l, operators[-1].basis_r
 
 
+class TimeDependentSum(AbstractOperator):
+    """TimeDependentSum(coefficients, operators; init_time=0) (src/time_dependent_operator.jl:150-170): a LazySum whose
+    factors are numbers or functions of time.  `set_time_` rewrites the static LazySum's factors (:279-290); `mul_` forwards
+    to the static operator (:274-277), which re-sends the coefficients to the device plan — a few hundred bytes, no
+    replanning (`qob_lazysum_set_coefs`)."""
+
+    def __init__(self, coefficients, operators, init_time=0.0):
+        if isinstance(operators, LazySum):
+            self.static_op = operators
+        else:
+            self.static_op = LazySum([0.0] * len(operators), list(operators))
+        self.coefficients = list(coefficients)
+        if len(self.coefficients) != len(self.static_op.operators):
+            raise ArgumentError("TimeDependentSum `coefficients` and `operators` have different lengths.")
+        self.basis_l, self.basis_r = self.static_op.basis_l, self.static_op.basis_r
+        self.current_time = None
+        self.set_time_(init_time)
+
+    def set_time_(self, t):
+        if self.current_time != t:
+            self.current_time = t
+            self.static_op.factors = [complex(c(t)) if callable(c) else complex(c) for c in self.coefficients]
+        for o in self.static_op.operators:
+            if isinstance(o, TimeDependentSum):
+                o.set_time_(t)
+        return self
+
+
 # ------------------------------------------------------------------------------------ handles
 def _factor_struct(d, keep):
     """qob_factor for operator data `d`; numpy arrays referenced by the struct are appended to `keep`."""
@@ -547,6 +575,10 @@ def mul_(result, a, b, alpha=1.0, beta=0.0):
       Op   <- DenseOp * op                 (:593, :227, :148, sparse:200)
     alpha/beta: any Python number (bool/int/float/complex), promoted to ComplexF64."""
     alpha, beta = complex(alpha), complex(beta)
+    if isinstance(a, TimeDependentSum):
+        a = a.static_op
+    if isinstance(b, TimeDependentSum):
+        b = b.static_op
     if _is_state_op(a) and (_is_state_op(b) or isinstance(b, Ket)) or (isinstance(a, Bra) and _is_state_op(b)):
         return _dense_device_mul(result, a, b, alpha, beta)
     if isinstance(b, Ket) and isinstance(a, AbstractOperator):

@@ -496,3 +496,30 @@ def test_qtile_more_masks_than_records_per_pass(Q, monkeypatch, n):
     d = Q.describe(s.q)
     assert "qtile" in d and d.count("{free:") >= (2 if n == 12 else 3), d
     H.check_mul(s, dims, dims, rng, tol=TOL, kinds=("ket", "bra"), scalars=((1, 0), (1.5, 2.1)))
+
+
+def test_time_dependent_sum_coefficient_updates(Q, monkeypatch):
+    """TimeDependentSum: set_time! rewrites the LazySum factors (time_dependent_operator.jl:279-290); the device plan keeps
+    its passes and only refills its weight tables.  Checked on the tile-kernel path at several times."""
+    monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    rng = np.random.default_rng(99)
+    n = 13
+    dims, coefs, terms = _chain_terms(n, "heis", False, rng)
+    fns = [(lambda t, c=c, k=k: c * np.cos(0.3 * k * t) + 0.1j * np.sin(t)) if k % 3 else c for k, c in enumerate(coefs)]
+    td = Q.TimeDependentSum(fns, [t_.q for t_ in terms])
+    assert "qtile" in Q.describe(td.static_op)
+    x = H.rnd(rng, 1 << n)
+    launches = None
+    for t in (0.0, 0.7, 1.9):
+        td.set_time_(t)
+        now = [complex(f(t)) if callable(f) else complex(f) for f in fns]
+        so = O.LazySum(dims, dims, now, [t_.o for t_ in terms])
+        ref = H.ket(dims, np.zeros(1 << n, dtype=complex))
+        O.mul(ref.o, so, H.ket(dims, x).o, 1.0, 0.0)
+        out = H.ket(dims, np.zeros(1 << n, dtype=complex))
+        before = Q.launch_count()
+        Q.mul_(out.q, td, H.ket(dims, x).q, 1.0, 0.0)
+        used = Q.launch_count() - before
+        launches = used if launches is None else launches
+        assert used == launches            # same plan every time
+        assert H.rel_err(out.q.to_host(), ref.o.data) <= TOL
