@@ -57,6 +57,8 @@ struct QPassParams {
   double2 alpha, beta;
   int mode;  // 0: y = a*acc ; 1: y = a*acc + beta*y ; 2: y = a*acc + y      (+ zadd[i] when zadd != nullptr)
   unsigned ntiles;          // tiles of this pass; the CTAs are persistent and stride over them
+  int bulk;                 // 1: stage the tile with TMA bulk copies (cp.async.bulk + mbarrier), one per contiguous run
+  int run_log2;             // log2 of the amplitudes per contiguous run (= width of the low free block)
   const double2 *zadd;      // optional extra addend in the local layout (contributions received from other ranks)
   // PEER variant (sharded states): the buffer addressed by this pass is the SWAPPED layout of the ranks' slabs.  Index bits
   // [peer_shift, peer_shift+peer_bits) of an address name the rank that holds the element; there it sits at the same
@@ -163,6 +165,12 @@ __global__ void __launch_bounds__(THREADS, MINB)
   }
   const unsigned lbt = tid * 16u;
   const int c_diag = P.npre, c_multi = c_diag + P.ndiag, c_single = c_multi + P.nmulti, c_end = c_single + P.nsingle;
+  __shared__ __align__(8) unsigned long long tile_bar;  // mbarrier tracking the bulk copies of the current tile
+  unsigned bar_phase = 0;
+  if (!PEER && P.bulk && tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&tile_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+  }
 
   // persistent CTAs: the grid is sized by the host (occupancy x SMs granted to this kernel) and strides over the tiles
 #pragma unroll 1
@@ -170,14 +178,34 @@ __global__ void __launch_bounds__(THREADS, MINB)
   const unsigned long long at = qexpand(tile, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g) | at_tid;  // per-thread address part
   __syncthreads();  // the previous tile is no longer read (first trip: orders the table stores)
 
-  // ---- stage the x tile: 16-byte cp.async per amplitude, lanes walk the contiguous low block
+  // ---- stage the x tile.  Local tiles: TMA bulk copies (cp.async.bulk -> SASS UBLKCP), one per contiguous run of the
+  // low free block, issued by warp 0 and tracked by an mbarrier, so the fill costs no LSU wavefronts and no per-thread
+  // address arithmetic.  Peer tiles (and QOB_QTILE_TMA=0): 16-byte cp.async per amplitude.
+  if (!PEER && P.bulk) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&tile_bar);
+    if (tid < 32) {
+      asm volatile("fence.proxy.async.shared::cta;\n" ::);  // earlier generic-proxy reads of xs precede the async writes
+      const unsigned nruns = (unsigned)TILE >> P.run_log2, run_bytes = 16u << P.run_log2;
+      if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((unsigned)TILE * 16u));
+      __syncwarp();
+      const unsigned long long tbase = at & ~at_tid;  // the tile's base address (fixed bits only)
+      for (unsigned r = tid; r < nruns; r += 32) {
+        const unsigned long long a = tbase | qexpand(r << P.run_log2, P.nfree_seg, P.fs_l, P.fs_n, P.fs_g);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(xsB + (size_t)r * run_bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                     "l"(x + a), "r"(run_bytes), "r"(bar)
+                     : "memory");
+      }
+    }
+  } else {
 #pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    const unsigned l = k * THREADS + tid;
-    const unsigned saddr = (unsigned)__cvta_generic_to_shared(xsB + (size_t)l * sizeof(double2));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(qaddr<PEER>(P, x, P.xpeer, at | P.eoff[k])));
+    for (int k = 0; k < PER; ++k) {
+      const unsigned l = k * THREADS + tid;
+      const unsigned saddr = (unsigned)__cvta_generic_to_shared(xsB + (size_t)l * sizeof(double2));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(qaddr<PEER>(P, x, P.xpeer, at | P.eoff[k])));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
   }
-  asm volatile("cp.async.commit_group;\n" ::);
   // read-modify-write passes: pull this tile's y (and z) lines into L2 now (no registers held), so that the
   // epilogue's loads find them there instead of paying the DRAM latency after the compute phase.  The low 3
   // tile-local bits are always contiguous address bits (L >= 3): one prefetch per 128-byte line.
@@ -191,8 +219,20 @@ __global__ void __launch_bounds__(THREADS, MINB)
       for (int k = 0; k < PER; ++k) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(P.zadd + (at | P.eoff[k])));
     }
   }
-  asm volatile("cp.async.wait_group 0;\n" ::);
-  __syncthreads();
+  if (!PEER && P.bulk) {
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&tile_bar);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                   : "=r"(done)
+                   : "r"(bar), "r"(bar_phase)
+                   : "memory");
+    }
+    bar_phase ^= 1u;
+  } else {
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+  }
 
   // thread part of the logical index (tile id, tid and rank bits); the amplitude-dependent part eoff[k] is warp-uniform
   const unsigned g_lo = (unsigned)(at | P.hi_or), g_hi = (unsigned)((at | P.hi_or) >> 32);
@@ -961,6 +1001,13 @@ int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta,
     P.beta = make_double2(beta.real(), beta.imag());
     P.mode = first ? (beta == cplx(0.0, 0.0) ? 0 : 1) : 2;
     P.ntiles = (unsigned)(1ull << (h.nbits - h.T));
+    {
+      static const bool tma = getenv("QOB_QTILE_TMA") && atoi(getenv("QOB_QTILE_TMA")) != 0;
+      int low = 0;  // contiguous low block of this pass's free bits
+      while (low < (int)pp->free_bits.size() && pp->free_bits[low] == low) ++low;
+      P.bulk = (tma && o.npeers == 0) ? 1 : 0;
+      P.run_log2 = low;
+    }
     P.zadd = (pi + 1 == run.size()) ? (const double2 *)o.zadd : nullptr;
     P.peer_shift = o.peer_shift;
     P.peer_rank = o.peer_rank;
