@@ -111,17 +111,7 @@ struct DevArray {  // owning device array uploaded from a host vector
   }
 };
 
-// One term of a fused tensor program: coef * scalar * (x)_k A_k on `sites`
-struct TermSpec {
-  int coef_index = -1;  // index into the owning sum's coefficient vector, -1: none
-  cplx scalar = 1.0;    // LazyTensor.factor
-  std::vector<int> sites;               // 0-based, sorted
-  std::vector<const HostMat *> mats;    // per site, as stored (left-application orientation)
-};
-
 // ---------------------------------------------------------------- kernels (qob_kernels_*.cu)
-struct GatherProgramDev;  // generic fused LazySum-of-LazyTensor program
-struct QTileProgram;      // qubit tile program
 
 // y[i] = beta*y[i] (beta == 0 -> zero fill without reading)
 int launch_scale(void *y, int64_t n, cplx beta, cudaStream_t s);
@@ -207,7 +197,6 @@ struct QLaunchOpts {
 };
 int qtile_launch(const QTileProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s,
                  const QLaunchOpts *opts = nullptr);
-bool qtile_supported_term(const QTerm &t);
 
 // misc device helpers
 int launch_fill_state(void *x, int64_t offset, int64_t n, uint64_t seed, double scale, cudaStream_t s);

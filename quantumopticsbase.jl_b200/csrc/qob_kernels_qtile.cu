@@ -404,8 +404,6 @@ struct QTileProgramHost {
   }
 };
 
-bool qtile_supported_term(const QTerm &t) { return t.bits.size() <= QT_MAXSEL; }
-
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   return v && *v ? atoi(v) : dflt;
@@ -1002,10 +1000,13 @@ int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta,
     P.mode = first ? (beta == cplx(0.0, 0.0) ? 0 : 1) : 2;
     P.ntiles = (unsigned)(1ull << (h.nbits - h.T));
     {
-      static const bool tma = getenv("QOB_QTILE_TMA") && atoi(getenv("QOB_QTILE_TMA")) != 0;
+      // TMA bulk staging pays when the runs are long (measured on N=28/30: the fully contiguous pass gains ~8 %, while
+      // 512 x 128-byte or 128 x 512-byte bulk copies per tile are 15-80 % slower than per-thread cp.async).
+      // QOB_QTILE_TMA = minimum log2(run length in amplitudes) for the bulk path; 0 disables it.
+      static const int tma_min = getenv("QOB_QTILE_TMA") ? atoi(getenv("QOB_QTILE_TMA")) : 9;
       int low = 0;  // contiguous low block of this pass's free bits
       while (low < (int)pp->free_bits.size() && pp->free_bits[low] == low) ++low;
-      P.bulk = (tma && o.npeers == 0) ? 1 : 0;
+      P.bulk = (tma_min > 0 && low >= tma_min && o.npeers == 0) ? 1 : 0;
       P.run_log2 = low;
     }
     P.zadd = (pi + 1 == run.size()) ? (const double2 *)o.zadd : nullptr;
