@@ -523,3 +523,30 @@ def test_time_dependent_sum_coefficient_updates(Q, monkeypatch):
         launches = used if launches is None else launches
         assert used == launches            # same plan every time
         assert H.rel_err(out.q.to_host(), ref.o.data) <= TOL
+
+
+def test_lindblad_rhs_call_pattern_with_bool_scalars(Q):
+    """The master-equation right-hand side as ODE solvers call it (test/test_sciml_broadcast_interfaces.jl:36-43):
+    3-argument mul!, Bool alpha/beta, lazy-adjoint jump operators, left and right application on a dense rho."""
+    rng = np.random.default_rng(101)
+    n = 6
+    dims, coefs, terms = _chain_terms(n, "heis", False, rng)
+    Hs = H.lazysum(dims, dims, coefs, terms)
+    sm = np.array([[0, 0], [1, 0]], dtype=complex)                       # sigma_minus as spin.jl builds it (lower diagonal)
+    J = H.lazytensor(dims, dims, [3], [sp.csc_matrix(sm)], 0.8)
+    Jd = H.lazytensor(dims, dims, [3], [("adj", sp.csc_matrix(sm))], 0.8)  # lazy dagger of the site operator
+    mh = H.lazytensor(dims, dims, [3], [-0.5 * 0.64 * (sm.conj().T @ sm)])
+    D = 1 << n
+    rho0 = H.rnd(rng, D, D)
+    rho = H.denseop(dims, dims, rho0)
+    tmp = H.denseop(dims, dims, np.full((D, D), np.nan + 0j))
+    drho = H.denseop(dims, dims, np.full((D, D), np.nan + 0j))
+    Q.mul_(tmp.q, rho.q, Jd.q)                  # tmp  = rho J^dagger          (alpha = true, beta = false)
+    Q.mul_(drho.q, J.q, tmp.q)                  # drho = J rho J^dagger
+    Q.mul_(drho.q, rho.q, mh.q, True, True)     # drho += rho (-J^dagger J / 2)
+    Q.mul_(drho.q, mh.q, rho.q, True, True)
+    Q.mul_(drho.q, Hs.q, rho.q, -1j, 1)         # drho += -i H rho
+    Q.mul_(drho.q, rho.q, Hs.q, 1j, True)       # drho += +i rho H
+    Hd, Jm = O.dense(Hs.o), O.dense(J.o)
+    ref = Jm @ rho0 @ Jm.conj().T - 0.5 * (Jm.conj().T @ Jm @ rho0 + rho0 @ Jm.conj().T @ Jm) - 1j * (Hd @ rho0 - rho0 @ Hd)
+    assert H.rel_err(drho.q.to_host(), ref) <= TOL
