@@ -171,10 +171,18 @@ int qob_layout_plan_describe(qob_op *sum, int32_t plan_id, char *buf, int64_t bu
  *            of an address select the owning rank; the tile kernel loads x straight from x_peers[owner] and stores its
  *            result straight into y_peers[owner] (device pointers into every rank's symmetric / IPC-mapped memory).
  *            x and y are ignored in that case.
- *   sm_budget>0 limits the persistent tile kernel to that many SMs so that another kernel (the local passes) runs beside it. */
+ *   sm_budget>0 limits the persistent tile kernel to that many SMs so that another kernel (the local passes) runs beside it.
+ *   chunk_index/nchunks: run one of nchunks equal tile ranges (nchunks <= 1: the whole pass). */
 int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const void *x, qob_c64 beta, void *y,
                              const void *zadd, int32_t npeers, const void *const *x_peers, void *const *y_peers,
-                             int32_t peer_shift, int32_t sm_budget, void *stream);
+                             int32_t peer_shift, int32_t sm_budget, int32_t chunk_index, int32_t nchunks, void *stream);
+/* Chunked launches (to pipeline the fold-in of received contributions behind the exchange): a plan with exactly one pass
+ * can be run on chunk `chunk_index` of `nchunks` equal ranges of its tiles.  qob_layout_plan_info reports how many passes
+ * hold work and which index bits are fixed (not free) in all of them; qob_layout_plan_set_chunk_bits makes the given
+ * fixed bits the most significant bits of the tile numbering, so that chunk c covers the same amplitudes (those bits = c)
+ * in every plan configured with the same chunk bits. */
+int qob_layout_plan_info(qob_op *sum, int32_t plan_id, int32_t *npasses, uint64_t *fixed_mask);
+int qob_layout_plan_set_chunk_bits(qob_op *sum, int32_t plan_id, uint64_t chunk_mask);
 /* SMs the persistent tile kernels may occupy by default (0 = all). */
 int qob_set_sm_budget(int32_t sms);
 

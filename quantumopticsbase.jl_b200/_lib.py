@@ -107,7 +107,10 @@ _sigs = {
     "qob_layout_plan_create": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.c_uint64, C.POINTER(C.c_uint8), C.POINTER(_i32)]),
     "qob_layout_plan_apply": (C.c_int, [_vp, _i32, c64, _vp, c64, _vp, _vp]),
     "qob_layout_plan_describe": (C.c_int, [_vp, _i32, C.c_char_p, _i64]),
-    "qob_layout_plan_apply_ex": (C.c_int, [_vp, _i32, c64, _vp, c64, _vp, _vp, _i32, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32, _vp]),
+    "qob_layout_plan_apply_ex": (C.c_int, [_vp, _i32, c64, _vp, c64, _vp, _vp, _i32, C.POINTER(_vp), C.POINTER(_vp), _i32, _i32,
+                                           _i32, _i32, _vp]),
+    "qob_layout_plan_info": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(C.c_uint64)]),
+    "qob_layout_plan_set_chunk_bits": (C.c_int, [_vp, _i32, C.c_uint64]),
     "qob_set_sm_budget": (C.c_int, [_i32]),
 }
 for _name, (_res, _args) in _sigs.items():

@@ -995,7 +995,7 @@ int qob_layout_plan_apply(qob_op *sum, int32_t plan_id, qob_c64 alpha, const voi
 
 int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const void *x, qob_c64 beta, void *y,
                              const void *zadd, int32_t npeers, const void *const *x_peers, void *const *y_peers,
-                             int32_t peer_shift, int32_t sm_budget, void *stream) {
+                             int32_t peer_shift, int32_t sm_budget, int32_t chunk_index, int32_t nchunks, void *stream) {
   LazySumOp *S = nullptr;
   QOB_TRY(qubit_sum(sum, &S));
   if (plan_id < 0 || plan_id >= (int)S->layouts.size()) QOB_FAIL(QOB_STATUS_INVALID_ARG, "bad layout plan id");
@@ -1006,6 +1006,8 @@ int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const 
   QLaunchOpts o;
   o.sm_budget = sm_budget;
   o.zadd = zadd;
+  o.chunk_index = chunk_index;
+  o.nchunks = nchunks < 1 ? 1 : nchunks;
   if (npeers > 0) {
     if (!is_pow2(npeers) || !x_peers || !y_peers) QOB_FAIL(QOB_STATUS_INVALID_ARG, "npeers must be a power of two with pointer tables");
     const int pb = ilog2(npeers);
@@ -1031,6 +1033,25 @@ int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const 
   }
   QOB_TRY(qtile_set_coefs(lp.prog, S->coefs, s));
   return qtile_launch(lp.prog, C(alpha), x, C(beta), y, s, &o);
+}
+
+int qob_layout_plan_info(qob_op *sum, int32_t plan_id, int32_t *npasses, uint64_t *fixed_mask) {
+  LazySumOp *S = nullptr;
+  QOB_TRY(qubit_sum(sum, &S));
+  if (plan_id < 0 || plan_id >= (int)S->layouts.size()) QOB_FAIL(QOB_STATUS_INVALID_ARG, "bad layout plan id");
+  int n = 0;
+  uint64_t m = 0;
+  qtile_info(S->layouts[plan_id]->prog, &n, &m);
+  if (npasses) *npasses = n;
+  if (fixed_mask) *fixed_mask = m;
+  return QOB_STATUS_OK;
+}
+
+int qob_layout_plan_set_chunk_bits(qob_op *sum, int32_t plan_id, uint64_t chunk_mask) {
+  LazySumOp *S = nullptr;
+  QOB_TRY(qubit_sum(sum, &S));
+  if (plan_id < 0 || plan_id >= (int)S->layouts.size()) QOB_FAIL(QOB_STATUS_INVALID_ARG, "bad layout plan id");
+  return qtile_set_chunk_bits(S->layouts[plan_id]->prog, chunk_mask);
 }
 
 int qob_layout_plan_describe(qob_op *sum, int32_t plan_id, char *buf, int64_t buflen) {

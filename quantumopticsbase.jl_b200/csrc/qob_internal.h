@@ -194,7 +194,10 @@ struct QLaunchOpts {
   int peer_shift = 0, peer_rank = 0;
   const void *const *xpeer = nullptr;
   void *const *ypeer = nullptr;
+  int chunk_index = 0, nchunks = 1;  // run only chunk `chunk_index` of `nchunks` equal tile ranges (single-pass plans)
 };
+void qtile_info(const QTileProgram &p, int *npasses, uint64_t *fixed_mask);
+int qtile_set_chunk_bits(QTileProgram &p, uint64_t chunk_mask);
 int qtile_launch(const QTileProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s,
                  const QLaunchOpts *opts = nullptr);
 

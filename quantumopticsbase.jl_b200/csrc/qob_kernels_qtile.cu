@@ -56,7 +56,8 @@ struct QPassParams {
   unsigned long long eoff[16];  // address part of tile-local index k*THREADS (k < TILE/THREADS), precomputed on the host
   double2 alpha, beta;
   int mode;  // 0: y = a*acc ; 1: y = a*acc + beta*y ; 2: y = a*acc + y      (+ zadd[i] when zadd != nullptr)
-  unsigned ntiles;          // tiles of this pass; the CTAs are persistent and stride over them
+  unsigned ntiles;          // tiles this launch processes; the CTAs are persistent and stride over them
+  unsigned tile_begin;      // first tile of this launch (chunked launches of one pass)
   int bulk;                 // 1: stage the tile with TMA bulk copies (cp.async.bulk + mbarrier), one per contiguous run
   int run_log2;             // log2 of the amplitudes per contiguous run (= width of the low free block)
   const double2 *zadd;      // optional extra addend in the local layout (contributions received from other ranks)
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
 
   // persistent CTAs: the grid is sized by the host (occupancy x SMs granted to this kernel) and strides over the tiles
 #pragma unroll 1
-  for (unsigned tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+  for (unsigned tile = P.tile_begin + blockIdx.x; tile < P.tile_begin + P.ntiles; tile += gridDim.x) {
   const unsigned long long at = qexpand(tile, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g) | at_tid;  // per-thread address part
   __syncthreads();  // the previous tile is no longer read (first trip: orders the table stores)
 
@@ -889,6 +890,51 @@ int qtile_build(QTileProgram &prog, int nbits, uint64_t hi_value, const std::vec
   return QOB_STATUS_OK;
 }
 
+// number of passes that hold work, and the index bits that are fixed (not free) in every one of them
+void qtile_info(const QTileProgram &prog, int *npasses, uint64_t *fixed_mask) {
+  const QTileProgramHost &h = *prog.h;
+  int n = 0;
+  uint64_t fixed = h.nbits >= 64 ? ~0ull : ((1ull << h.nbits) - 1);
+  for (auto &pp : h.passes) {
+    const QPassParams &q = pp->params;
+    if (q.npre + q.ndiag + q.nmulti + q.nsingle == 0) continue;
+    ++n;
+    for (int b : pp->free_bits) fixed &= ~(1ull << b);
+  }
+  if (npasses) *npasses = n;
+  if (fixed_mask) *fixed_mask = n ? fixed : 0;
+}
+
+// Reorder the tile numbering of every pass so that the bits of `chunk_mask` (which must be fixed bits) are the MOST
+// significant bits of the tile id: a contiguous range of tile ids then corresponds to fixed values of those index bits,
+// the same amplitudes in every plan that uses the same chunk bits.
+int qtile_set_chunk_bits(QTileProgram &prog, uint64_t chunk_mask) {
+  QTileProgramHost &h = *prog.h;
+  for (auto &pp : h.passes) {
+    uint64_t fs = 0;
+    for (int b : pp->free_bits) fs |= 1ull << b;
+    if (fs & chunk_mask) QOB_FAIL(QOB_STATUS_INVALID_ARG, "chunk bits must not be free bits of a pass");
+    std::vector<int> lo, hi;
+    for (int b = 0; b < h.nbits; ++b) {
+      if (fs >> b & 1) continue;
+      ((chunk_mask >> b & 1) ? hi : lo).push_back(b);
+    }
+    QPassParams &P = pp->params;
+    int nlo = 0, nhi = 0;
+    unsigned char sl[QT_MAXSEG], sn[QT_MAXSEG], sg[QT_MAXSEG];
+    make_segments(lo, P.xs_l, P.xs_n, P.xs_g, nlo);
+    make_segments(hi, sl, sn, sg, nhi);
+    if (nlo + nhi > QT_MAXSEG) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: too many index segments");
+    for (int i = 0; i < nhi; ++i) {
+      P.xs_l[nlo + i] = (unsigned char)(sl[i] + lo.size());
+      P.xs_n[nlo + i] = sn[i];
+      P.xs_g[nlo + i] = sg[i];
+    }
+    P.nfixed_seg = nlo + nhi;
+  }
+  return QOB_STATUS_OK;
+}
+
 int qtile_set_coefs(QTileProgram &prog, const std::vector<cplx> &coefs, cudaStream_t s) {
   QTileProgramHost &h = *prog.h;
   for (auto &c : h.comps)
@@ -908,8 +954,8 @@ static int launch_pass(const QTileProgramHost &h, const QPassHost &p, const QPas
     QOB_CUDA(cudaFuncSetAttribute(qtile_kernel<T, THREADS, MINB, IDX64, REALW, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const uint64_t ntiles = 1ull << (h.nbits - T);
-  if (ntiles > 0x7FFFFFFFull) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: too many tiles");
+  if ((1ull << (h.nbits - T)) > 0x7FFFFFFFull) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: too many tiles");
+  const uint64_t ntiles = P.ntiles;
   uint64_t grid = std::min<uint64_t>(ntiles, (uint64_t)std::max(1, max_ctas));
   qtile_kernel<T, THREADS, MINB, IDX64, REALW, PEER><<<(unsigned)grid, THREADS, smem, s>>>(P, (const double2 *)x, (double2 *)y);
   QOB_LAUNCHED();
@@ -990,8 +1036,9 @@ int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta,
       cudaEventCreate(&pe.a);
       cudaEventCreate(&pe.b);
       pe.pass = (int)pi;
-      pe.bytes = (double)(1ull << h.nbits) * ((first && beta == cplx(0.0, 0.0)) ? 32.0 : 48.0) +
-                 ((o.zadd && pi + 1 == run.size()) ? 16.0 * (double)(1ull << h.nbits) : 0.0);
+      pe.bytes = ((double)(1ull << h.nbits) * ((first && beta == cplx(0.0, 0.0)) ? 32.0 : 48.0) +
+                  ((o.zadd && pi + 1 == run.size()) ? 16.0 * (double)(1ull << h.nbits) : 0.0)) /
+                 (double)std::max(1, o.nchunks);
       cudaEventRecord(pe.a, s);
     }
     QPassParams P = pp->params;
@@ -999,6 +1046,16 @@ int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta,
     P.beta = make_double2(beta.real(), beta.imag());
     P.mode = first ? (beta == cplx(0.0, 0.0) ? 0 : 1) : 2;
     P.ntiles = (unsigned)(1ull << (h.nbits - h.T));
+    P.tile_begin = 0;
+    if (o.nchunks > 1) {
+      // a chunk = a contiguous range of tile ids = fixed values of the most significant fixed bits (see qtile_set_chunk_bits)
+      if (run.size() != 1) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "chunked launches need a plan with exactly one pass");
+      if (o.chunk_index < 0 || o.chunk_index >= o.nchunks || (P.ntiles % (unsigned)o.nchunks) != 0)
+        QOB_FAIL(QOB_STATUS_INVALID_ARG, "bad chunk %d of %d", o.chunk_index, o.nchunks);
+      P.ntiles /= (unsigned)o.nchunks;
+      P.tile_begin = P.ntiles * (unsigned)o.chunk_index;
+      // beta handling (mode) is per tile, so a chunked pass is just the same pass restricted to some tiles
+    }
     {
       // TMA bulk staging pays when the runs are long (measured on N=28/30: the fully contiguous pass gains ~8 %, while
       // 512 x 128-byte or 128 x 512-byte bulk copies per tile are 15-80 % slower than per-thread cp.async).

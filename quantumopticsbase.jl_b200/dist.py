@@ -135,6 +135,9 @@ class ShardedLazySum:
             self.swap_lo = swap_window(self.nloc, self.p, touched & lowmask)
             self.plan_swapped = make(sel["R"], swapped_bitpos(self.n, self.nloc, self.p, self.swap_lo))
         self._buf = None
+        self.nchunks, self.chunk_mask = 1, 0
+        if os.environ.get("QOB_DIST_CHUNKS", "4") not in ("0", "1"):
+            self._setup_chunks(int(os.environ.get("QOB_DIST_CHUNKS", "4")))
         # fused exchange (symmetric memory): peers' pointer tables, keyed by the local tensor's data_ptr
         self._symm = {}
         self._zbuf = None
@@ -160,7 +163,7 @@ class ShardedLazySum:
     def _peer_table(self, ptrs):
         return (C.c_void_p * len(ptrs))(*ptrs)
 
-    def _apply_ex(self, plan, alpha, x, beta, y, zadd=None, peers=None, sm_budget=0):
+    def _apply_ex(self, plan, alpha, x, beta, y, zadd=None, peers=None, sm_budget=0, chunk=(0, 1)):
         import torch
 
         handle(self.H, self.ctx)
@@ -171,7 +174,36 @@ class ShardedLazySum:
         _lib.check(lib.qob_layout_plan_apply_ex(
             self.h, plan, c64.of(alpha), C.c_void_p(x.data_ptr() if x is not None else 0), c64.of(beta),
             C.c_void_p(y.data_ptr() if y is not None else 0), C.c_void_p(zadd.data_ptr() if zadd is not None else 0),
-            npeers, xp, yp, shift, int(sm_budget), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            npeers, xp, yp, shift, int(sm_budget), int(chunk[0]), int(chunk[1]),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def _plan_info(self, plan):
+        n, m = C.c_int32(), C.c_uint64()
+        _lib.check(lib.qob_layout_plan_info(self.h, plan, C.byref(n), C.byref(m)))
+        return n.value, m.value
+
+    def _setup_chunks(self, want=4):
+        """Pipeline the fold-in behind the exchange: when the remote-term plan and the last local group are single-pass
+        plans, both are chunked on the same (top common fixed) index bits, so chunk c of the local group can run as soon
+        as chunk c of the exchange has landed on every rank."""
+        self.nchunks = 1
+        if self.plan_swapped is None or self.plan_local_b is None or not self.overlap:
+            return
+        (ns, fs), (nb, fb) = self._plan_info(self.plan_swapped), self._plan_info(self.plan_local_b)
+        if ns != 1 or nb != 1:
+            return
+        window = ((1 << self.p) - 1) << self.swap_lo
+        common = fs & fb & ((1 << self.nloc) - 1) & ~window
+        bits = [b for b in range(self.nloc - 1, -1, -1) if common >> b & 1][: max(1, want.bit_length() - 1)]
+        if len(bits) < 1:
+            return
+        mask = 0
+        for b in bits:
+            mask |= 1 << b
+        _lib.check(lib.qob_layout_plan_set_chunk_bits(self.h, self.plan_swapped, C.c_uint64(mask)))
+        _lib.check(lib.qob_layout_plan_set_chunk_bits(self.h, self.plan_local_b, C.c_uint64(mask)))
+        self.nchunks = 1 << len(bits)
+        self.chunk_mask = mask
 
     def mul_fused_(self, y, x, alpha=1.0, beta=0.0):
         """Same result as mul_, with the exchange fused into the compute kernel: the remote-term pass reads x tiles from
@@ -196,16 +228,23 @@ class ShardedLazySum:
         two_groups = self.plan_local_b is not None
         if self.overlap and two_groups:
             side = self._side
+            nc = self.nchunks
             side.wait_stream(main)                     # x is ready on this rank
+            events = []
             with torch.cuda.stream(side):
                 zh.barrier(channel=0)                  # ... and on every rank; last call's contributions are consumed
-                self._apply_ex(self.plan_swapped, alpha, None, 0.0, None, peers=(xptrs, zptrs), sm_budget=k)
-                zh.barrier(channel=1)                  # every rank's contributions have landed
+                for c in range(nc):
+                    self._apply_ex(self.plan_swapped, alpha, None, 0.0, None, peers=(xptrs, zptrs), sm_budget=k, chunk=(c, nc))
+                    zh.barrier(channel=1)              # chunk c of every rank's contributions has landed
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    events.append(ev)
             # beside the exchange: the local passes use a full grid; the exchange kernel is persistent with k*occupancy
             # CTAs on a high-priority stream, so it keeps its share of the slots while local CTAs come and go
             self._apply_ex(self.plan_local, alpha, x, beta, y, sm_budget=self.local_budget)
-            main.wait_stream(side)
-            self._apply_ex(self.plan_local_b, alpha, x, 1.0, y, zadd=self._zbuf)
+            for c in range(nc):                        # fold the contributions in, chunk by chunk, behind the exchange
+                main.wait_event(events[c])
+                self._apply_ex(self.plan_local_b, alpha, x, 1.0, y, zadd=self._zbuf, chunk=(c, nc))
         else:
             zh.barrier(channel=0)
             self._apply_ex(self.plan_swapped, alpha, None, 0.0, None, peers=(xptrs, zptrs))

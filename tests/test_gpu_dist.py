@@ -105,17 +105,48 @@ def test_fused_peer_exchange_all_ranks_on_one_gpu(world, n, beta):
     zs = [torch.full((1 << nloc,), float("nan"), dtype=torch.complex128, device="cuda") for _ in range(world)]
     xptrs, zptrs = [t.data_ptr() for t in xs], [t.data_ptr() for t in zs]
     for r, sh in enumerate(ranks):
-        sh._apply_ex(sh.plan_swapped, alpha, None, 0.0, None, peers=(xptrs, zptrs), sm_budget=8 + r)
+        for c in reversed(range(sh.nchunks)):   # chunked launches of the exchange pass, in any order
+            sh._apply_ex(sh.plan_swapped, alpha, None, 0.0, None, peers=(xptrs, zptrs), sm_budget=8 + r, chunk=(c, sh.nchunks))
     torch.cuda.synchronize()
     for r, sh in enumerate(ranks):
         assert torch.isfinite(torch.view_as_real(zs[r])).all()   # every element written exactly once
         if sh.plan_local_b is not None:
             sh._apply_ex(sh.plan_local, alpha, xs[r], beta, ys[r], sm_budget=100)
-            sh._apply_ex(sh.plan_local_b, alpha, xs[r], 1.0, ys[r], zadd=zs[r])
+            for c in range(sh.nchunks):
+                sh._apply_ex(sh.plan_local_b, alpha, xs[r], 1.0, ys[r], zadd=zs[r], chunk=(c, sh.nchunks))
         else:
             sh._apply_ex(sh.plan_local, alpha, xs[r], beta, ys[r], zadd=zs[r])
     got = np.concatenate([y.cpu().numpy() for y in ys])
     assert H.rel_err(got, oracle_result(n, spec, alpha, beta, xfull, yfull0)) <= 1e-12
+
+
+def test_chunks_cover_the_same_amplitudes_in_both_plans():
+    """chunk c of the exchange pass writes exactly the contribution amplitudes that chunk c of the last local group reads"""
+    import torch
+
+    import qob200 as Q
+    from qob200.dist import ShardedLazySum
+
+    world, n = 4, 18
+    p, nloc = 2, 16
+    spec = chain_spec(n, 29)
+    ranks = [ShardedLazySum(build_q(Q, n, spec), r, world) for r in range(world)]
+    if ranks[0].nchunks < 2:
+        pytest.skip("plans are not single-pass at this size")
+    nc, mask = ranks[0].nchunks, ranks[0].chunk_mask
+    xs = [torch.randn(1 << nloc, dtype=torch.complex128, device="cuda") for _ in range(world)]
+    zs = [torch.full((1 << nloc,), float("nan"), dtype=torch.complex128, device="cuda") for _ in range(world)]
+    xptrs, zptrs = [t.data_ptr() for t in xs], [t.data_ptr() for t in zs]
+    c = 1
+    for r, sh in enumerate(ranks):
+        sh._apply_ex(sh.plan_swapped, 1.0, None, 0.0, None, peers=(xptrs, zptrs), chunk=(c, nc))
+    torch.cuda.synchronize()
+    idx = torch.arange(1 << nloc, device="cuda")
+    bits = [b for b in range(nloc) if mask >> b & 1]
+    val = sum(((idx >> b) & 1) << i for i, b in enumerate(bits))
+    for r in range(world):
+        written = torch.isfinite(zs[r].real)
+        assert torch.equal(written, val == c)
 
 
 def _free_port():
