@@ -391,12 +391,15 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
                 "whole_mul_frac_of_peak": 32.0 * (1 << nloc) / 1e9 / (ms_step * 1e-3) / peak}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"Heisenberg XYZ spin-1/2 chain N={n} periodic, LazySum of {nterms} LazyTensor terms "
                                f"(sparse sigma factors), mul!(y,H,x,alpha,0) on Ket of 2^{n} ComplexF64",
                    "state_bytes": 16 * (1 << n), "l2": "operands (>= 4 GiB per GPU) exceed the 126 MB L2; no flush needed",
-                   "plan": plan, "parallelism": "single GPU" if world == 1 else f"state sharded on top {world.bit_length() - 1} axes, NCCL all-to-all axis swap"},
+                   "plan": plan, "parallelism": "single GPU" if world == 1 else
+                   f"state sharded on the top {world.bit_length() - 1} spin axes ({16 * (1 << nloc) / 2**30:.0f} GiB slab per GPU, the largest "
+                   f"chain that fits); remote terms " + ("exchanged by the fused peer-memory tile pass over NVLink"
+                                                         if plan.startswith("exchange=fused") else "through NCCL all-to-all axis swaps")},
         "term_updates_per_s": value * nterms,
         "hbm_GBps_algorithmic": 32.0 * (1 << nloc) / 1e9 / (ms_step * 1e-3),
         "clocks": clocks,

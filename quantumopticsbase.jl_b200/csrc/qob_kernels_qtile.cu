@@ -911,6 +911,8 @@ void qtile_info(const QTileProgram &prog, int *npasses, uint64_t *fixed_mask) {
 int qtile_set_chunk_bits(QTileProgram &prog, uint64_t chunk_mask) {
   QTileProgramHost &h = *prog.h;
   for (auto &pp : h.passes) {
+    const QPassParams &q0 = pp->params;
+    if (q0.npre + q0.ndiag + q0.nmulti + q0.nsingle == 0) continue;   // empty passes are never launched
     uint64_t fs = 0;
     for (int b : pp->free_bits) fs |= 1ull << b;
     if (fs & chunk_mask) QOB_FAIL(QOB_STATUS_INVALID_ARG, "chunk bits must not be free bits of a pass");

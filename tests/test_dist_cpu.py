@@ -125,3 +125,30 @@ def test_sharded_apply_orchestration_gloo(tmp_path, world, beta):
     y = O.Ket(dims, O.fill_state(1 << n, 4, 1.0))
     O.mul(y, Ho, O.Ket(dims, O.fill_state(1 << n, 3, 2.0 ** (-n / 2))), 0.7 - 0.2j, beta)
     assert H.rel_err(got, y.data) <= 1e-12
+
+
+@pytest.mark.parametrize("world,n", [(2, 20), (4, 20), (8, 21), (8, 33), (2, 32), (8, 17)])
+def test_chunk_bits_are_fixed_in_both_single_pass_plans(world, n):
+    """Planning only (no GPU): the exchange pass and the last local group may be launched in chunks only on index bits that
+    are fixed (not free) in both plans, outside the swap window, and every rank must choose the same bits."""
+    import qob200 as Q
+    from qob200.dist import ShardedLazySum
+
+    spec = chain_spec(n, 11)
+    b = Q.SpinBasis(0.5)
+    B = Q.tensor(*[b] * n)
+    sig = (Q.sigmax(b), Q.sigmay(b), Q.sigmaz(b))
+    Hq = Q.LazySum([c for c, _, _ in spec], [Q.LazyTensor(B, idx, (sig[a], sig[a])) for _, idx, a in spec])
+    chosen = set()
+    for rank in (0, world - 1):
+        sh = ShardedLazySum(Hq, rank, world, ctx=Q.context(-1))
+        (ns, fs), (nb, fb) = sh._plan_info(sh.plan_swapped), sh._plan_info(sh.plan_local_b)
+        if sh.nchunks == 1:
+            assert n == 17 and (ns != 1 or nb != 1)
+            return
+        assert ns == 1 and nb == 1 and sh.nchunks == 4
+        m = sh.chunk_mask
+        assert bin(m).count("1") == 2 and m & fs == m and m & fb == m
+        assert m & (((1 << sh.p) - 1) << sh.swap_lo) == 0 and m < (1 << sh.nloc)
+        chosen.add(m)
+    assert len(chosen) == 1

@@ -81,7 +81,7 @@ def test_sharded_apply_all_ranks_on_one_gpu(world, n, beta):
     assert H.rel_err(got, oracle_result(n, spec, alpha, beta, xfull, yfull0)) <= 1e-12
 
 
-@pytest.mark.parametrize("world,n", [(2, 14), (4, 16), (8, 17)])
+@pytest.mark.parametrize("world,n", [(2, 14), (4, 16), (8, 17), (2, 20), (4, 20), (8, 21)])   # the last three run chunked
 @pytest.mark.parametrize("beta", [0.0, 0.5 + 0.25j])
 def test_fused_peer_exchange_all_ranks_on_one_gpu(world, n, beta):
     """The PEER variant of the tile kernel (loads x tiles from the owners' slabs, stores contributions into the owners'
@@ -100,6 +100,7 @@ def test_fused_peer_exchange_all_ranks_on_one_gpu(world, n, beta):
     yfull0 = O.fill_state(1 << n, 6, 1.0)
     alpha = -0.3 + 0.9j
     ranks = [ShardedLazySum(build_q(Q, n, spec), r, world) for r in range(world)]
+    assert (ranks[0].nchunks > 1) == (n >= 20)
     xs = [torch.from_numpy(xfull[r << nloc:(r + 1) << nloc].copy()).cuda() for r in range(world)]
     ys = [torch.from_numpy(yfull0[r << nloc:(r + 1) << nloc].copy()).cuda() for r in range(world)]
     zs = [torch.full((1 << nloc,), float("nan"), dtype=torch.complex128, device="cuda") for _ in range(world)]
@@ -127,8 +128,8 @@ def test_chunks_cover_the_same_amplitudes_in_both_plans():
     import qob200 as Q
     from qob200.dist import ShardedLazySum
 
-    world, n = 4, 18
-    p, nloc = 2, 16
+    world, n = 4, 20
+    p, nloc = 2, 18
     spec = chain_spec(n, 29)
     ranks = [ShardedLazySum(build_q(Q, n, spec), r, world) for r in range(world)]
     if ranks[0].nchunks < 2:
@@ -185,9 +186,10 @@ def _nccl_worker(rank, world, port, n, beta, out_dir, fused):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("n", [18, 21])   # 21 spins: the fused schedule runs its exchange / fold-in passes in 4 chunks
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("beta", [0.0, 0.5 + 0.25j])
-def test_sharded_apply_nccl(tmp_path, beta, fused):
+def test_sharded_apply_nccl(tmp_path, beta, fused, n):
     import torch
     import torch.multiprocessing as mp
 
@@ -196,7 +198,6 @@ def test_sharded_apply_nccl(tmp_path, beta, fused):
         world *= 2
     if world < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
-    n = 18
     mp.spawn(_nccl_worker, args=(world, _free_port(), n, beta, str(tmp_path), fused), nprocs=world, join=True)
     got = np.concatenate([np.load(tmp_path / f"y{r}.npy") for r in range(world)])
     spec = chain_spec(n, 21)
