@@ -124,7 +124,11 @@ int qob_op_apply(qob_op *op, int32_t side, qob_c64 alpha, const void *x, qob_c64
                  int64_t batch, void *stream);
 
 /* Same call with HOST buffers: stages x (and y when beta != 0) to the device, applies, copies y back.
- * This is the end-to-end path bench.py times as `e2e`. */
+ * This is the end-to-end path bench.py times as `e2e`.  A LEFT-side batch of kets of at least
+ * 2 x QOB_HOST_PIPE_MIN_BYTES (env, default 32 MiB; 0 disables) is streamed through the device in column
+ * groups: upload of group j+1, kernels of group j and download of group j-1 run on separate streams, so the
+ * call is bound by one direction of the host link.  Pinned (page-locked) host buffers are needed for the
+ * overlap; pageable ones still give correct results. */
 int qob_op_apply_host(qob_op *op, int32_t side, qob_c64 alpha, const qob_c64 *x, qob_c64 beta,
                       qob_c64 *y, int64_t batch);
 

@@ -654,6 +654,8 @@ int qob_ctx_create(int device, qob_ctx **out) {
 int qob_ctx_destroy(qob_ctx *ctx) {
   if (!ctx) return QOB_STATUS_OK;
   ctx->clear_scratch();
+  for (cudaStream_t st : ctx->pipe_streams)
+    if (st) cudaStreamDestroy(st);
   delete ctx;
   return QOB_STATUS_OK;
 }
@@ -857,6 +859,81 @@ int qob_op_apply(qob_op *op, int32_t side, qob_c64 alpha, const void *x, qob_c64
   return op->apply(side, C(alpha), x, C(beta), y, batch, (cudaStream_t)stream);
 }
 
+static int64_t env_int64(const char *name, int64_t dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoll(v) : dflt;
+}
+
+// Host-buffer apply of `batch` kets in groups of `g` columns over two lanes (device buffer pairs) and three streams:
+// up (H2D), one compute stream per lane, down (D2H).  Events only order what must be ordered:
+//   up:   x_j after lane's previous apply has consumed its x buffer (and y_j staged after the previous download, beta != 0)
+//   lane: apply_j after x_j (and y_j) are up and the lane's previous result has gone down
+//   down: y_j after apply_j
+static int apply_host_pipelined(qob_op *op, cplx alpha, const qob_c64 *x, cplx beta, qob_c64 *y, int64_t batch, int64_t g,
+                                int64_t d_in, int64_t d_out) {
+  qob_ctx *ctx = op->ctx;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (int i = 0; i < 4; ++i)
+      if (!ctx->pipe_streams[i]) QOB_CUDA(cudaStreamCreateWithFlags(&ctx->pipe_streams[i], cudaStreamNonBlocking));
+  }
+  cudaStream_t up = ctx->pipe_streams[0], down = ctx->pipe_streams[1], lane[2] = {ctx->pipe_streams[2], ctx->pipe_streams[3]};
+  void *dx[2] = {nullptr, nullptr}, *dy[2] = {nullptr, nullptr};
+  for (int l = 0; l < 2; ++l) {
+    QOB_TRY(ctx->get_scratch(lane[l], op->slot_base + 6, (size_t)std::max<int64_t>(1, d_in * g) * 16, &dx[l]));
+    QOB_TRY(ctx->get_scratch(lane[l], op->slot_base + 7, (size_t)std::max<int64_t>(1, d_out * g) * 16, &dy[l]));
+  }
+  cudaEvent_t e_up[2], e_done[2], e_down[2];
+  for (int l = 0; l < 2; ++l) {
+    QOB_CUDA(cudaEventCreateWithFlags(&e_up[l], cudaEventDisableTiming));
+    QOB_CUDA(cudaEventCreateWithFlags(&e_done[l], cudaEventDisableTiming));
+    QOB_CUDA(cudaEventCreateWithFlags(&e_down[l], cudaEventDisableTiming));
+  }
+  int rc = QOB_STATUS_OK;
+  const int64_t ngroups = (batch + g - 1) / g;
+  for (int64_t j = 0; j < ngroups && rc == QOB_STATUS_OK; ++j) {
+    const int l = (int)(j & 1);
+    const int64_t c0 = j * g, nc = std::min(g, batch - c0);
+    cudaError_t ce = cudaSuccess;
+    auto ok = [&](cudaError_t e) { if (ce == cudaSuccess) ce = e; };
+    if (j >= 2) ok(cudaStreamWaitEvent(up, e_done[l], 0));
+    ok(cudaMemcpyAsync(dx[l], x + c0 * d_in, (size_t)(nc * d_in) * 16, cudaMemcpyHostToDevice, up));
+    if (beta != ZERO) {
+      if (j >= 2) ok(cudaStreamWaitEvent(up, e_down[l], 0));
+      ok(cudaMemcpyAsync(dy[l], y + c0 * d_out, (size_t)(nc * d_out) * 16, cudaMemcpyHostToDevice, up));
+    }
+    ok(cudaEventRecord(e_up[l], up));
+    ok(cudaStreamWaitEvent(lane[l], e_up[l], 0));
+    if (j >= 2) ok(cudaStreamWaitEvent(lane[l], e_down[l], 0));
+    if (ce != cudaSuccess) {
+      qob_set_error("CUDA error in pipelined host apply: %s", cudaGetErrorString(ce));
+      rc = QOB_STATUS_CUDA_ERROR;
+      break;
+    }
+    rc = op->apply(QOB_SIDE_LEFT, alpha, dx[l], beta, dy[l], nc, lane[l]);
+    if (rc != QOB_STATUS_OK) break;
+    ok(cudaEventRecord(e_done[l], lane[l]));
+    ok(cudaStreamWaitEvent(down, e_done[l], 0));
+    ok(cudaMemcpyAsync(y + c0 * d_out, dy[l], (size_t)(nc * d_out) * 16, cudaMemcpyDeviceToHost, down));
+    ok(cudaEventRecord(e_down[l], down));
+    if (ce != cudaSuccess) {
+      qob_set_error("CUDA error in pipelined host apply: %s", cudaGetErrorString(ce));
+      rc = QOB_STATUS_CUDA_ERROR;
+    }
+  }
+  cudaError_t e1 = cudaStreamSynchronize(up), e2 = cudaStreamSynchronize(lane[0]), e3 = cudaStreamSynchronize(lane[1]),
+              e4 = cudaStreamSynchronize(down);
+  for (int l = 0; l < 2; ++l) {
+    cudaEventDestroy(e_up[l]);
+    cudaEventDestroy(e_done[l]);
+    cudaEventDestroy(e_down[l]);
+  }
+  if (rc != QOB_STATUS_OK) return rc;
+  for (cudaError_t e : {e1, e2, e3, e4})
+    if (e != cudaSuccess) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "CUDA error in pipelined host apply: %s", cudaGetErrorString(e));
+  return QOB_STATUS_OK;
+}
+
 int qob_op_apply_host(qob_op *op, int32_t side, qob_c64 alpha, const qob_c64 *x, qob_c64 beta, qob_c64 *y,
                       int64_t batch) {
   if (!op) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null operator");
@@ -868,6 +945,16 @@ int qob_op_apply_host(qob_op *op, int32_t side, qob_c64 alpha, const qob_c64 *x,
   if ((const void *)x == (const void *)y) QOB_FAIL(QOB_STATUS_ALIASING, "output matrix must not be aliased with input matrix");
   if (op->ctx->device < 0) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
   QOB_CUDA(cudaSetDevice(op->ctx->device));
+  const int64_t d_in = side == QOB_SIDE_LEFT ? op->dr : op->dl, d_out = side == QOB_SIDE_LEFT ? op->dl : op->dr;
+  // A batch of kets (LEFT side: the columns are contiguous) that is large enough is streamed through the device in column
+  // groups: group j+1 goes up on one copy engine while group j is applied and group j-1 comes down on the other, so the
+  // call is bound by ONE direction of the host link instead of the sum of both directions plus the kernels.
+  const int64_t pipe_min = env_int64("QOB_HOST_PIPE_MIN_BYTES", 32ll << 20);
+  const int64_t col_bytes = 16 * std::max(d_in, d_out);
+  if (side == QOB_SIDE_LEFT && batch >= 2 && pipe_min > 0 && col_bytes * batch >= 2 * pipe_min) {
+    const int64_t g = std::max<int64_t>(1, std::min<int64_t>(batch / 2, pipe_min / col_bytes));
+    return apply_host_pipelined(op, C(alpha), x, C(beta), y, batch, g, d_in, d_out);
+  }
   void *dx = nullptr, *dy = nullptr;
   cudaStream_t s = 0;
   QOB_TRY(op->ctx->get_scratch(s, op->slot_base + 6, (size_t)std::max<int64_t>(1, n_in) * 16, &dx));

@@ -73,6 +73,7 @@ struct qob_ctx {
   // scratch slots keyed by (stream, slot): the analogue of the reference's LRU temp cache keyed by
   // (stage symbol, task id) — operators_lazytensor.jl:303-315
   std::map<std::pair<cudaStream_t, int>, DevBuf> scratch;
+  cudaStream_t pipe_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // up, down, two compute lanes (qob_op_apply_host)
   int get_scratch(cudaStream_t s, int slot, size_t bytes, void **out);
   int64_t scratch_bytes();
   void clear_scratch();

@@ -363,6 +363,43 @@ def test_apply_host_end_to_end(Q):
     assert H.rel_err(y, ref.o.data) <= TOL
 
 
+@pytest.mark.parametrize("pipe_min,batch", [(16384, 7), (40000, 7), (16384, 2), (0, 5)])
+@pytest.mark.parametrize("beta", [0.0, 0.4 - 1.1j])
+def test_apply_host_batch_of_kets_is_pipelined(Q, monkeypatch, pipe_min, batch, beta):
+    """qob_op_apply_host on a batch of host kets streams column groups through two device lanes (H2D / apply / D2H on
+    separate streams): groups of 1 and of 2 columns with a ragged last group, the two-group minimum, and the plain
+    path (pipe_min = 0 disables the pipeline).  beta != 0 also stages y."""
+    monkeypatch.setenv("QOB_HOST_PIPE_MIN_BYTES", str(pipe_min))
+    rng = np.random.default_rng(91)
+    dims, coefs, terms = _chain_terms(10, "heis", False, rng)
+    s = H.lazysum(dims, dims, coefs, terms)
+    D = 1 << 10
+    x, y0 = H.rnd(rng, D, batch), H.rnd(rng, D, batch)
+    ref = H.denseop(dims, (batch,), y0)
+    O.mul(ref.o, s.o, H.denseop(dims, (batch,), x).o, 0.3 + 0.2j, beta)
+    y = np.ascontiguousarray(y0.reshape(-1, order="F"))
+    l0 = Q.launch_count()
+    Q.apply_host(s.q, x, alpha=0.3 + 0.2j, beta=beta, y=y, batch=batch)
+    assert H.rel_err(y, np.asarray(ref.o.data).reshape(-1, order="F")) <= TOL
+    col = 16 * D
+    groups = 1 if pipe_min == 0 or col * batch < 2 * pipe_min else -(-batch // max(1, min(batch // 2, pipe_min // col)))
+    assert Q.launch_count() - l0 >= groups   # one apply per column group
+
+
+def test_apply_host_pipelined_isometry(Q, monkeypatch):
+    """different input and output dimensions per ket (Eye isometry factor) through the pipelined host path"""
+    monkeypatch.setenv("QOB_HOST_PIPE_MIN_BYTES", "4096")
+    rng = np.random.default_rng(92)
+    dl, dr = (3, 4, 5), (3, 6, 5)
+    op = H.lazytensor(dl, dr, [1, 3], [H.sprnd(rng, 3, 3), H.rnd(rng, 5, 5)], factor=0.7)
+    batch = 9
+    x = H.rnd(rng, 90, batch)
+    ref = H.denseop(dl, (batch,), np.zeros((60, batch), dtype=complex))
+    O.mul(ref.o, op.o, H.denseop(dr, (batch,), x).o, 1.0, 0.0)
+    y = Q.apply_host(op.q, x, batch=batch)
+    assert H.rel_err(y, np.asarray(ref.o.data).reshape(-1, order="F")) <= TOL
+
+
 def test_expect_and_variance(Q):
     """expect / variance built on mul! + a device reduction (src/operators.jl:119-150)."""
     rng = np.random.default_rng(95)
