@@ -203,3 +203,88 @@ def test_sharded_apply_nccl(tmp_path, beta, fused, n):
     spec = chain_spec(n, 21)
     ref = oracle_result(n, spec, 0.7 - 0.2j, beta, O.fill_state(1 << n, 3, 2.0 ** (-n / 2)), O.fill_state(1 << n, 4, 1.0))
     assert H.rel_err(got, ref) <= 1e-12
+
+
+def _spot(spec, index, xval):
+    """(H x)[index] from the definition (each output amplitude of a 2-site-term LazySum depends on <= 1 + n_terms inputs)"""
+    acc = 0.0 + 0.0j
+    for c, idx, a in spec:
+        A = PAULI[a]
+        k1, k2 = idx[0] - 1, idx[1] - 1
+        i1, i2 = (index >> k1) & 1, (index >> k2) & 1
+        for j1 in (0, 1):
+            for j2 in (0, 1):
+                w = A[i1, j1] * A[i2, j2]
+                if w != 0:
+                    acc += c * w * xval((index & ~((1 << k1) | (1 << k2))) | (j1 << k1) | (j2 << k2))
+    return acc
+
+
+def _full_size_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        import qob200 as Q
+        from qob200.dist import ShardedLazySum
+
+        p = world.bit_length() - 1
+        free, _ = torch.cuda.mem_get_info()
+        n = 33
+        while 3 * 16 * (1 << (n - p)) > 0.85 * free and n > 20:   # x, y, contributions: the same rule as bench.py
+            n -= 1
+        nloc = n - p
+        spec = chain_spec(n, 37)
+        sh = ShardedLazySum(build_q(Q, n, spec), rank, world)
+        seed, scale, al = 4321, 2.0 ** (-n / 2), 0.7 - 0.4j
+        x = sh.empty_state()
+        Q.fill_state(x, seed, scale, offset=rank << nloc)
+        y = torch.full((1 << nloc,), float("nan"), dtype=torch.complex128, device="cuda")   # beta = 0 must not read y
+        sh.mul_fused_(y, x, al, 0.0)
+        sh.mul_fused_(y, x, al, 0.0)   # again: the contribution buffer is reused
+        # ---- exact spot oracle: slab boundaries, tile / chunk boundaries, random places
+        L = 1 << nloc
+        rng = np.random.default_rng(500 + rank)
+        loc = [0, 1, 4095, 4096, L - 1, L - 2, L // 2, L // 2 - 1, L // 4, 3 * (L // 4) - 1, 0x55555555 % L, 0x2AAAAAAA % L]
+        loc += [int(v) for v in rng.integers(0, L, 52)]
+        got = y[torch.tensor(loc, device="cuda")].cpu().numpy()
+        ref = np.array([al * _spot(spec, (rank << nloc) | i, lambda j: O.state_at(seed, j, scale)) for i in loc])
+        err = float(np.abs(got - ref).max() / np.abs(ref).max())
+        # ---- Hermiticity: <x|Hx> summed over the ranks is real for real coefficients; all of y is finite
+        d = torch.tensor([complex(Q.dot(x, y) / al)], dtype=torch.complex128, device="cuda")
+        dr = torch.view_as_real(d).clone()
+        dist.all_reduce(dr)
+        nrm = torch.tensor([Q.norm2(y)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(nrm)
+        with open(os.path.join(out_dir, f"r{rank}.txt"), "w") as f:
+            f.write(f"{n} {err:.3e} {float(dr[0, 0]):.17g} {float(dr[0, 1]):.3e} {float(nrm[0]):.17g} {sh.nchunks}\n")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_apply_full_size_spot_oracle(tmp_path):
+    """BASELINE config 5 at the size bench.py runs (N=33 on 4/8 GPUs, N=32 on 2): the fused sharded apply against the
+    exact per-amplitude oracle at sampled indices of every slab, plus <x|Hx> real and a finite norm."""
+    import torch
+    import torch.multiprocessing as mp
+
+    world = 1
+    while world * 2 <= min(torch.cuda.device_count(), 8):
+        world *= 2
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    mp.spawn(_full_size_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    lines = []
+    for r in range(world):
+        n, err, re, im, nrm, nch = open(tmp_path / f"r{r}.txt").read().split()
+        assert float(err) <= 1e-12, f"rank {r}: spot oracle {err}"
+        assert abs(float(im)) <= 1e-12 * max(1.0, abs(float(re)))
+        assert np.isfinite(float(nrm)) and float(nrm) > 0
+        lines.append(f"rank {r}: N={n} chunks={nch} spot_oracle_max_rel_err={err} <x|Hx>={re}{float(im):+.1e}i |y|^2={nrm}")
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, f"full_size_spot_{world}gpu.txt"), "w") as f:
+            f.write("\n".join(lines) + "\n")
