@@ -521,7 +521,7 @@ struct SparseOp : qob_op {
   }
   std::string describe(int, int64_t) override {
     return "sparse " + std::to_string(dl) + "x" + std::to_string(dr) + " nnz=" + std::to_string(m.vals.size()) +
-           " spmm(thread-per-output, CSR gather)";
+           " spmm(CSR/CSC gather, 1-4 outputs per thread" + (csc.order.n ? ", right side in Cuthill-McKee column order)" : ")");
   }
 };
 
@@ -727,6 +727,48 @@ static int sparse_upload(const std::vector<int32_t> &ptr, const std::vector<int3
   return QOB_STATUS_OK;
 }
 
+// Cuthill-McKee ordering of the graph of a square sparse operator (pattern of M + M^T): breadth-first from a
+// minimum-degree vertex of every component, neighbours by increasing degree.  The right-side SpMM walks its output
+// columns in this order so that the input columns it gathers from stay close in time (L2 reuse).
+static std::vector<int32_t> cuthill_mckee_order(const HostMat &m) {
+  const int64_t n = m.cols;
+  std::vector<std::vector<int32_t>> adj((size_t)n);
+  for (int64_t c = 0; c < n; ++c)
+    for (int64_t p = m.colptr[c]; p < m.colptr[c + 1]; ++p) {
+      const int64_t r = m.rowidx[p];
+      if (r == c) continue;
+      adj[(size_t)c].push_back((int32_t)r);
+      adj[(size_t)r].push_back((int32_t)c);
+    }
+  for (auto &a : adj) {
+    std::sort(a.begin(), a.end());
+    a.erase(std::unique(a.begin(), a.end()), a.end());
+  }
+  std::vector<int32_t> by_degree((size_t)n), order;
+  for (int64_t i = 0; i < n; ++i) by_degree[(size_t)i] = (int32_t)i;
+  std::stable_sort(by_degree.begin(), by_degree.end(), [&](int32_t a, int32_t b) { return adj[a].size() < adj[b].size(); });
+  std::vector<char> seen((size_t)n, 0);
+  order.reserve((size_t)n);
+  for (int32_t start : by_degree) {
+    if (seen[start]) continue;
+    seen[start] = 1;
+    size_t head = order.size();
+    order.push_back(start);
+    while (head < order.size()) {
+      const int32_t v = order[head++];
+      std::vector<int32_t> nb;
+      for (int32_t w : adj[v])
+        if (!seen[w]) {
+          seen[w] = 1;
+          nb.push_back(w);
+        }
+      std::stable_sort(nb.begin(), nb.end(), [&](int32_t a, int32_t b) { return adj[a].size() < adj[b].size(); });
+      for (int32_t w : nb) order.push_back(w);
+    }
+  }
+  return order;
+}
+
 int qob_sparse_create(qob_ctx *ctx, const qob_factor *f, qob_op **out) {
   if (!ctx || !out || !f) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null argument");
   PlanningScope ps(ctx->device < 0);
@@ -742,6 +784,12 @@ int qob_sparse_create(qob_ctx *ctx, const qob_factor *f, qob_op **out) {
   QOB_TRY(sparse_upload(rp, ci, v, op->csr));
   std::vector<int32_t> cp(op->m.colptr.begin(), op->m.colptr.end()), ri(op->m.rowidx.begin(), op->m.rowidx.end());
   QOB_TRY(sparse_upload(cp, ri, op->m.vals, op->csc));
+  if (op->m.rows == op->m.cols && op->m.cols >= 1024) {
+    std::vector<int32_t> order = cuthill_mckee_order(op->m);
+    bool identity = true;
+    for (size_t i = 0; i < order.size() && identity; ++i) identity = order[i] == (int32_t)i;
+    if (!identity) QOB_TRY(op->csc.order.upload(order));
+  }
   *out = op.release();
   return QOB_STATUS_OK;
 }

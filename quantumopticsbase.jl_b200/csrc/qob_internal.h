@@ -134,6 +134,7 @@ int launch_axis_dense(const AxisMatrixDev &A, int64_t L, int64_t R, cplx alpha, 
 struct SparseDev {
   DevArray<int32_t> ptr, idx;
   DevArray<double2> val;
+  DevArray<int32_t> order;   // CSC only, optional: column processing order of the right-side SpMM (Cuthill-McKee)
   int64_t nptr = 0;
 };
 int launch_spmm_left(const SparseDev &csr, int64_t m, int64_t k, int64_t n, cplx alpha, const void *B, cplx beta,

@@ -460,14 +460,132 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Large operands (the bandwidth regime): several outputs per thread.  One output per thread leaves a single 16-byte load in
+// flight behind a rowptr -> colidx -> B dependency chain, far below the bytes in flight HBM3e needs; here a thread
+// reads its CSR row (CSC column) ONCE and gathers for CPT columns (RPT rows) with independent loads.  blockIdx.x =
+// (column group, row block) with the row block fastest, so CTAs running together work on the same few columns of B.
+template <int CPT>
+__global__ void __launch_bounds__(256)
+    spmm_left_multi_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double2 *__restrict__ val,
+                           long long m, long long k, long long n, double2 alpha, double2 beta, int beta_zero,
+                           const double2 *__restrict__ B, double2 *__restrict__ R, unsigned row_blocks) {
+  const unsigned rb = blockIdx.x % row_blocks, cg = blockIdx.x / row_blocks;
+  const long long i = (long long)rb * 256 + threadIdx.x;
+  if (i >= m) return;
+  const long long c0 = (long long)cg * CPT;
+  const int nc = (int)min((long long)CPT, n - c0);
+  const int p0 = rowptr[i], p1 = rowptr[i + 1];
+  double re[CPT], im[CPT];
+#pragma unroll
+  for (int u = 0; u < CPT; ++u) re[u] = im[u] = 0.0;
+  const double2 *b = B + c0 * k;
+  for (int p = p0; p < p1; ++p) {
+    const double2 v = val[p];
+    const double2 *bp = b + colidx[p];
+    double2 w[CPT];
+#pragma unroll
+    for (int u = 0; u < CPT; ++u)
+      if (u < nc) w[u] = bp[(long long)u * k];
+#pragma unroll
+    for (int u = 0; u < CPT; ++u)
+      if (u < nc) {
+        re[u] = fma(v.x, w[u].x, re[u]);
+        re[u] = fma(-v.y, w[u].y, re[u]);
+        im[u] = fma(v.x, w[u].y, im[u]);
+        im[u] = fma(v.y, w[u].x, im[u]);
+      }
+  }
+  double2 *r = R + c0 * m + i;
+  double2 yo[CPT];
+  if (!beta_zero) {
+#pragma unroll
+    for (int u = 0; u < CPT; ++u)
+      if (u < nc) yo[u] = r[(long long)u * m];
+  }
+#pragma unroll
+  for (int u = 0; u < CPT; ++u)
+    if (u < nc) {
+      double2 o = make_double2(alpha.x * re[u] - alpha.y * im[u], alpha.x * im[u] + alpha.y * re[u]);
+      if (!beta_zero) {
+        o.x += beta.x * yo[u].x - beta.y * yo[u].y;
+        o.y += beta.x * yo[u].y + beta.y * yo[u].x;
+      }
+      r[(long long)u * m] = o;
+    }
+}
+
+// `order` (may be null) is the sequence in which the output columns are processed: a Cuthill-McKee ordering of the
+// operator's graph, so that the columns of B an output column gathers from are the ones its neighbours in time gather
+// from too and come out of L2 (for a Jaynes-Cummings H the partner column is ~D/2 columns = hundreds of MB away).
+template <int RPT>
+__global__ void __launch_bounds__(256)
+    spmm_right_multi_kernel(const int *__restrict__ colptr, const int *__restrict__ rowidx, const double2 *__restrict__ val,
+                            long long q, long long m, long long n, double2 alpha, double2 beta, int beta_zero,
+                            const double2 *__restrict__ B, double2 *__restrict__ R, unsigned row_blocks,
+                            const int *__restrict__ order) {
+  const unsigned rb = blockIdx.x % row_blocks, cb = blockIdx.x / row_blocks;
+  const long long c = order ? order[cb] : cb;
+  const long long r0 = (long long)rb * (256 * RPT) + threadIdx.x;
+  const int p0 = colptr[c], p1 = colptr[c + 1];
+  double re[RPT], im[RPT];
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) re[u] = im[u] = 0.0;
+  for (int p = p0; p < p1; ++p) {
+    const double2 v = val[p];
+    const double2 *bp = B + q * (long long)rowidx[p] + r0;
+    double2 w[RPT];
+#pragma unroll
+    for (int u = 0; u < RPT; ++u)
+      if (r0 + u * 256 < q) w[u] = bp[u * 256];
+#pragma unroll
+    for (int u = 0; u < RPT; ++u)
+      if (r0 + u * 256 < q) {
+        re[u] = fma(v.x, w[u].x, re[u]);
+        re[u] = fma(-v.y, w[u].y, re[u]);
+        im[u] = fma(v.x, w[u].y, im[u]);
+        im[u] = fma(v.y, w[u].x, im[u]);
+      }
+  }
+  double2 *r = R + c * q + r0;
+  double2 yo[RPT];
+  if (!beta_zero) {
+#pragma unroll
+    for (int u = 0; u < RPT; ++u)
+      if (r0 + u * 256 < q) yo[u] = r[u * 256];
+  }
+#pragma unroll
+  for (int u = 0; u < RPT; ++u)
+    if (r0 + u * 256 < q) {
+      double2 o = make_double2(alpha.x * re[u] - alpha.y * im[u], alpha.x * im[u] + alpha.y * re[u]);
+      if (!beta_zero) {
+        o.x += beta.x * yo[u].x - beta.y * yo[u].y;
+        o.y += beta.x * yo[u].y + beta.y * yo[u].x;
+      }
+      r[u * 256] = o;
+    }
+}
+
+static const int64_t kSpmmFill = 148 * 2048;   // outputs that give every SM a full complement of threads
+
 int launch_spmm_left(const SparseDev &csr, int64_t m, int64_t k, int64_t n, cplx alpha, const void *B, cplx beta,
                      void *R, cudaStream_t s) {
   if (m * n == 0) return QOB_STATUS_OK;
-  int64_t blocks = std::min<int64_t>((m * n + 255) / 256, (int64_t)1 << 30);
-  spmm_left_kernel<<<(unsigned)blocks, 256, 0, s>>>(csr.ptr.ptr, csr.idx.ptr, csr.val.ptr, m, k, n,
-                                                    make_double2(alpha.real(), alpha.imag()),
-                                                    make_double2(beta.real(), beta.imag()), beta == cplx(0.0, 0.0),
-                                                    (const double2 *)B, (double2 *)R);
+  const double2 a2 = make_double2(alpha.real(), alpha.imag()), b2 = make_double2(beta.real(), beta.imag());
+  const int bz = beta == cplx(0.0, 0.0);
+  const int cpt = (n >= 4 && m * n >= 4 * kSpmmFill) ? 4 : (n >= 2 && m * n >= 2 * kSpmmFill) ? 2 : 1;
+  const int64_t row_blocks = (m + 255) / 256, blocks_multi = row_blocks * ((n + cpt - 1) / cpt);
+  if (m >= 256 && cpt > 1 && blocks_multi < ((int64_t)1 << 31)) {
+    if (cpt == 4)
+      spmm_left_multi_kernel<4><<<(unsigned)blocks_multi, 256, 0, s>>>(csr.ptr.ptr, csr.idx.ptr, csr.val.ptr, m, k, n, a2, b2, bz,
+                                                                       (const double2 *)B, (double2 *)R, (unsigned)row_blocks);
+    else
+      spmm_left_multi_kernel<2><<<(unsigned)blocks_multi, 256, 0, s>>>(csr.ptr.ptr, csr.idx.ptr, csr.val.ptr, m, k, n, a2, b2, bz,
+                                                                       (const double2 *)B, (double2 *)R, (unsigned)row_blocks);
+  } else {
+    int64_t blocks = std::min<int64_t>((m * n + 255) / 256, (int64_t)1 << 30);
+    spmm_left_kernel<<<(unsigned)blocks, 256, 0, s>>>(csr.ptr.ptr, csr.idx.ptr, csr.val.ptr, m, k, n, a2, b2, bz,
+                                                      (const double2 *)B, (double2 *)R);
+  }
   QOB_LAUNCHED();
   QOB_CUDA(cudaGetLastError());
   return QOB_STATUS_OK;
@@ -476,11 +594,23 @@ int launch_spmm_left(const SparseDev &csr, int64_t m, int64_t k, int64_t n, cplx
 int launch_spmm_right(const SparseDev &csc, int64_t q, int64_t m, int64_t n, cplx alpha, const void *B, cplx beta,
                       void *R, cudaStream_t s) {
   if (q * n == 0) return QOB_STATUS_OK;
-  int64_t blocks = std::min<int64_t>((q * n + 255) / 256, (int64_t)1 << 30);
-  spmm_right_kernel<<<(unsigned)blocks, 256, 0, s>>>(csc.ptr.ptr, csc.idx.ptr, csc.val.ptr, q, m, n,
-                                                     make_double2(alpha.real(), alpha.imag()),
-                                                     make_double2(beta.real(), beta.imag()), beta == cplx(0.0, 0.0),
-                                                     (const double2 *)B, (double2 *)R);
+  const double2 a2 = make_double2(alpha.real(), alpha.imag()), b2 = make_double2(beta.real(), beta.imag());
+  const int bz = beta == cplx(0.0, 0.0);
+  const int rpt = (q >= 1024 && q * n >= 4 * kSpmmFill) ? 4 : (q >= 512 && q * n >= 2 * kSpmmFill) ? 2 : 1;
+  const int64_t row_blocks = (q + 256 * rpt - 1) / (256 * rpt), blocks_multi = row_blocks * n;
+  if (rpt > 1 && blocks_multi < ((int64_t)1 << 31)) {
+    const int *order = csc.order.n == (size_t)n ? csc.order.ptr : nullptr;
+    if (rpt == 4)
+      spmm_right_multi_kernel<4><<<(unsigned)blocks_multi, 256, 0, s>>>(csc.ptr.ptr, csc.idx.ptr, csc.val.ptr, q, m, n, a2, b2, bz,
+                                                                        (const double2 *)B, (double2 *)R, (unsigned)row_blocks, order);
+    else
+      spmm_right_multi_kernel<2><<<(unsigned)blocks_multi, 256, 0, s>>>(csc.ptr.ptr, csc.idx.ptr, csc.val.ptr, q, m, n, a2, b2, bz,
+                                                                        (const double2 *)B, (double2 *)R, (unsigned)row_blocks, order);
+  } else {
+    int64_t blocks = std::min<int64_t>((q * n + 255) / 256, (int64_t)1 << 30);
+    spmm_right_kernel<<<(unsigned)blocks, 256, 0, s>>>(csc.ptr.ptr, csc.idx.ptr, csc.val.ptr, q, m, n, a2, b2, bz,
+                                                       (const double2 *)B, (double2 *)R);
+  }
   QOB_LAUNCHED();
   QOB_CUDA(cudaGetLastError());
   return QOB_STATUS_OK;

@@ -230,6 +230,44 @@ def test_sparse_gemm_gemv(Q, shape):
         Q.mul_(Q.Ket(Q.GenericBasis(m + 1)), op.q, Q.Ket(op.q.basis_r))
 
 
+@pytest.mark.parametrize("m,k,n", [(1201, 1201, 1103), (1300, 1100, 517), (700, 650, 901)])
+def test_sparse_gemm_bandwidth_regime(Q, m, k, n):
+    """Operands large enough for the several-outputs-per-thread SpMM kernels (4 and 2 columns / rows per thread, ragged
+    edges); the square case is >= 1024 wide, so the right-side product walks its columns in Cuthill-McKee order."""
+    rng = np.random.default_rng(33)
+    M = sp.random(m, k, density=4.0 / k, random_state=np.random.RandomState(5), format="csc", dtype=float).astype(complex)
+    M.data = H.rnd(rng, M.nnz)
+    op = H.operator((m,), (k,), M)
+    if m == k:
+        assert "Cuthill-McKee" in Q.describe(op.q)
+    H.check_mul(op, (m,), (k,), rng, tol=TOL, nbatch=n, kinds=("opl", "opr"), scalars=((1.5, 2.1), (-1j, 0)))
+    opa = H.operator((k,), (m,), ("adj", M))
+    H.check_mul(opa, (k,), (m,), rng, tol=TOL, nbatch=n, kinds=("opl", "opr"), scalars=((0.3 - 0.2j, 1),))
+
+
+def test_jaynes_cummings_large_cutoff_commutator(Q):
+    """BASELINE config 2 in its bandwidth regime (cutoff 1024, dim 2050): the partner column of the coupling term is
+    ~D/2 columns away; same two mul! calls as the small case, against the oracle's CSC loops."""
+    nc = 1024
+    nf = nc + 1
+    a, ad, num = O.destroy(nc).data, O.create(nc).data, O.number(nc).data
+    sz, spl, smi = O.sigmaz().data, O.sigmap().data, O.sigmam().data
+    i2, inf = sp.identity(2, format="csc"), sp.identity(nf, format="csc")
+    Hm = (1.0 * sp.kron(i2, num) + 0.45 * sp.kron(sz, inf) + 0.1 * (sp.kron(spl, a) + sp.kron(smi, ad))).tocsc()
+    D = 2 * nf
+    rng = np.random.default_rng(34)
+    op = H.operator((D,), (D,), Hm)
+    assert "Cuthill-McKee" in Q.describe(op.q)
+    rho = H.rnd(rng, D, D)
+    s = H.denseop((D,), (D,), rho)
+    r = H.denseop((D,), (D,), np.zeros((D, D), dtype=complex))
+    O.mul(r.o, op.o, s.o, -1j, 0.0)
+    O.mul(r.o, s.o, op.o, 1j, 1.0)
+    Q.mul_(r.q, op.q, s.q, -1j, 0.0)
+    Q.mul_(r.q, s.q, op.q, 1j, 1.0)
+    assert H.rel_err(r.q.to_host(), r.o.data) <= TOL
+
+
 def test_dense_operator_as_operator(Q):
     rng = np.random.default_rng(31)
     for (m, k) in [(7, 5), (40, 33)]:
