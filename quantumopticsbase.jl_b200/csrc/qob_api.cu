@@ -257,8 +257,9 @@ struct Compiled {
   int64_t batch;
   std::vector<int64_t> dims_out, dims_in;
   int64_t d_out = 1, d_in = 1;
-  bool has_qtile = false, has_gather = false;
+  bool has_qtile = false, has_gather = false, has_dtile = false;
   QTileProgram qtile;
+  DTileProgram dtile;
   GatherProgram gather;
   std::vector<std::unique_ptr<SeqTerm>> seq;
   std::string text;
@@ -407,12 +408,51 @@ int TensorGroup::compile(int side, int64_t batch, Compiled **out) {
       c.has_qtile = true;
     }
   }
+  if (!gterms.empty() && all_same && !env_i("QOB_DISABLE_DTILE", 0) &&
+      (double)c.d_out * (double)batch >= (double)env_i("QOB_DTILE_MIN_ELEMS", 1 << 18)) {
+    // large state on subsystems of any dimension: mixed-radix tile passes.  The batch is one more tensor axis: the
+    // slowest one for op*X, the fastest one for X*op (split in two when it is long, so that a short run of it can be
+    // the coalesced low block of every tile).
+    std::vector<int64_t> dd;
+    int shift = 0;
+    bool ok = true;
+    if (side == QOB_SIDE_RIGHT && batch > 1) {
+      int64_t lo = batch;
+      if (batch > 64) {
+        lo = 0;
+        for (int64_t v = 64; v >= 8 && !lo; --v)
+          if (batch % v == 0) lo = v;
+        if (!lo) ok = batch <= 256, lo = batch;
+      }
+      dd.push_back(lo);
+      shift = 1;
+      if (lo != batch) {
+        dd.push_back(batch / lo);
+        shift = 2;
+      }
+    }
+    for (int k = 0; k < n; ++k) dd.push_back(c.dims_out[k]);
+    if (side == QOB_SIDE_LEFT && batch > 1) dd.push_back(batch);
+    if (ok) {
+      std::vector<OrientedTerm> shifted = gterms;
+      for (auto &o : shifted)
+        for (int &a : o.axes) a += shift;
+      const int st = dtile_build(c.dtile, dd, shifted);
+      if (st == QOB_STATUS_OK) {
+        c.has_dtile = true;
+        gterms.clear();
+      } else if (st != QOB_STATUS_UNSUPPORTED) {
+        return st;
+      }
+    }
+  }
   if (!gterms.empty()) {
     QOB_TRY(gather_program_build(c.gather, c.dims_out, c.dims_in, gterms));
     c.has_gather = true;
   }
   c.text = std::string(side == QOB_SIDE_LEFT ? "left" : "right") + " batch=" + std::to_string(batch) + ":";
   if (c.has_qtile) c.text += " " + c.qtile.describe;
+  if (c.has_dtile) c.text += " " + c.dtile.describe;
   if (c.has_gather) c.text += " " + c.gather.describe;
   if (!c.seq.empty()) {
     c.text += " seq[terms=" + std::to_string(c.seq.size()) + ":";
@@ -434,6 +474,7 @@ int TensorGroup::apply(int side, cplx alpha, const void *x, cplx beta, void *y, 
   if (coefs_dirty || coefs != last_coefs) {
     for (auto &cc : cache) {
       if (cc->has_qtile) QOB_TRY(qtile_set_coefs(cc->qtile, coefs, s));
+      if (cc->has_dtile) QOB_TRY(dtile_set_coefs(cc->dtile, coefs, s));
       if (cc->has_gather) QOB_TRY(gather_program_set_coefs(cc->gather, coefs, s));
     }
     last_coefs = coefs;
@@ -447,6 +488,7 @@ int TensorGroup::apply(int side, cplx alpha, const void *x, cplx beta, void *y, 
     return b;
   };
   if (c.has_qtile) QOB_TRY(qtile_launch(c.qtile, alpha, x, beta_now(), y, s));
+  if (c.has_dtile) QOB_TRY(dtile_launch(c.dtile, alpha, x, beta_now(), y, s));
   if (c.has_gather) QOB_TRY(gather_program_launch(c.gather, pre, post, alpha, x, beta_now(), y, s));
   for (auto &stp : c.seq) {
     SeqTerm &st = *stp;

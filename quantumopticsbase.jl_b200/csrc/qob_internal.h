@@ -203,6 +203,19 @@ int qtile_set_chunk_bits(QTileProgram &p, uint64_t chunk_mask);
 int qtile_launch(const QTileProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s,
                  const QLaunchOpts *opts = nullptr);
 
+// Mixed-radix tile program (any subsystem dimensions, large states) --------------------------
+struct DTileProgramHost;
+struct DTileProgram {
+  std::shared_ptr<DTileProgramHost> h;
+  std::string describe;
+  int npasses = 0;
+};
+// dims: every tensor axis of the state incl. the batch axis (fastest first); terms: square oriented factors on those axes.
+// Returns QOB_STATUS_UNSUPPORTED when the terms do not fit the scheme (the caller then uses the gather kernel).
+int dtile_build(DTileProgram &p, const std::vector<int64_t> &dims, const std::vector<OrientedTerm> &terms);
+int dtile_set_coefs(DTileProgram &p, const std::vector<cplx> &coefs, cudaStream_t s);
+int dtile_launch(const DTileProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s);
+
 // misc device helpers
 int launch_fill_state(void *x, int64_t offset, int64_t n, uint64_t seed, double scale, cudaStream_t s);
 int launch_norm2(const void *x, int64_t n, double *host_out, cudaStream_t s);

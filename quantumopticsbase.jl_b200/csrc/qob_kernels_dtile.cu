@@ -1,0 +1,573 @@
+// qob_kernels_dtile.cu — mixed-radix tile passes: the fused LazySum kernel for LARGE states on subsystems of ANY
+// dimension (Fock, spin-1, N-level ... lattices), the counterpart of qob_kernels_qtile.cu for non-qubit systems.
+//
+// Reference semantics: y = beta*y + alpha * sum_t coef_t (A_t x), A_t = (x)_k A_{t,k} on a few tensor axes
+// (src/operators_lazysum.jl:189-200 looping over src/operators_lazytensor.jl:539-557 / :612-751), subsystem 1 fastest.
+//
+// Idea.  Every site factor is split into its shifted diagonals A^(s)[i] = A[i, i+s]; a term then is a sum of
+// "components" that each read ONE source amplitude per output amplitude:
+//        y[..i_k..] += coef * prod_k A_k^(s_k)[i_k] * x[..i_k+s_k..]
+// (number, destroy, create, sigma+-, transition operators have one diagonal; sigmax has two).  A pass picks a set of
+// FREE axes — a low contiguous block (coalesced runs) plus a window of higher axes — whose joint extent fits a
+// shared-memory tile; all terms whose off-diagonal factors lie on free axes are accumulated in that pass from the tile,
+// factors on the other (fixed) axes are diagonal there and fold into one weight per component and CTA.
+// The state is streamed once per pass (read x + read/write y) instead of being gathered from L2 with a mixed-radix
+// index decode per term and amplitude (qob_kernels_gather.cu), which is ALU/latency bound at a few % of HBM peak.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "qob_internal.h"
+
+#define DT_MAXF 4        // factors per component (free + fixed each)
+#define DT_MAXAX 64      // tensor axes (incl. the batch axis)
+#define DT_THREADS 256
+#define DT_U 8           // outputs per thread and sweep
+#define DT_TILE_CAP 4096 // amplitudes per tile (64 KiB)
+
+struct DCompDev {
+  int delta;                        // source element = output element + delta (tile numbering)
+  int coef;                         // index into the per-term coefficient array
+  unsigned char nfree, nfixed, pad0, pad1;
+  unsigned int f_mts[DT_MAXF];      // magic multiplier for division by the tile stride (0: stride 1)
+  unsigned int f_md[DT_MAXF];       // magic multiplier for the modulo by the axis dimension (0: top digit, no modulo)
+  unsigned short f_d[DT_MAXF];      // axis dimension
+  unsigned short f_tab[DT_MAXF];    // weight table (entries of double2) indexed by the output digit on a free axis
+  unsigned short x_tab[DT_MAXF];    // same for fixed axes
+  unsigned char x_slot[DT_MAXF];    // which fixed axis
+  int pad2[2];
+};
+static_assert(sizeof(DCompDev) == 80 && sizeof(DCompDev) % 16 == 0, "component records are copied in 16-byte units");
+
+struct DPassParams {
+  const DCompDev *comps;
+  const double2 *tables;
+  const double2 *coef;
+  const long long *woff;            // global offset of window element w (tile element = r + R*w)
+  int ncomp, ntab;
+  int tile, R;                      // amplitudes per tile; length of the contiguous low run
+  unsigned int mR;                  // magic for division by R (0: R == 1)
+  int nfixed;
+  unsigned int fx_dim[DT_MAXAX];    // fixed axes: dimension, product of the dimensions below (tile-id radix), stride
+  unsigned int fx_below[DT_MAXAX];
+  long long fx_stride[DT_MAXAX];
+  double2 alpha, beta;
+  int mode;                         // 0: y = alpha*acc; 1: y = alpha*acc + beta*y
+};
+
+__device__ __forceinline__ double2 dmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ void dfma(double2 &acc, double2 a, double2 b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+
+__global__ void __launch_bounds__(DT_THREADS) dtile_kernel(const __grid_constant__ DPassParams P,
+                                                           const double2 *__restrict__ x, double2 *__restrict__ y) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *xs = reinterpret_cast<double2 *>(smem_raw);
+  double2 *tab = xs + P.tile;
+  double2 *cw = tab + P.ntab;
+  DCompDev *comps = reinterpret_cast<DCompDev *>(cw + P.ncomp);
+  __shared__ unsigned int fdig[DT_MAXAX];
+  __shared__ long long s_base;
+  const unsigned tid = threadIdx.x;
+
+  // ---- which tile: digits of the fixed axes (one thread per axis), base offset of the tile
+  if (tid < 32) {
+    long long part = 0;
+    for (unsigned a = tid; a < (unsigned)P.nfixed; a += 32) {
+      const unsigned dg = (blockIdx.x / P.fx_below[a]) % P.fx_dim[a];
+      fdig[a] = dg;
+      part += (long long)dg * P.fx_stride[a];
+    }
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (tid == 0) s_base = part;
+  }
+  // ---- operator data of this pass -> shared memory
+  for (int i = tid; i < P.ntab; i += DT_THREADS) tab[i] = P.tables[i];
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(P.comps);
+    uint4 *dst = reinterpret_cast<uint4 *>(comps);
+    const int n16 = P.ncomp * (int)(sizeof(DCompDev) / 16);
+    for (int i = tid; i < n16; i += DT_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const long long base = s_base;
+  // ---- the tile of x: contiguous runs of R amplitudes
+  for (unsigned e = tid; e < (unsigned)P.tile; e += DT_THREADS) {
+    const unsigned w = P.mR ? __umulhi(e, P.mR) : e;
+    const unsigned r = e - w * (unsigned)P.R;
+    const double2 *g = x + base + r + P.woff[w];
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(xs + e);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+  }
+  // ---- per-component weight that is uniform over the tile: coefficient x diagonal factors on fixed axes
+  for (int c = tid; c < P.ncomp; c += DT_THREADS) {
+    const DCompDev &C = comps[c];
+    double2 w = P.coef[C.coef];
+    for (int f = 0; f < C.nfixed; ++f) w = dmul(w, tab[C.x_tab[f] + fdig[C.x_slot[f]]]);
+    cw[c] = w;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+
+  for (unsigned sweep = 0; sweep < (unsigned)P.tile; sweep += DT_THREADS * DT_U) {
+    double2 acc[DT_U];
+#pragma unroll
+    for (int k = 0; k < DT_U; ++k) acc[k] = make_double2(0.0, 0.0);
+    for (int c = 0; c < P.ncomp; ++c) {
+      const DCompDev &C = comps[c];
+      const double2 w0 = cw[c];
+      const int delta = C.delta, nfree = C.nfree;
+      if (nfree == 0) {
+#pragma unroll
+        for (int k = 0; k < DT_U; ++k) {
+          const unsigned e = sweep + k * DT_THREADS + tid;
+          if (e < (unsigned)P.tile) dfma(acc[k], w0, xs[e]);
+        }
+      } else if (nfree == 1) {
+        const unsigned m0 = C.f_mts[0], n0 = C.f_md[0], d0 = C.f_d[0];
+        const double2 *t0 = tab + C.f_tab[0];
+#pragma unroll
+        for (int k = 0; k < DT_U; ++k) {
+          const unsigned e = sweep + k * DT_THREADS + tid;
+          if (e < (unsigned)P.tile) {
+            unsigned q = m0 ? __umulhi(e, m0) : e;
+            if (n0) q -= __umulhi(q, n0) * d0;
+            const double2 w = dmul(w0, t0[q]);
+            if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xs[(int)e + delta]);
+          }
+        }
+      } else if (nfree == 2) {
+        const unsigned m0 = C.f_mts[0], n0 = C.f_md[0], d0 = C.f_d[0];
+        const unsigned m1 = C.f_mts[1], n1 = C.f_md[1], d1 = C.f_d[1];
+        const double2 *t0 = tab + C.f_tab[0], *t1 = tab + C.f_tab[1];
+#pragma unroll
+        for (int k = 0; k < DT_U; ++k) {
+          const unsigned e = sweep + k * DT_THREADS + tid;
+          if (e < (unsigned)P.tile) {
+            unsigned q0 = m0 ? __umulhi(e, m0) : e;
+            if (n0) q0 -= __umulhi(q0, n0) * d0;
+            unsigned q1 = m1 ? __umulhi(e, m1) : e;
+            if (n1) q1 -= __umulhi(q1, n1) * d1;
+            const double2 w = dmul(w0, dmul(t0[q0], t1[q1]));
+            if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xs[(int)e + delta]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < DT_U; ++k) {
+          const unsigned e = sweep + k * DT_THREADS + tid;
+          if (e < (unsigned)P.tile) {
+            double2 w = w0;
+#pragma unroll 1
+            for (int f = 0; f < nfree; ++f) {
+              unsigned q = C.f_mts[f] ? __umulhi(e, C.f_mts[f]) : e;
+              if (C.f_md[f]) q -= __umulhi(q, C.f_md[f]) * C.f_d[f];
+              w = dmul(w, tab[C.f_tab[f] + q]);
+            }
+            if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xs[(int)e + delta]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < DT_U; ++k) {
+      const unsigned e = sweep + k * DT_THREADS + tid;
+      if (e < (unsigned)P.tile) {
+        const unsigned w = P.mR ? __umulhi(e, P.mR) : e;
+        const unsigned r = e - w * (unsigned)P.R;
+        double2 *g = y + base + r + P.woff[w];
+        double2 o = dmul(P.alpha, acc[k]);
+        if (P.mode) dfma(o, P.beta, *g);
+        *g = o;
+      }
+    }
+  }
+}
+
+// ================================================================================ host: planner
+struct DComp {           // host form of a component
+  int term;
+  std::vector<int> axes;                 // factor axes
+  std::vector<int> shift;                // s_k: source digit = output digit + s_k
+  std::vector<std::vector<cplx>> table;  // per factor: weight by output digit (0 where there is no entry)
+};
+struct DPassHost {
+  std::vector<int> free_axes;            // ascending; the first `nlow` are axes 0..nlow-1
+  int nlow = 0;
+  int tile = 1, R = 1;
+  std::vector<int> terms;
+  DevArray<DCompDev> d_comps;
+  DevArray<double2> d_tables;
+  DevArray<long long> d_woff;
+  DPassParams params;
+  size_t smem = 0;
+  int64_t ntiles = 1;
+};
+struct DTileProgramHost {
+  std::vector<int64_t> dims;
+  std::vector<std::unique_ptr<DPassHost>> passes;
+  std::vector<int> coef_of_term;
+  std::vector<cplx> scalars;
+  DevArray<double2> d_coef;
+  int64_t total = 1;
+};
+
+static unsigned magic32(unsigned d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) / d) + 1ull); }
+
+// shifted diagonals of an oriented square factor (rows = output digit, cols = input digit)
+static void factor_diagonals(const HostMat &m, std::vector<int> &shifts, std::vector<std::vector<cplx>> &tables) {
+  const int64_t d = m.rows;
+  std::map<int, std::vector<cplx>> diag;
+  auto put = [&](int64_t i, int64_t j, cplx v) {
+    auto &t = diag[(int)(j - i)];
+    if (t.empty()) t.assign((size_t)d, cplx(0.0, 0.0));
+    t[(size_t)i] += v;
+  };
+  if (m.kind == QOB_FACTOR_CSC) {
+    for (int64_t c = 0; c < m.cols; ++c)
+      for (int64_t p = m.colptr[c]; p < m.colptr[c + 1]; ++p) put(m.rowidx[p], c, m.vals[p]);
+  } else if (m.kind == QOB_FACTOR_DENSE) {
+    for (int64_t c = 0; c < m.cols; ++c)
+      for (int64_t r = 0; r < m.rows; ++r) put(r, c, m.dense[(size_t)(r + c * m.rows)]);
+  } else {
+    for (int64_t i = 0; i < d; ++i) put(i, i, cplx(1.0, 0.0));
+  }
+  for (auto &kv : diag) {
+    shifts.push_back(kv.first);
+    tables.push_back(kv.second);
+  }
+}
+
+int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std::vector<OrientedTerm> &terms) {
+  auto hp = std::make_shared<DTileProgramHost>();
+  DTileProgramHost &H = *hp;
+  H.dims = dims;
+  const int n = (int)dims.size();
+  if (n > DT_MAXAX) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: more than %d axes", DT_MAXAX);
+  for (int64_t d : dims) {
+    if (d < 1 || d > 4096) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: axis dimension %lld", (long long)d);
+    H.total *= d;
+  }
+  // ---- components of every term
+  std::vector<std::vector<DComp>> comps(terms.size());
+  std::vector<std::vector<int>> offaxes(terms.size());
+  for (size_t t = 0; t < terms.size(); ++t) {
+    const OrientedTerm &T = terms[t];
+    H.coef_of_term.push_back(T.coef_index);
+    cplx scalar = T.scalar;
+    if (T.axes.size() > DT_MAXF) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: more than %d factors in a term", DT_MAXF);
+    std::vector<std::vector<int>> shifts(T.axes.size());
+    std::vector<std::vector<std::vector<cplx>>> tables(T.axes.size());
+    std::vector<int> axes;
+    size_t ncomb = 1;
+    for (size_t f = 0; f < T.axes.size(); ++f) {
+      const HostMat &m = T.mats[f];
+      const int ax = T.axes[f];
+      if (m.rows != m.cols || m.rows != dims[ax]) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: non-square factor");
+      if (m.is_square_eye()) continue;
+      if (dims[ax] == 1) {  // a 1x1 factor is a scalar
+        scalar *= m.at(0, 0);
+        continue;
+      }
+      std::vector<int> sh;
+      std::vector<std::vector<cplx>> tb;
+      factor_diagonals(m, sh, tb);
+      if (sh.empty()) {  // a factor without entries: the term vanishes
+        ncomb = 0;
+        break;
+      }
+      bool off = false;
+      for (int s : sh) off |= s != 0;
+      if (off) offaxes[t].push_back(ax);
+      ncomb *= sh.size();
+      axes.push_back(ax);
+      shifts[axes.size() - 1] = sh;
+      tables[axes.size() - 1] = tb;
+    }
+    H.scalars.push_back(scalar);
+    if (ncomb == 0) continue;
+    if (ncomb > 64) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: %zu components in one term", ncomb);
+    std::vector<size_t> cur(axes.size(), 0);
+    for (size_t it = 0; it < ncomb; ++it) {
+      DComp c;
+      c.term = (int)t;
+      for (size_t f = 0; f < axes.size(); ++f) {
+        c.axes.push_back(axes[f]);
+        c.shift.push_back(shifts[f][cur[f]]);
+        c.table.push_back(tables[f][cur[f]]);
+      }
+      comps[t].push_back(std::move(c));
+      for (size_t f = 0; f < axes.size(); ++f) {
+        if (++cur[f] < shifts[f].size()) break;
+        cur[f] = 0;
+      }
+    }
+  }
+  // ---- low block: the fewest leading axes whose joint extent gives >= 8-amplitude (128-byte) contiguous runs
+  int nlow = 0;
+  int64_t R = 1;
+  while (nlow < n && R < 8) R *= dims[nlow++];
+  if (R > DT_TILE_CAP / 2) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: leading axis too large for a tile");
+  auto extent = [&](const std::vector<int> &axs) {
+    int64_t e = 1;
+    for (int a : axs) e *= dims[a];
+    return e;
+  };
+  auto merged = [&](std::vector<int> a, const std::vector<int> &b) {
+    a.insert(a.end(), b.begin(), b.end());
+    std::sort(a.begin(), a.end());
+    a.erase(std::unique(a.begin(), a.end()), a.end());
+    return a;
+  };
+  std::vector<int> low(nlow);
+  std::iota(low.begin(), low.end(), 0);
+  std::vector<char> covered(terms.size(), 0);
+  std::vector<std::vector<int>> pass_free;
+  std::vector<std::vector<int>> pass_terms;
+  {  // pass 0: the longest leading run of axes that fits a tile (fully contiguous tiles)
+    std::vector<int> fr;
+    int64_t e = 1;
+    for (int a = 0; a < n && e * dims[a] <= DT_TILE_CAP; ++a) {
+      fr.push_back(a);
+      e *= dims[a];
+    }
+    if ((int)fr.size() < nlow) fr = low;
+    pass_free.push_back(fr);
+    pass_terms.emplace_back();
+  }
+  auto subset = [](const std::vector<int> &a, const std::vector<int> &of) {
+    for (int v : a)
+      if (!std::binary_search(of.begin(), of.end(), v)) return false;
+    return true;
+  };
+  for (size_t t = 0; t < terms.size(); ++t)
+    if (subset(offaxes[t], pass_free[0])) {
+      covered[t] = 1;
+      pass_terms[0].push_back((int)t);
+    }
+  while (true) {
+    // seed: the uncovered term whose highest off-diagonal axis is lowest
+    int seed = -1;
+    for (size_t t = 0; t < terms.size(); ++t)
+      if (!covered[t] && (seed < 0 || offaxes[t].back() < offaxes[seed].back())) seed = (int)t;
+    if (seed < 0) break;
+    std::vector<int> fr = merged(low, offaxes[seed]);
+    if (extent(fr) > DT_TILE_CAP) {
+      fr = offaxes[seed];  // give up the coalesced low block for this pass
+      std::sort(fr.begin(), fr.end());
+      if (extent(fr) > DT_TILE_CAP) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: a term does not fit a tile");
+    }
+    // grow with the uncovered terms that come next
+    std::vector<int> order;
+    for (size_t t = 0; t < terms.size(); ++t)
+      if (!covered[t]) order.push_back((int)t);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return offaxes[a].back() < offaxes[b].back(); });
+    for (int t : order) {
+      std::vector<int> g = merged(fr, offaxes[t]);
+      if (extent(g) <= DT_TILE_CAP) fr = g;
+    }
+    // a small window wastes the CTA: pad the tile with the axes just below the window (more work per CTA, longer
+    // strided runs), as long as it stays within the capacity
+    for (int a = (fr.size() > (size_t)nlow ? *std::find_if(fr.begin(), fr.end(), [&](int v) { return v >= nlow; }) : n) - 1;
+         a >= nlow && extent(fr) * dims[a] <= DT_TILE_CAP; --a)
+      fr = merged(fr, {a});
+    pass_free.push_back(fr);
+    pass_terms.emplace_back();
+    for (size_t t = 0; t < terms.size(); ++t)
+      if (!covered[t] && subset(offaxes[t], fr)) {
+        covered[t] = 1;
+        pass_terms.back().push_back((int)t);
+      }
+  }
+  // a leading pass that only holds diagonal terms is not worth a sweep over the state: fold them into the next pass
+  if (pass_free.size() > 1) {
+    bool only_diag = true;
+    for (int t : pass_terms[0]) only_diag &= offaxes[t].empty();
+    if (only_diag) {
+      pass_terms[1].insert(pass_terms[1].end(), pass_terms[0].begin(), pass_terms[0].end());
+      pass_terms[0].clear();
+    }
+  }
+  // ---- device programs
+  std::string text;
+  for (size_t pi = 0; pi < pass_free.size(); ++pi) {
+    if (pass_terms[pi].empty() && !(pi == 0 && pass_free.size() == 1)) continue;
+    auto pp = std::make_unique<DPassHost>();
+    DPassHost &Pz = *pp;
+    Pz.free_axes = pass_free[pi];
+    Pz.terms = pass_terms[pi];
+    const std::vector<int> &fr = Pz.free_axes;
+    // low run: leading free axes that are exactly axes 0,1,2,...
+    int nl = 0;
+    int64_t Rr = 1;
+    while (nl < (int)fr.size() && fr[nl] == nl) Rr *= dims[nl++];
+    Pz.nlow = nl;
+    Pz.R = (int)Rr;
+    Pz.tile = (int)extent(fr);
+    std::vector<int64_t> gstride(n);
+    {
+      int64_t s = 1;
+      for (int a = 0; a < n; ++a) {
+        gstride[a] = s;
+        s *= dims[a];
+      }
+    }
+    std::vector<int64_t> tstride(n, 0);
+    {
+      int64_t s = 1;
+      for (int a : fr) {
+        tstride[a] = s;
+        s *= dims[a];
+      }
+    }
+    // window offsets
+    const int W = Pz.tile / Pz.R;
+    std::vector<long long> woff((size_t)W);
+    for (int w = 0; w < W; ++w) {
+      int64_t rem = w, off = 0;
+      for (size_t k = nl; k < fr.size(); ++k) {
+        off += (rem % dims[fr[k]]) * gstride[fr[k]];
+        rem /= dims[fr[k]];
+      }
+      woff[(size_t)w] = off;
+    }
+    DPassParams &Q = Pz.params;
+    memset(&Q, 0, sizeof(Q));
+    std::vector<int> fixed_slot(n, -1);
+    {
+      int64_t below = 1;
+      for (int a = 0; a < n; ++a) {
+        if (std::binary_search(fr.begin(), fr.end(), a)) continue;
+        if (dims[a] == 1) continue;
+        if (below * dims[a] > 0xFFFFFFFFll) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: more than 2^32 tiles");
+        fixed_slot[a] = Q.nfixed;
+        Q.fx_dim[Q.nfixed] = (unsigned)dims[a];
+        Q.fx_below[Q.nfixed] = (unsigned)below;
+        Q.fx_stride[Q.nfixed] = gstride[a];
+        ++Q.nfixed;
+        below *= dims[a];
+      }
+      Pz.ntiles = below;
+      if (below >= (1ll << 31)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: more than 2^31 tiles");
+    }
+    std::vector<DCompDev> recs;
+    std::vector<double2> tabs;
+    auto add_table = [&](const std::vector<cplx> &t) {
+      // identical tables are shared (the same site operator appears in many terms)
+      for (size_t o = 0; o + t.size() <= tabs.size(); ++o) {
+        bool same = true;
+        for (size_t i = 0; i < t.size() && same; ++i) same = tabs[o + i].x == t[i].real() && tabs[o + i].y == t[i].imag();
+        if (same) return (int)o;
+      }
+      const int o = (int)tabs.size();
+      for (cplx v : t) tabs.push_back(make_double2(v.real(), v.imag()));
+      return o;
+    };
+    for (int t : Pz.terms)
+      for (const DComp &c : comps[t]) {
+        DCompDev r;
+        memset(&r, 0, sizeof(r));
+        r.coef = t;
+        int64_t delta = 0;
+        for (size_t f = 0; f < c.axes.size(); ++f) {
+          const int ax = c.axes[f];
+          const bool is_free = std::binary_search(fr.begin(), fr.end(), ax);
+          if (!is_free && c.shift[f] != 0) QOB_FAIL(QOB_STATUS_INVALID_ARG, "dtile: internal planner error");
+          const int off = add_table(c.table[f]);
+          if (off + (int)dims[ax] > 65535) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: operator tables too large");
+          if (is_free) {
+            const int k = r.nfree++;
+            r.f_mts[k] = magic32((unsigned)tstride[ax]);
+            const bool top = tstride[ax] * dims[ax] == Pz.tile;
+            r.f_md[k] = top ? 0u : magic32((unsigned)dims[ax]);
+            r.f_d[k] = (unsigned short)dims[ax];
+            r.f_tab[k] = (unsigned short)off;
+            delta += (int64_t)c.shift[f] * tstride[ax];
+          } else {
+            const int k = r.nfixed++;
+            r.x_tab[k] = (unsigned short)off;
+            r.x_slot[k] = (unsigned char)fixed_slot[ax];
+          }
+        }
+        r.delta = (int)delta;
+        recs.push_back(r);
+      }
+    if (recs.size() > 2048 || tabs.size() > 2048) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: too many components in a pass");
+    // components with few free factors first is not needed; keep term order (deterministic accumulation order)
+    Q.ncomp = (int)recs.size();
+    Q.ntab = (int)tabs.size();
+    Q.tile = Pz.tile;
+    Q.R = Pz.R;
+    Q.mR = magic32((unsigned)Pz.R);
+    if (recs.empty()) recs.push_back(DCompDev{});
+    if (tabs.empty()) tabs.push_back(make_double2(0.0, 0.0));
+    QOB_TRY(Pz.d_comps.upload(recs));
+    QOB_TRY(Pz.d_tables.upload(tabs));
+    QOB_TRY(Pz.d_woff.upload(woff));
+    Q.comps = Pz.d_comps.ptr;
+    Q.tables = Pz.d_tables.ptr;
+    Q.woff = Pz.d_woff.ptr;
+    Pz.smem = (size_t)Pz.tile * 16 + (size_t)Q.ntab * 16 + (size_t)Q.ncomp * (16 + sizeof(DCompDev));
+    if (Pz.smem > 200 * 1024) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: pass needs %zu bytes of shared memory", Pz.smem);
+    char buf[256];
+    std::string fa;
+    for (int a : fr) fa += (fa.empty() ? "" : ",") + std::to_string(a + 1);
+    snprintf(buf, sizeof(buf), " {free axes:%s tile:%d run:%d terms:%zu components:%d tables:%dB}", fa.c_str(), Pz.tile, Pz.R,
+             Pz.terms.size(), Q.ncomp, Q.ntab * 16);
+    text += buf;
+    H.passes.push_back(std::move(pp));
+  }
+  {
+    std::vector<double2> c(std::max<size_t>(1, terms.size()), make_double2(0.0, 0.0));
+    QOB_TRY(H.d_coef.upload(c));
+  }
+  prog.h = hp;
+  prog.npasses = (int)H.passes.size();
+  prog.describe = "dtile[axes=" + std::to_string(n) + ",passes=" + std::to_string(prog.npasses) + "]" + text;
+  return QOB_STATUS_OK;
+}
+
+int dtile_set_coefs(DTileProgram &prog, const std::vector<cplx> &coefs, cudaStream_t s) {
+  DTileProgramHost &H = *prog.h;
+  std::vector<double2> c(std::max<size_t>(1, H.coef_of_term.size()), make_double2(0.0, 0.0));
+  for (size_t t = 0; t < H.coef_of_term.size(); ++t) {
+    cplx v = H.scalars[t];
+    if (H.coef_of_term[t] >= 0) {
+      if ((size_t)H.coef_of_term[t] >= coefs.size()) QOB_FAIL(QOB_STATUS_INVALID_ARG, "coefficient index out of range");
+      v *= coefs[H.coef_of_term[t]];
+    }
+    c[t] = make_double2(v.real(), v.imag());
+  }
+  return H.d_coef.upload_async(c, s);
+}
+
+int dtile_launch(const DTileProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s) {
+  DTileProgramHost &H = *prog.h;
+  if (t_planning_only) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dtile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+  if (attr_err != cudaSuccess) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  bool first = true;
+  for (auto &pp : H.passes) {
+    DPassHost &Pz = *pp;
+    DPassParams P = Pz.params;
+    P.coef = H.d_coef.ptr;
+    P.alpha = make_double2(alpha.real(), alpha.imag());
+    const cplx b = first ? beta : cplx(1.0, 0.0);
+    P.beta = make_double2(b.real(), b.imag());
+    P.mode = (b == cplx(0.0, 0.0)) ? 0 : 1;
+    first = false;
+    dtile_kernel<<<(unsigned)Pz.ntiles, DT_THREADS, Pz.smem, s>>>(P, (const double2 *)x, (double2 *)y);
+    QOB_LAUNCHED();
+    QOB_CUDA(cudaGetLastError());
+  }
+  return QOB_STATUS_OK;
+}
