@@ -17,11 +17,13 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <type_traits>
 
 #include "qob_internal.h"
 
 #define DT_MAXF 4        // factors per component (free + fixed each)
 #define DT_MAXAX 64      // tensor axes (incl. the batch axis)
+#define DT_MAXFREE 12    // free axes of a pass (2^12 = tile capacity)
 #define DT_THREADS 256
 #define DT_U 8           // outputs per thread and sweep
 #define DT_TILE_CAP 4096 // amplitudes per tile (64 KiB)
@@ -30,10 +32,10 @@ struct DCompDev {
   int delta;                        // source element = output element + delta (tile numbering)
   int coef;                         // index into the per-term coefficient array
   unsigned char nfree, nfixed, pad0, pad1;
-  unsigned int f_mts[DT_MAXF];      // magic multiplier for division by the tile stride (0: stride 1)
-  unsigned int f_md[DT_MAXF];       // magic multiplier for the modulo by the axis dimension (0: top digit, no modulo)
+  unsigned int f_sh[DT_MAXF];       // position of the factor's digit in the packed digit word of an output element
+  unsigned int f_mask[DT_MAXF];     // ... and its mask
   unsigned short f_d[DT_MAXF];      // axis dimension
-  unsigned short f_tab[DT_MAXF];    // weight table (entries of double2) indexed by the output digit on a free axis
+  unsigned short f_tab[DT_MAXF];    // weight table (entries) indexed by the output digit on a free axis
   unsigned short x_tab[DT_MAXF];    // same for fixed axes
   unsigned char x_slot[DT_MAXF];    // which fixed axis
   int pad2[2];
@@ -46,9 +48,12 @@ struct DPassParams {
   const double2 *coef;
   const long long *woff;            // global offset of window element w (tile element = r + R*w)
   int ncomp, ntab;
+  int nwoff_s;                      // window offsets staged in shared memory (0: read them from global memory)
   int tile, R;                      // amplitudes per tile; length of the contiguous low run
   unsigned int mR;                  // magic for division by R (0: R == 1)
   int nfixed;
+  int nfree_ax;                     // free axes: digit extraction (magic multipliers, see magic32) and packing position
+  unsigned int fa_mts[DT_MAXFREE], fa_md[DT_MAXFREE], fa_dim[DT_MAXFREE], fa_shift[DT_MAXFREE];
   unsigned int fx_dim[DT_MAXAX];    // fixed axes: dimension, product of the dimensions below (tile-id radix), stride
   unsigned int fx_below[DT_MAXAX];
   long long fx_stride[DT_MAXAX];
@@ -66,13 +71,33 @@ __device__ __forceinline__ void dfma(double2 &acc, double2 a, double2 b) {
   acc.y = fma(a.y, b.x, acc.y);
 }
 
-__global__ void __launch_bounds__(DT_THREADS) dtile_kernel(const __grid_constant__ DPassParams P,
-                                                           const double2 *__restrict__ x, double2 *__restrict__ y) {
+// Digits of a tile element on the free axes, packed into one word (sum of ceil(log2 d) <= 24 bits for a tile of <= 4096
+// amplitudes): computed once per output and sweep, a bit-field extract per factor lookup afterwards.
+__device__ __forceinline__ unsigned dt_pack_digits(const DPassParams &P, unsigned e) {
+  unsigned pk = 0;
+  for (int a = 0; a < P.nfree_ax; ++a) {
+    unsigned q = P.fa_mts[a] ? __umulhi(e, P.fa_mts[a]) : e;
+    if (P.fa_md[a]) q -= __umulhi(q, P.fa_md[a]) * P.fa_dim[a];
+    pk |= q << P.fa_shift[a];
+  }
+  return pk;
+}
+
+// REALT: every weight table of the pass is real (number, destroy, create, sigma+-, ... are): tables are stored as
+// 8-byte doubles (half the shared-memory wavefronts of a 16-byte lookup) and the weight product is real arithmetic.
+// REALW (needs REALT): the coefficients are real as well, so the whole weight is one double (2 DFMA per gather).
+template <bool REALT, bool REALW>
+__global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_constant__ DPassParams P,
+                                                              const double2 *__restrict__ x, double2 *__restrict__ y) {
+  typedef typename std::conditional<REALT, double, double2>::type TabT;
+  typedef typename std::conditional<REALW, double, double2>::type WT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *xs = reinterpret_cast<double2 *>(smem_raw);
-  double2 *tab = xs + P.tile;
-  double2 *cw = tab + P.ntab;
-  DCompDev *comps = reinterpret_cast<DCompDev *>(cw + P.ncomp);
+  double2 *cw2 = xs + P.tile;
+  WT *cw = reinterpret_cast<WT *>(cw2);
+  DCompDev *comps = reinterpret_cast<DCompDev *>(cw2 + P.ncomp);
+  TabT *tab = reinterpret_cast<TabT *>(comps + P.ncomp);   // 16-byte aligned: records are 80 bytes
+  long long *woff_s = reinterpret_cast<long long *>(tab + P.ntab);
   __shared__ unsigned int fdig[DT_MAXAX];
   __shared__ long long s_base;
   const unsigned tid = threadIdx.x;
@@ -89,7 +114,11 @@ __global__ void __launch_bounds__(DT_THREADS) dtile_kernel(const __grid_constant
     if (tid == 0) s_base = part;
   }
   // ---- operator data of this pass -> shared memory
-  for (int i = tid; i < P.ntab; i += DT_THREADS) tab[i] = P.tables[i];
+  for (int i = tid; i < P.ntab; i += DT_THREADS) {
+    if constexpr (REALT) tab[i] = P.tables[i].x;
+    else tab[i] = P.tables[i];
+  }
+  for (int i = tid; i < P.nwoff_s; i += DT_THREADS) woff_s[i] = P.woff[i];
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(P.comps);
     uint4 *dst = reinterpret_cast<uint4 *>(comps);
@@ -98,80 +127,108 @@ __global__ void __launch_bounds__(DT_THREADS) dtile_kernel(const __grid_constant
   }
   __syncthreads();
   const long long base = s_base;
-  // ---- the tile of x: contiguous runs of R amplitudes
+  const long long *woff = P.nwoff_s ? woff_s : P.woff;
+  // ---- the tile of x: contiguous runs of R amplitudes; y lines are pulled into L2 for the read-modify-write epilogue
   for (unsigned e = tid; e < (unsigned)P.tile; e += DT_THREADS) {
     const unsigned w = P.mR ? __umulhi(e, P.mR) : e;
     const unsigned r = e - w * (unsigned)P.R;
-    const double2 *g = x + base + r + P.woff[w];
+    const long long off = base + r + woff[w];
     const unsigned sa = (unsigned)__cvta_generic_to_shared(xs + e);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(x + off) : "memory");
+    if (P.mode && (off & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + off));
   }
   // ---- per-component weight that is uniform over the tile: coefficient x diagonal factors on fixed axes
   for (int c = tid; c < P.ncomp; c += DT_THREADS) {
     const DCompDev &C = comps[c];
     double2 w = P.coef[C.coef];
-    for (int f = 0; f < C.nfixed; ++f) w = dmul(w, tab[C.x_tab[f] + fdig[C.x_slot[f]]]);
-    cw[c] = w;
+    for (int f = 0; f < C.nfixed; ++f) {
+      if constexpr (REALT) {
+        const double t = tab[C.x_tab[f] + fdig[C.x_slot[f]]];
+        w.x *= t;
+        w.y *= t;
+      } else {
+        w = dmul(w, tab[C.x_tab[f] + fdig[C.x_slot[f]]]);
+      }
+    }
+    if constexpr (REALW) cw[c] = w.x;
+    else cw[c] = w;
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   for (unsigned sweep = 0; sweep < (unsigned)P.tile; sweep += DT_THREADS * DT_U) {
     double2 acc[DT_U];
+    unsigned pk[DT_U];
 #pragma unroll
-    for (int k = 0; k < DT_U; ++k) acc[k] = make_double2(0.0, 0.0);
+    for (int k = 0; k < DT_U; ++k) {
+      const unsigned e = sweep + k * DT_THREADS + tid;
+      acc[k] = make_double2(0.0, 0.0);
+      pk[k] = e < (unsigned)P.tile ? dt_pack_digits(P, e) : 0xffffffffu;   // out of range: no lookups (guards below)
+    }
+    const unsigned e0 = sweep + tid;
     for (int c = 0; c < P.ncomp; ++c) {
       const DCompDev &C = comps[c];
-      const double2 w0 = cw[c];
+      const WT w0 = cw[c];
       const int delta = C.delta, nfree = C.nfree;
+      const double2 *xsrc = xs + (int)e0 + delta;
       if (nfree == 0) {
 #pragma unroll
         for (int k = 0; k < DT_U; ++k) {
-          const unsigned e = sweep + k * DT_THREADS + tid;
-          if (e < (unsigned)P.tile) dfma(acc[k], w0, xs[e]);
-        }
-      } else if (nfree == 1) {
-        const unsigned m0 = C.f_mts[0], n0 = C.f_md[0], d0 = C.f_d[0];
-        const double2 *t0 = tab + C.f_tab[0];
-#pragma unroll
-        for (int k = 0; k < DT_U; ++k) {
-          const unsigned e = sweep + k * DT_THREADS + tid;
-          if (e < (unsigned)P.tile) {
-            unsigned q = m0 ? __umulhi(e, m0) : e;
-            if (n0) q -= __umulhi(q, n0) * d0;
-            const double2 w = dmul(w0, t0[q]);
-            if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xs[(int)e + delta]);
+          if (pk[k] != 0xffffffffu) {
+            const double2 xv = xsrc[k * DT_THREADS];
+            if constexpr (REALW) {
+              acc[k].x = fma(w0, xv.x, acc[k].x);
+              acc[k].y = fma(w0, xv.y, acc[k].y);
+            } else {
+              dfma(acc[k], w0, xv);
+            }
           }
         }
-      } else if (nfree == 2) {
-        const unsigned m0 = C.f_mts[0], n0 = C.f_md[0], d0 = C.f_d[0];
-        const unsigned m1 = C.f_mts[1], n1 = C.f_md[1], d1 = C.f_d[1];
-        const double2 *t0 = tab + C.f_tab[0], *t1 = tab + C.f_tab[1];
+      } else if (nfree <= 2) {
+        const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0];
+        const unsigned s1 = C.f_sh[1], k1 = C.f_mask[1];   // nfree == 1: mask 0 and a table holding the single entry 1
+        const TabT *t0 = tab + C.f_tab[0], *t1 = tab + C.f_tab[1];
 #pragma unroll
         for (int k = 0; k < DT_U; ++k) {
-          const unsigned e = sweep + k * DT_THREADS + tid;
-          if (e < (unsigned)P.tile) {
-            unsigned q0 = m0 ? __umulhi(e, m0) : e;
-            if (n0) q0 -= __umulhi(q0, n0) * d0;
-            unsigned q1 = m1 ? __umulhi(e, m1) : e;
-            if (n1) q1 -= __umulhi(q1, n1) * d1;
-            const double2 w = dmul(w0, dmul(t0[q0], t1[q1]));
-            if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xs[(int)e + delta]);
+          if (pk[k] != 0xffffffffu) {
+            const unsigned q0 = (pk[k] >> s0) & k0, q1 = (pk[k] >> s1) & k1;
+            if constexpr (REALT) {
+              const double t = t0[q0] * t1[q1];
+              if (t != 0.0) {
+                const double2 xv = xsrc[k * DT_THREADS];
+                if constexpr (REALW) {
+                  const double w = w0 * t;
+                  acc[k].x = fma(w, xv.x, acc[k].x);
+                  acc[k].y = fma(w, xv.y, acc[k].y);
+                } else {
+                  dfma(acc[k], make_double2(w0.x * t, w0.y * t), xv);
+                }
+              }
+            } else {
+              const double2 w = dmul(w0, dmul(t0[q0], t1[q1]));
+              if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xsrc[k * DT_THREADS]);
+            }
           }
         }
       } else {
 #pragma unroll
         for (int k = 0; k < DT_U; ++k) {
-          const unsigned e = sweep + k * DT_THREADS + tid;
-          if (e < (unsigned)P.tile) {
-            double2 w = w0;
+          if (pk[k] != 0xffffffffu) {
+            double2 w;
+            if constexpr (REALW) w = make_double2(w0, 0.0);
+            else w = w0;
 #pragma unroll 1
             for (int f = 0; f < nfree; ++f) {
-              unsigned q = C.f_mts[f] ? __umulhi(e, C.f_mts[f]) : e;
-              if (C.f_md[f]) q -= __umulhi(q, C.f_md[f]) * C.f_d[f];
-              w = dmul(w, tab[C.f_tab[f] + q]);
+              const unsigned q = (pk[k] >> C.f_sh[f]) & C.f_mask[f];
+              if constexpr (REALT) {
+                const double t = tab[C.f_tab[f] + q];
+                w.x *= t;
+                w.y *= t;
+              } else {
+                w = dmul(w, tab[C.f_tab[f] + q]);
+              }
             }
-            if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xs[(int)e + delta]);
+            if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xsrc[k * DT_THREADS]);
           }
         }
       }
@@ -182,7 +239,7 @@ __global__ void __launch_bounds__(DT_THREADS) dtile_kernel(const __grid_constant
       if (e < (unsigned)P.tile) {
         const unsigned w = P.mR ? __umulhi(e, P.mR) : e;
         const unsigned r = e - w * (unsigned)P.R;
-        double2 *g = y + base + r + P.woff[w];
+        double2 *g = y + base + r + woff[w];
         double2 o = dmul(P.alpha, acc[k]);
         if (P.mode) dfma(o, P.beta, *g);
         *g = o;
@@ -207,6 +264,7 @@ struct DPassHost {
   DevArray<double2> d_tables;
   DevArray<long long> d_woff;
   DPassParams params;
+  bool real_tables = true;
   size_t smem = 0;
   int64_t ntiles = 1;
 };
@@ -216,6 +274,7 @@ struct DTileProgramHost {
   std::vector<int> coef_of_term;
   std::vector<cplx> scalars;
   DevArray<double2> d_coef;
+  bool coefs_real = false;   // every coef*scalar currently loaded is real (set by dtile_set_coefs)
   int64_t total = 1;
 };
 
@@ -457,8 +516,28 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
       Pz.ntiles = below;
       if (below >= (1ll << 31)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: more than 2^31 tiles");
     }
+    std::vector<int> ax_shift(n, 0), ax_bits(n, 0);
+    {
+      int pos = 0;
+      for (int a : fr) {
+        if (dims[a] == 1) continue;
+        if (Q.nfree_ax >= DT_MAXFREE) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: too many free axes");
+        int bits = 1;
+        while ((1ll << bits) < dims[a]) ++bits;
+        ax_shift[a] = pos;
+        ax_bits[a] = bits;
+        const int k = Q.nfree_ax++;
+        Q.fa_mts[k] = magic32((unsigned)tstride[a]);
+        Q.fa_md[k] = (tstride[a] * dims[a] == Pz.tile) ? 0u : magic32((unsigned)dims[a]);
+        Q.fa_dim[k] = (unsigned)dims[a];
+        Q.fa_shift[k] = (unsigned)pos;
+        pos += bits;
+      }
+      if (pos > 31) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: packed digits do not fit");
+    }
     std::vector<DCompDev> recs;
     std::vector<double2> tabs;
+    tabs.push_back(make_double2(1.0, 0.0));   // entry 0: the neutral table of an absent second factor
     auto add_table = [&](const std::vector<cplx> &t) {
       // identical tables are shared (the same site operator appears in many terms)
       for (size_t o = 0; o + t.size() <= tabs.size(); ++o) {
@@ -484,9 +563,8 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
           if (off + (int)dims[ax] > 65535) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: operator tables too large");
           if (is_free) {
             const int k = r.nfree++;
-            r.f_mts[k] = magic32((unsigned)tstride[ax]);
-            const bool top = tstride[ax] * dims[ax] == Pz.tile;
-            r.f_md[k] = top ? 0u : magic32((unsigned)dims[ax]);
+            r.f_sh[k] = (unsigned)ax_shift[ax];
+            r.f_mask[k] = (1u << ax_bits[ax]) - 1u;
             r.f_d[k] = (unsigned short)dims[ax];
             r.f_tab[k] = (unsigned short)off;
             delta += (int64_t)c.shift[f] * tstride[ax];
@@ -514,13 +592,15 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
     Q.comps = Pz.d_comps.ptr;
     Q.tables = Pz.d_tables.ptr;
     Q.woff = Pz.d_woff.ptr;
-    Pz.smem = (size_t)Pz.tile * 16 + (size_t)Q.ntab * 16 + (size_t)Q.ncomp * (16 + sizeof(DCompDev));
+    for (const double2 &v : tabs) Pz.real_tables &= v.y == 0.0;
+    Q.nwoff_s = W <= 1024 ? W : 0;
+    Pz.smem = (size_t)Pz.tile * 16 + (size_t)Q.ntab * 16 + (size_t)Q.ncomp * (16 + sizeof(DCompDev)) + (size_t)Q.nwoff_s * 8;
     if (Pz.smem > 200 * 1024) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: pass needs %zu bytes of shared memory", Pz.smem);
     char buf[256];
     std::string fa;
     for (int a : fr) fa += (fa.empty() ? "" : ",") + std::to_string(a + 1);
-    snprintf(buf, sizeof(buf), " {free axes:%s tile:%d run:%d terms:%zu components:%d tables:%dB}", fa.c_str(), Pz.tile, Pz.R,
-             Pz.terms.size(), Q.ncomp, Q.ntab * 16);
+    snprintf(buf, sizeof(buf), " {free axes:%s tile:%d run:%d terms:%zu components:%d tables:%dB%s}", fa.c_str(), Pz.tile, Pz.R,
+             Pz.terms.size(), Q.ncomp, Q.ntab * (Pz.real_tables ? 8 : 16), Pz.real_tables ? " real" : "");
     text += buf;
     H.passes.push_back(std::move(pp));
   }
@@ -545,6 +625,8 @@ int dtile_set_coefs(DTileProgram &prog, const std::vector<cplx> &coefs, cudaStre
     }
     c[t] = make_double2(v.real(), v.imag());
   }
+  H.coefs_real = true;
+  for (const double2 &v : c) H.coefs_real &= v.y == 0.0;
   return H.d_coef.upload_async(c, s);
 }
 
@@ -553,7 +635,13 @@ int dtile_launch(const DTileProgram &prog, cplx alpha, const void *x, cplx beta,
   if (t_planning_only) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dtile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(dtile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(dtile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(dtile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
   if (attr_err != cudaSuccess) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   bool first = true;
   for (auto &pp : H.passes) {
@@ -565,7 +653,12 @@ int dtile_launch(const DTileProgram &prog, cplx alpha, const void *x, cplx beta,
     P.beta = make_double2(b.real(), b.imag());
     P.mode = (b == cplx(0.0, 0.0)) ? 0 : 1;
     first = false;
-    dtile_kernel<<<(unsigned)Pz.ntiles, DT_THREADS, Pz.smem, s>>>(P, (const double2 *)x, (double2 *)y);
+    if (Pz.real_tables && H.coefs_real)
+      dtile_kernel<true, true><<<(unsigned)Pz.ntiles, DT_THREADS, Pz.smem, s>>>(P, (const double2 *)x, (double2 *)y);
+    else if (Pz.real_tables)
+      dtile_kernel<true, false><<<(unsigned)Pz.ntiles, DT_THREADS, Pz.smem, s>>>(P, (const double2 *)x, (double2 *)y);
+    else
+      dtile_kernel<false, false><<<(unsigned)Pz.ntiles, DT_THREADS, Pz.smem, s>>>(P, (const double2 *)x, (double2 *)y);
     QOB_LAUNCHED();
     QOB_CUDA(cudaGetLastError());
   }
