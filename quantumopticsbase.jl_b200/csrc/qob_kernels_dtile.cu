@@ -23,7 +23,6 @@
 
 #define DT_MAXF 4        // factors per component (free + fixed each)
 #define DT_MAXAX 64      // tensor axes (incl. the batch axis)
-#define DT_MAXFREE 12    // free axes of a pass (2^12 = tile capacity)
 #define DT_THREADS 256
 #define DT_U 8           // outputs per thread and sweep
 #define DT_TILE_CAP 4096 // amplitudes per tile (64 KiB)
@@ -46,14 +45,12 @@ struct DPassParams {
   const DCompDev *comps;
   const double2 *tables;
   const double2 *coef;
-  const long long *woff;            // global offset of window element w (tile element = r + R*w)
+  const uint2 *etab;                // per tile element: {packed free-axis digits, offset from the tile base}
   int ncomp, ntab;
-  int nwoff_s;                      // window offsets staged in shared memory (0: read them from global memory)
+  int n_off, n_dfree;               // components [0, n_off): off-diagonal; [n_off, n_off+n_dfree): diagonal with free
+                                    // factors; the rest: diagonal and uniform over the tile
   int tile, R;                      // amplitudes per tile; length of the contiguous low run
-  unsigned int mR;                  // magic for division by R (0: R == 1)
   int nfixed;
-  int nfree_ax;                     // free axes: digit extraction (magic multipliers, see magic32) and packing position
-  unsigned int fa_mts[DT_MAXFREE], fa_md[DT_MAXFREE], fa_dim[DT_MAXFREE], fa_shift[DT_MAXFREE];
   unsigned int fx_dim[DT_MAXAX];    // fixed axes: dimension, product of the dimensions below (tile-id radix), stride
   unsigned int fx_below[DT_MAXAX];
   long long fx_stride[DT_MAXAX];
@@ -71,22 +68,14 @@ __device__ __forceinline__ void dfma(double2 &acc, double2 a, double2 b) {
   acc.y = fma(a.y, b.x, acc.y);
 }
 
-// Digits of a tile element on the free axes, packed into one word (sum of ceil(log2 d) <= 24 bits for a tile of <= 4096
-// amplitudes): computed once per output and sweep, a bit-field extract per factor lookup afterwards.
-__device__ __forceinline__ unsigned dt_pack_digits(const DPassParams &P, unsigned e) {
-  unsigned pk = 0;
-  for (int a = 0; a < P.nfree_ax; ++a) {
-    unsigned q = P.fa_mts[a] ? __umulhi(e, P.fa_mts[a]) : e;
-    if (P.fa_md[a]) q -= __umulhi(q, P.fa_md[a]) * P.fa_dim[a];
-    pk |= q << P.fa_shift[a];
-  }
-  return pk;
-}
-
+// Per tile element (the same for every tile of a pass, built on the host, read through L1): the digits of the element on
+// the free axes packed into one word (sum of ceil(log2 d) <= 24 bits for a tile of <= 4096 amplitudes; a bit-field
+// extract per factor lookup) and its offset from the tile base in the state.
 // REALT: every weight table of the pass is real (number, destroy, create, sigma+-, ... are): tables are stored as
 // 8-byte doubles (half the shared-memory wavefronts of a 16-byte lookup) and the weight product is real arithmetic.
 // REALW (needs REALT): the coefficients are real as well, so the whole weight is one double (2 DFMA per gather).
-template <bool REALT, bool REALW>
+// FULL: the tile is a multiple of the sweep (threads x outputs per thread), no range guards.
+template <bool REALT, bool REALW, bool FULL>
 __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_constant__ DPassParams P,
                                                               const double2 *__restrict__ x, double2 *__restrict__ y) {
   typedef typename std::conditional<REALT, double, double2>::type TabT;
@@ -97,7 +86,6 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
   WT *cw = reinterpret_cast<WT *>(cw2);
   DCompDev *comps = reinterpret_cast<DCompDev *>(cw2 + P.ncomp);
   TabT *tab = reinterpret_cast<TabT *>(comps + P.ncomp);   // 16-byte aligned: records are 80 bytes
-  long long *woff_s = reinterpret_cast<long long *>(tab + P.ntab);
   __shared__ unsigned int fdig[DT_MAXAX];
   __shared__ long long s_base;
   const unsigned tid = threadIdx.x;
@@ -118,7 +106,6 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
     if constexpr (REALT) tab[i] = P.tables[i].x;
     else tab[i] = P.tables[i];
   }
-  for (int i = tid; i < P.nwoff_s; i += DT_THREADS) woff_s[i] = P.woff[i];
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(P.comps);
     uint4 *dst = reinterpret_cast<uint4 *>(comps);
@@ -127,12 +114,9 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
   }
   __syncthreads();
   const long long base = s_base;
-  const long long *woff = P.nwoff_s ? woff_s : P.woff;
-  // ---- the tile of x: contiguous runs of R amplitudes; y lines are pulled into L2 for the read-modify-write epilogue
+  // ---- the tile of x (contiguous runs of R amplitudes); y lines are pulled into L2 for the read-modify-write epilogue
   for (unsigned e = tid; e < (unsigned)P.tile; e += DT_THREADS) {
-    const unsigned w = P.mR ? __umulhi(e, P.mR) : e;
-    const unsigned r = e - w * (unsigned)P.R;
-    const long long off = base + r + woff[w];
+    const long long off = base + (long long)__ldg(&P.etab[e]).y;
     const unsigned sa = (unsigned)__cvta_generic_to_shared(xs + e);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(x + off) : "memory");
     if (P.mode && (off & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + off));
@@ -163,10 +147,92 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
     for (int k = 0; k < DT_U; ++k) {
       const unsigned e = sweep + k * DT_THREADS + tid;
       acc[k] = make_double2(0.0, 0.0);
-      pk[k] = e < (unsigned)P.tile ? dt_pack_digits(P, e) : 0xffffffffu;   // out of range: no lookups (guards below)
+      pk[k] = (FULL || e < (unsigned)P.tile) ? __ldg(&P.etab[e]).x : 0xffffffffu;   // out of range: no lookups (guards below)
     }
     const unsigned e0 = sweep + tid;
-    for (int c = 0; c < P.ncomp; ++c) {
+    // ---- diagonal components (source = the output element itself): their weights are summed first — one lookup and
+    // one multiply-add each — and applied with a single multiply per output; the ones without a free factor are
+    // uniform over the tile
+    if (P.n_off < P.ncomp) {
+      WT wu;
+      if constexpr (REALW) wu = 0.0;
+      else wu = make_double2(0.0, 0.0);
+      for (int c = P.n_off + P.n_dfree; c < P.ncomp; ++c) {
+        if constexpr (REALW) wu += cw[c];
+        else {
+          wu.x += cw[c].x;
+          wu.y += cw[c].y;
+        }
+      }
+      WT wd[DT_U];
+#pragma unroll
+      for (int k = 0; k < DT_U; ++k) wd[k] = wu;
+      for (int c = P.n_off; c < P.n_off + P.n_dfree; ++c) {
+        const DCompDev &C = comps[c];
+        const WT w0 = cw[c];
+        const int nfree = C.nfree;
+        if (nfree <= 2) {
+          const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0], s1 = C.f_sh[1], k1 = C.f_mask[1];
+          const TabT *t0 = tab + C.f_tab[0], *t1 = tab + C.f_tab[1];
+#pragma unroll
+          for (int k = 0; k < DT_U; ++k) {
+            if (FULL || pk[k] != 0xffffffffu) {
+              const unsigned q0 = (pk[k] >> s0) & k0, q1 = (pk[k] >> s1) & k1;
+              if constexpr (REALT) {
+                const double t = t0[q0] * t1[q1];
+                if constexpr (REALW) wd[k] = fma(w0, t, wd[k]);
+                else {
+                  wd[k].x = fma(w0.x, t, wd[k].x);
+                  wd[k].y = fma(w0.y, t, wd[k].y);
+                }
+              } else {
+                dfma(wd[k], w0, dmul(t0[q0], t1[q1]));
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < DT_U; ++k) {
+            if (FULL || pk[k] != 0xffffffffu) {
+              double2 w;
+              if constexpr (REALW) w = make_double2(w0, 0.0);
+              else w = w0;
+#pragma unroll 1
+              for (int f = 0; f < nfree; ++f) {
+                const unsigned q = (pk[k] >> C.f_sh[f]) & C.f_mask[f];
+                if constexpr (REALT) {
+                  const double t = tab[C.f_tab[f] + q];
+                  w.x *= t;
+                  w.y *= t;
+                } else {
+                  w = dmul(w, tab[C.f_tab[f] + q]);
+                }
+              }
+              if constexpr (REALW) wd[k] += w.x;
+              else {
+                wd[k].x += w.x;
+                wd[k].y += w.y;
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < DT_U; ++k) {
+        if (FULL || pk[k] != 0xffffffffu) {
+          if constexpr (REALW) {
+            if (wd[k] != 0.0) {
+              const double2 xv = xs[e0 + k * DT_THREADS];
+              acc[k].x = fma(wd[k], xv.x, acc[k].x);
+              acc[k].y = fma(wd[k], xv.y, acc[k].y);
+            }
+          } else {
+            if (wd[k].x != 0.0 || wd[k].y != 0.0) dfma(acc[k], wd[k], xs[e0 + k * DT_THREADS]);
+          }
+        }
+      }
+    }
+    for (int c = 0; c < P.n_off; ++c) {
       const DCompDev &C = comps[c];
       const WT w0 = cw[c];
       const int delta = C.delta, nfree = C.nfree;
@@ -174,7 +240,7 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
       if (nfree == 0) {
 #pragma unroll
         for (int k = 0; k < DT_U; ++k) {
-          if (pk[k] != 0xffffffffu) {
+          if (FULL || pk[k] != 0xffffffffu) {
             const double2 xv = xsrc[k * DT_THREADS];
             if constexpr (REALW) {
               acc[k].x = fma(w0, xv.x, acc[k].x);
@@ -190,7 +256,7 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
         const TabT *t0 = tab + C.f_tab[0], *t1 = tab + C.f_tab[1];
 #pragma unroll
         for (int k = 0; k < DT_U; ++k) {
-          if (pk[k] != 0xffffffffu) {
+          if (FULL || pk[k] != 0xffffffffu) {
             const unsigned q0 = (pk[k] >> s0) & k0, q1 = (pk[k] >> s1) & k1;
             if constexpr (REALT) {
               const double t = t0[q0] * t1[q1];
@@ -213,7 +279,7 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
       } else {
 #pragma unroll
         for (int k = 0; k < DT_U; ++k) {
-          if (pk[k] != 0xffffffffu) {
+          if (FULL || pk[k] != 0xffffffffu) {
             double2 w;
             if constexpr (REALW) w = make_double2(w0, 0.0);
             else w = w0;
@@ -233,16 +299,31 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
         }
       }
     }
+    // epilogue in batches of 4: the loads of y first (independent, in flight together), then the stores
 #pragma unroll
-    for (int k = 0; k < DT_U; ++k) {
-      const unsigned e = sweep + k * DT_THREADS + tid;
-      if (e < (unsigned)P.tile) {
-        const unsigned w = P.mR ? __umulhi(e, P.mR) : e;
-        const unsigned r = e - w * (unsigned)P.R;
-        double2 *g = y + base + r + woff[w];
-        double2 o = dmul(P.alpha, acc[k]);
-        if (P.mode) dfma(o, P.beta, *g);
-        *g = o;
+    for (int kb = 0; kb < DT_U; kb += 4) {
+      long long goff[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned e = sweep + (kb + j) * DT_THREADS + tid;
+        goff[j] = (FULL || e < (unsigned)P.tile) ? base + (long long)__ldg(&P.etab[e]).y : -1;
+      }
+      if (P.mode) {
+        double2 yv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (FULL || goff[j] >= 0) yv[j] = y[goff[j]];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (FULL || goff[j] >= 0) {
+            double2 o = dmul(P.alpha, acc[kb + j]);
+            dfma(o, P.beta, yv[j]);
+            y[goff[j]] = o;
+          }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (FULL || goff[j] >= 0) y[goff[j]] = dmul(P.alpha, acc[kb + j]);
       }
     }
   }
@@ -262,7 +343,7 @@ struct DPassHost {
   std::vector<int> terms;
   DevArray<DCompDev> d_comps;
   DevArray<double2> d_tables;
-  DevArray<long long> d_woff;
+  DevArray<uint2> d_etab;
   DPassParams params;
   bool real_tables = true;
   size_t smem = 0;
@@ -278,7 +359,6 @@ struct DTileProgramHost {
   int64_t total = 1;
 };
 
-static unsigned magic32(unsigned d) { return d <= 1 ? 0u : (unsigned)(((1ull << 32) / d) + 1ull); }
 
 // shifted diagonals of an oriented square factor (rows = output digit, cols = input digit)
 static void factor_diagonals(const HostMat &m, std::vector<int> &shifts, std::vector<std::vector<cplx>> &tables) {
@@ -486,17 +566,6 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
         s *= dims[a];
       }
     }
-    // window offsets
-    const int W = Pz.tile / Pz.R;
-    std::vector<long long> woff((size_t)W);
-    for (int w = 0; w < W; ++w) {
-      int64_t rem = w, off = 0;
-      for (size_t k = nl; k < fr.size(); ++k) {
-        off += (rem % dims[fr[k]]) * gstride[fr[k]];
-        rem /= dims[fr[k]];
-      }
-      woff[(size_t)w] = off;
-    }
     DPassParams &Q = Pz.params;
     memset(&Q, 0, sizeof(Q));
     std::vector<int> fixed_slot(n, -1);
@@ -521,19 +590,26 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
       int pos = 0;
       for (int a : fr) {
         if (dims[a] == 1) continue;
-        if (Q.nfree_ax >= DT_MAXFREE) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: too many free axes");
         int bits = 1;
         while ((1ll << bits) < dims[a]) ++bits;
         ax_shift[a] = pos;
         ax_bits[a] = bits;
-        const int k = Q.nfree_ax++;
-        Q.fa_mts[k] = magic32((unsigned)tstride[a]);
-        Q.fa_md[k] = (tstride[a] * dims[a] == Pz.tile) ? 0u : magic32((unsigned)dims[a]);
-        Q.fa_dim[k] = (unsigned)dims[a];
-        Q.fa_shift[k] = (unsigned)pos;
         pos += bits;
       }
       if (pos > 31) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: packed digits do not fit");
+    }
+    std::vector<uint2> etab((size_t)Pz.tile);
+    for (int e = 0; e < Pz.tile; ++e) {
+      int64_t rem = e, off = 0;
+      unsigned pk = 0;
+      for (int a : fr) {
+        const int64_t dg = rem % dims[a];
+        rem /= dims[a];
+        off += dg * gstride[a];
+        pk |= (unsigned)dg << ax_shift[a];
+      }
+      if (off > 0xFFFFFFFFll) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: tile spans more than 2^32 amplitudes");
+      etab[(size_t)e] = make_uint2(pk, (unsigned)off);
     }
     std::vector<DCompDev> recs;
     std::vector<double2> tabs;
@@ -575,26 +651,32 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
           }
         }
         r.delta = (int)delta;
+        bool diag = true;
+        for (int sft : c.shift) diag &= sft == 0;
+        r.pad0 = diag ? (r.nfree ? 1 : 2) : 0;   // ordering class
         recs.push_back(r);
       }
+    std::stable_sort(recs.begin(), recs.end(), [](const DCompDev &a, const DCompDev &b) { return a.pad0 < b.pad0; });
+    for (const DCompDev &r : recs) {
+      Q.n_off += r.pad0 == 0;
+      Q.n_dfree += r.pad0 == 1;
+    }
     if (recs.size() > 2048 || tabs.size() > 2048) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: too many components in a pass");
     // components with few free factors first is not needed; keep term order (deterministic accumulation order)
     Q.ncomp = (int)recs.size();
     Q.ntab = (int)tabs.size();
     Q.tile = Pz.tile;
     Q.R = Pz.R;
-    Q.mR = magic32((unsigned)Pz.R);
     if (recs.empty()) recs.push_back(DCompDev{});
     if (tabs.empty()) tabs.push_back(make_double2(0.0, 0.0));
     QOB_TRY(Pz.d_comps.upload(recs));
     QOB_TRY(Pz.d_tables.upload(tabs));
-    QOB_TRY(Pz.d_woff.upload(woff));
+    QOB_TRY(Pz.d_etab.upload(etab));
     Q.comps = Pz.d_comps.ptr;
     Q.tables = Pz.d_tables.ptr;
-    Q.woff = Pz.d_woff.ptr;
+    Q.etab = Pz.d_etab.ptr;
     for (const double2 &v : tabs) Pz.real_tables &= v.y == 0.0;
-    Q.nwoff_s = W <= 1024 ? W : 0;
-    Pz.smem = (size_t)Pz.tile * 16 + (size_t)Q.ntab * 16 + (size_t)Q.ncomp * (16 + sizeof(DCompDev)) + (size_t)Q.nwoff_s * 8;
+    Pz.smem = (size_t)Pz.tile * 16 + (size_t)Q.ntab * 16 + (size_t)Q.ncomp * (16 + sizeof(DCompDev));
     if (Pz.smem > 200 * 1024) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: pass needs %zu bytes of shared memory", Pz.smem);
     char buf[256];
     std::string fa;
@@ -636,11 +718,15 @@ int dtile_launch(const DTileProgram &prog, cplx alpha, const void *x, cplx beta,
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(dtile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(dtile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(dtile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    auto set = [](const void *f) {
+      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    };
+    set((const void *)dtile_kernel<true, true, true>);
+    set((const void *)dtile_kernel<true, true, false>);
+    set((const void *)dtile_kernel<true, false, true>);
+    set((const void *)dtile_kernel<true, false, false>);
+    set((const void *)dtile_kernel<false, false, true>);
+    set((const void *)dtile_kernel<false, false, false>);
   });
   if (attr_err != cudaSuccess) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
   bool first = true;
@@ -653,12 +739,19 @@ int dtile_launch(const DTileProgram &prog, cplx alpha, const void *x, cplx beta,
     P.beta = make_double2(b.real(), b.imag());
     P.mode = (b == cplx(0.0, 0.0)) ? 0 : 1;
     first = false;
-    if (Pz.real_tables && H.coefs_real)
-      dtile_kernel<true, true><<<(unsigned)Pz.ntiles, DT_THREADS, Pz.smem, s>>>(P, (const double2 *)x, (double2 *)y);
-    else if (Pz.real_tables)
-      dtile_kernel<true, false><<<(unsigned)Pz.ntiles, DT_THREADS, Pz.smem, s>>>(P, (const double2 *)x, (double2 *)y);
-    else
-      dtile_kernel<false, false><<<(unsigned)Pz.ntiles, DT_THREADS, Pz.smem, s>>>(P, (const double2 *)x, (double2 *)y);
+    const bool full = Pz.tile % (DT_THREADS * DT_U) == 0;
+    const unsigned grid = (unsigned)Pz.ntiles;
+    const double2 *xp = (const double2 *)x;
+    double2 *yp = (double2 *)y;
+#define DT_GO(RT, RW)                                                                       \
+  do {                                                                                      \
+    if (full) dtile_kernel<RT, RW, true><<<grid, DT_THREADS, Pz.smem, s>>>(P, xp, yp);      \
+    else dtile_kernel<RT, RW, false><<<grid, DT_THREADS, Pz.smem, s>>>(P, xp, yp);          \
+  } while (0)
+    if (Pz.real_tables && H.coefs_real) DT_GO(true, true);
+    else if (Pz.real_tables) DT_GO(true, false);
+    else DT_GO(false, false);
+#undef DT_GO
     QOB_LAUNCHED();
     QOB_CUDA(cudaGetLastError());
   }
