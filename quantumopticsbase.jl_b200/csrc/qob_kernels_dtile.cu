@@ -525,13 +525,29 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
         pass_terms.back().push_back((int)t);
       }
   }
-  // a leading pass that only holds diagonal terms is not worth a sweep over the state: fold them into the next pass
-  if (pass_free.size() > 1) {
-    bool only_diag = true;
-    for (int t : pass_terms[0]) only_diag &= offaxes[t].empty();
-    if (only_diag) {
-      pass_terms[1].insert(pass_terms[1].end(), pass_terms[0].begin(), pass_terms[0].end());
-      pass_terms[0].clear();
+  // diagonal terms can run in any pass: take them out of pass 0 and hand each to the pass that has the least work so far
+  // (passes with few components are memory bound and have issue slots to spare); a leading pass left without terms is
+  // dropped
+  {
+    std::vector<int> diag_terms;
+    for (auto it = pass_terms[0].begin(); it != pass_terms[0].end();) {
+      if (offaxes[*it].empty()) {
+        diag_terms.push_back(*it);
+        it = pass_terms[0].erase(it);
+      } else {
+        ++it;
+      }
+    }
+    std::vector<size_t> load(pass_free.size(), 0);
+    for (size_t pi = 0; pi < pass_free.size(); ++pi)
+      for (int t : pass_terms[pi]) load[pi] += 2 * comps[t].size();   // an off-diagonal component costs about two diagonal ones
+    const bool drop0 = pass_terms[0].empty() && pass_free.size() > 1;
+    for (int t : diag_terms) {
+      size_t best = drop0 ? 1 : 0;
+      for (size_t pi = best; pi < pass_free.size(); ++pi)
+        if (load[pi] < load[best]) best = pi;
+      pass_terms[best].push_back(t);
+      load[best] += comps[t].size();
     }
   }
   // ---- device programs

@@ -202,3 +202,40 @@ def test_layout_plans_and_term_masks(Q):
     assert swapped_bitpos(24, 21, 3, 17) == list(range(17)) + [21, 22, 23, 20, 17, 18, 19]
     d = sh.describe()
     assert "local[64 terms]" in d and "swapped[8 terms, window bit 17]" in d
+
+
+def _bose_hubbard(Q, sites, cutoff):
+    f = Q.FockBasis(cutoff)
+    B = Q.tensor(*[f] * sites)
+    a, ad, n = Q.destroy(f), Q.create(f), Q.number(f)
+    terms = []
+    for i in range(1, sites):
+        terms += [Q.LazyTensor(B, [i, i + 1], (ad, a)), Q.LazyTensor(B, [i, i + 1], (a, ad))]
+    terms += [Q.LazyTensor(B, [i], (n,)) for i in range(1, sites + 1)]
+    return Q.LazySum([1.0] * len(terms), terms)
+
+
+def test_mixed_radix_tile_planner(Q, monkeypatch):
+    """Planning only: a Bose-Hubbard chain of 8 x Fock(7) (2^24 amplitudes) runs as 3 mixed-radix tile passes: the first
+    four sites contiguously, then {site 1} + a window of three higher sites twice; every off-diagonal bond is in exactly one
+    pass, the diagonal terms are spread; small states and a disabled planner keep the gather kernel."""
+    ctx = Q.context(-1)
+    d = Q.describe(_bose_hubbard(Q, 8, 7), ctx=ctx)
+    assert "dtile[axes=8,passes=3]" in d and "gather[" not in d, d
+    assert "{free axes:1,2,3,4 tile:4096 run:4096" in d and "{free axes:1,4,5,6 tile:4096 run:8" in d and "{free axes:1,6,7,8 tile:4096 run:8" in d, d
+    assert sum(int(s.split(" ")[0]) for s in d.split("components:")[1:]) == 22 and d.count(" real}") == 3, d
+    # X*op with 96 rows: the batch becomes two leading axes (32 x 3), 8 tensor axes in all
+    assert "dtile[axes=10," in Q.describe(_bose_hubbard(Q, 8, 7), "right", 96, ctx=ctx)
+    # below the size threshold, or switched off: the generic gather kernel
+    assert "gather[" in Q.describe(_bose_hubbard(Q, 4, 3), ctx=ctx)
+    monkeypatch.setenv("QOB_DISABLE_DTILE", "1")
+    assert "gather[" in Q.describe(_bose_hubbard(Q, 8, 7), ctx=ctx)
+    monkeypatch.delenv("QOB_DISABLE_DTILE")
+    # a term that expands into more than 64 single-gather components makes the planner decline the whole sum
+    import numpy as np
+
+    g = Q.GenericBasis(9)
+    Bg = Q.tensor(g, g, g, g, g, g)
+    rng = np.random.default_rng(0)
+    dense9 = [Q.Operator(g, g, rng.standard_normal((9, 9)) + 0j) for _ in range(2)]
+    assert "gather[" in Q.describe(Q.LazySum([1.0], [Q.LazyTensor(Bg, [1, 2], tuple(dense9))]), ctx=ctx)
