@@ -115,11 +115,23 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
   __syncthreads();
   const long long base = s_base;
   // ---- the tile of x (contiguous runs of R amplitudes); y lines are pulled into L2 for the read-modify-write epilogue
-  for (unsigned e = tid; e < (unsigned)P.tile; e += DT_THREADS) {
-    const long long off = base + (long long)__ldg(&P.etab[e]).y;
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(xs + e);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(x + off) : "memory");
-    if (P.mode && (off & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + off));
+  for (unsigned e0 = tid; e0 < (unsigned)P.tile; e0 += 8 * DT_THREADS) {
+    unsigned eo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {   // the table lookups first (independent), then the copies
+      const unsigned e = e0 + j * DT_THREADS;
+      eo[j] = (FULL || e < (unsigned)P.tile) ? __ldg(&P.etab[e]).y : 0xffffffffu;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const unsigned e = e0 + j * DT_THREADS;
+      if (FULL || e < (unsigned)P.tile) {
+        const long long off = base + (long long)eo[j];
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(xs + e);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(x + off) : "memory");
+        if (P.mode && (off & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + off));
+      }
+    }
   }
   // ---- per-component weight that is uniform over the tile: coefficient x diagonal factors on fixed axes
   for (int c = tid; c < P.ncomp; c += DT_THREADS) {
@@ -142,12 +154,14 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
 
   for (unsigned sweep = 0; sweep < (unsigned)P.tile; sweep += DT_THREADS * DT_U) {
     double2 acc[DT_U];
-    unsigned pk[DT_U];
+    unsigned pk[DT_U], eo[DT_U];
 #pragma unroll
     for (int k = 0; k < DT_U; ++k) {
       const unsigned e = sweep + k * DT_THREADS + tid;
       acc[k] = make_double2(0.0, 0.0);
-      pk[k] = (FULL || e < (unsigned)P.tile) ? __ldg(&P.etab[e]).x : 0xffffffffu;   // out of range: no lookups (guards below)
+      const uint2 t = (FULL || e < (unsigned)P.tile) ? __ldg(&P.etab[e]) : make_uint2(0xffffffffu, 0u);
+      pk[k] = t.x;   // 0xffffffff: out of range, no lookups (guards below)
+      eo[k] = t.y;
     }
     const unsigned e0 = sweep + tid;
     // ---- diagonal components (source = the output element itself): their weights are summed first — one lookup and
@@ -304,10 +318,7 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
     for (int kb = 0; kb < DT_U; kb += 4) {
       long long goff[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned e = sweep + (kb + j) * DT_THREADS + tid;
-        goff[j] = (FULL || e < (unsigned)P.tile) ? base + (long long)__ldg(&P.etab[e]).y : -1;
-      }
+      for (int j = 0; j < 4; ++j) goff[j] = (FULL || pk[kb + j] != 0xffffffffu) ? base + (long long)eo[kb + j] : -1;
       if (P.mode) {
         double2 yv[4];
 #pragma unroll
