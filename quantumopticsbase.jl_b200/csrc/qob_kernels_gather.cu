@@ -382,10 +382,11 @@ int launch_fill_state(void *x, int64_t offset, int64_t n, uint64_t seed, double 
   return QOB_STATUS_OK;
 }
 
-// reductions: per-block tree in shared memory, one atomicAdd(double) per block and component
+// reductions, deterministic (the same bits on every run): per-block tree in shared memory -> one partial per block and
+// component, then one block folds the partials in a fixed order
 template <int MODE>  // 0: sum |x|^2 ; 1: sum conj(x)*y
 __global__ void reduce_kernel(const double2 *__restrict__ x, const double2 *__restrict__ y, long long n,
-                              double *__restrict__ out) {
+                              double *__restrict__ partial) {
   double re = 0.0, im = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double2 a = x[i];
@@ -414,24 +415,53 @@ __global__ void reduce_kernel(const double2 *__restrict__ x, const double2 *__re
       re += sre[k];
       im += sim[k];
     }
-    atomicAdd(out, re);
-    if (MODE == 1) atomicAdd(out + 1, im);
+    partial[2 * blockIdx.x] = re;
+    partial[2 * blockIdx.x + 1] = im;
+  }
+}
+__global__ void reduce_final_kernel(const double *__restrict__ partial, int nblocks, double *__restrict__ out) {
+  double re = 0.0, im = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) {
+    re += partial[2 * i];
+    im += partial[2 * i + 1];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    re += __shfl_down_sync(0xffffffffu, re, o);
+    im += __shfl_down_sync(0xffffffffu, im, o);
+  }
+  __shared__ double sre[8], sim[8];
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    sre[w] = re;
+    sim[w] = im;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+      re += sre[k];
+      im += sim[k];
+    }
+    out[0] = re;
+    out[1] = im;
   }
 }
 static int reduce_common(int mode, const void *x, const void *y, int64_t n, double *host2, cudaStream_t s) {
-  double *d = nullptr;
-  QOB_CUDA(cudaMalloc(&d, 2 * sizeof(double)));
-  cudaMemsetAsync(d, 0, 2 * sizeof(double), s);
-  int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 16));
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 16));
+  double *d = nullptr;   // [2*blocks partials][2 result], stream-ordered allocation (no device-wide synchronisation)
+  QOB_CUDA(cudaMallocAsync(&d, (size_t)(2 * blocks + 2) * sizeof(double), s));
   if (mode == 0)
     reduce_kernel<0><<<(unsigned)blocks, 256, 0, s>>>((const double2 *)x, nullptr, n, d);
   else
     reduce_kernel<1><<<(unsigned)blocks, 256, 0, s>>>((const double2 *)x, (const double2 *)y, n, d);
   QOB_LAUNCHED();
-  cudaError_t e = cudaMemcpyAsync(host2, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, s);
+  reduce_final_kernel<<<1, 256, 0, s>>>(d, blocks, d + 2 * blocks);
+  QOB_LAUNCHED();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host2, d + 2 * blocks, 2 * sizeof(double), cudaMemcpyDeviceToHost, s);
+  cudaError_t e2 = cudaFreeAsync(d, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  cudaFree(d);
   QOB_CUDA(e);
+  QOB_CUDA(e2);
   return QOB_STATUS_OK;
 }
 int launch_norm2(const void *x, int64_t n, double *host_out, cudaStream_t s) {
