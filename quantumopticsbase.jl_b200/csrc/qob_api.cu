@@ -437,10 +437,13 @@ int TensorGroup::compile(int side, int64_t batch, Compiled **out) {
       std::vector<OrientedTerm> shifted = gterms;
       for (auto &o : shifted)
         for (int &a : o.axes) a += shift;
-      const int st = dtile_build(c.dtile, dd, shifted);
+      std::vector<int> declined;
+      const int st = dtile_build(c.dtile, dd, shifted, &declined);
       if (st == QOB_STATUS_OK) {
         c.has_dtile = true;
-        gterms.clear();
+        std::vector<OrientedTerm> rest;   // the terms the tile planner left out go through the gather kernel
+        for (int t : declined) rest.push_back(std::move(gterms[t]));
+        gterms = std::move(rest);
       } else if (st != QOB_STATUS_UNSUPPORTED) {
         return st;
       }

@@ -212,7 +212,10 @@ struct DTileProgram {
 };
 // dims: every tensor axis of the state incl. the batch axis (fastest first); terms: square oriented factors on those axes.
 // Returns QOB_STATUS_UNSUPPORTED when the terms do not fit the scheme (the caller then uses the gather kernel).
-int dtile_build(DTileProgram &p, const std::vector<int64_t> &dims, const std::vector<OrientedTerm> &terms);
+// `declined` (optional) receives the indices of terms the scheme cannot take (too many components, larger than a
+// tile): the program then covers the others and the caller applies the declined ones another way.
+int dtile_build(DTileProgram &p, const std::vector<int64_t> &dims, const std::vector<OrientedTerm> &terms,
+                std::vector<int> *declined = nullptr);
 int dtile_set_coefs(DTileProgram &p, const std::vector<cplx> &coefs, cudaStream_t s);
 int dtile_launch(const DTileProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s);
 

@@ -385,7 +385,10 @@ static void factor_diagonals(const HostMat &m, std::vector<int> &shifts, std::ve
       for (int64_t p = m.colptr[c]; p < m.colptr[c + 1]; ++p) put(m.rowidx[p], c, m.vals[p]);
   } else if (m.kind == QOB_FACTOR_DENSE) {
     for (int64_t c = 0; c < m.cols; ++c)
-      for (int64_t r = 0; r < m.rows; ++r) put(r, c, m.dense[(size_t)(r + c * m.rows)]);
+      for (int64_t r = 0; r < m.rows; ++r) {
+        const cplx v = m.dense[(size_t)(r + c * m.rows)];
+        if (v != cplx(0.0, 0.0)) put(r, c, v);   // zero weights skip their gather in the kernel anyway
+      }
   } else {
     for (int64_t i = 0; i < d; ++i) put(i, i, cplx(1.0, 0.0));
   }
@@ -395,7 +398,9 @@ static void factor_diagonals(const HostMat &m, std::vector<int> &shifts, std::ve
   }
 }
 
-int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std::vector<OrientedTerm> &terms) {
+int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std::vector<OrientedTerm> &terms,
+                std::vector<int> *declined_out) {
+  std::vector<char> declined(terms.size(), 0);   // terms the scheme cannot take: left to the caller (gather kernel)
   auto hp = std::make_shared<DTileProgramHost>();
   DTileProgramHost &H = *hp;
   H.dims = dims;
@@ -412,7 +417,7 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
     const OrientedTerm &T = terms[t];
     H.coef_of_term.push_back(T.coef_index);
     cplx scalar = T.scalar;
-    if (T.axes.size() > DT_MAXF) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: more than %d factors in a term", DT_MAXF);
+    bool decline = T.axes.size() > DT_MAXF;
     std::vector<std::vector<int>> shifts(T.axes.size());
     std::vector<std::vector<std::vector<cplx>>> tables(T.axes.size());
     std::vector<int> axes;
@@ -420,6 +425,7 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
     for (size_t f = 0; f < T.axes.size(); ++f) {
       const HostMat &m = T.mats[f];
       const int ax = T.axes[f];
+      if (decline) break;
       if (m.rows != m.cols || m.rows != dims[ax]) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: non-square factor");
       if (m.is_square_eye()) continue;
       if (dims[ax] == 1) {  // a 1x1 factor is a scalar
@@ -442,8 +448,12 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
       tables[axes.size() - 1] = tb;
     }
     H.scalars.push_back(scalar);
+    if (decline || ncomb > 64) {   // too many single-gather components (e.g. two dense 8x8 factors): not this kernel's job
+      declined[t] = 1;
+      offaxes[t].clear();
+      continue;
+    }
     if (ncomb == 0) continue;
-    if (ncomb > 64) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: %zu components in one term", ncomb);
     std::vector<size_t> cur(axes.size(), 0);
     for (size_t it = 0; it < ncomb; ++it) {
       DComp c;
@@ -497,11 +507,14 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
       if (!std::binary_search(of.begin(), of.end(), v)) return false;
     return true;
   };
-  for (size_t t = 0; t < terms.size(); ++t)
-    if (subset(offaxes[t], pass_free[0])) {
+  for (size_t t = 0; t < terms.size(); ++t) {
+    if (declined[t]) {
+      covered[t] = 1;
+    } else if (subset(offaxes[t], pass_free[0])) {
       covered[t] = 1;
       pass_terms[0].push_back((int)t);
     }
+  }
   while (true) {
     // seed: the uncovered term whose highest off-diagonal axis is lowest
     int seed = -1;
@@ -512,7 +525,11 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
     if (extent(fr) > DT_TILE_CAP) {
       fr = offaxes[seed];  // give up the coalesced low block for this pass
       std::sort(fr.begin(), fr.end());
-      if (extent(fr) > DT_TILE_CAP) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: a term does not fit a tile");
+      if (extent(fr) > DT_TILE_CAP) {   // this term alone exceeds a tile
+        declined[seed] = 1;
+        covered[seed] = 1;
+        continue;
+      }
     }
     // grow with the uncovered terms that come next
     std::vector<int> order;
@@ -535,6 +552,18 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
         covered[t] = 1;
         pass_terms.back().push_back((int)t);
       }
+  }
+  {
+    size_t nd = 0;
+    for (char d : declined) nd += d;
+    if (nd == terms.size() && !terms.empty()) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: no term fits the scheme");
+    if (declined_out) {
+      declined_out->clear();
+      for (size_t t = 0; t < terms.size(); ++t)
+        if (declined[t]) declined_out->push_back((int)t);
+    } else if (nd) {
+      QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: %zu terms do not fit the scheme", nd);
+    }
   }
   // diagonal terms can run in any pass: take them out of pass 0 and hand each to the pass that has the least work so far
   // (passes with few components are memory bound and have issue slots to spare); a leading pass left without terms is

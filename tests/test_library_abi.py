@@ -238,4 +238,10 @@ def test_mixed_radix_tile_planner(Q, monkeypatch):
     Bg = Q.tensor(g, g, g, g, g, g)
     rng = np.random.default_rng(0)
     dense9 = [Q.Operator(g, g, rng.standard_normal((9, 9)) + 0j) for _ in range(2)]
-    assert "gather[" in Q.describe(Q.LazySum([1.0], [Q.LazyTensor(Bg, [1, 2], tuple(dense9))]), ctx=ctx)
+    heavy = Q.LazyTensor(Bg, [1, 2], tuple(dense9))
+    d = Q.describe(Q.LazySum([1.0], [heavy]), ctx=ctx)
+    assert "gather[" in d and "dtile" not in d, d
+    # ... and only that term when there are others
+    light = Q.LazyTensor(Bg, [3, 4], (Q.Operator(g, g, np.diag(np.arange(9.0)) + 0j), Q.Operator(g, g, np.eye(9, k=1) + 0j)))
+    d = Q.describe(Q.LazySum([1.0, 2.0], [heavy, light]), ctx=ctx)
+    assert "dtile[" in d and "terms:1 components:1" in d and "gather[terms=1," in d, d
