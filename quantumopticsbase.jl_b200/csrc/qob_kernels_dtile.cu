@@ -185,7 +185,26 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
         const DCompDev &C = comps[c];
         const WT w0 = cw[c];
         const int nfree = C.nfree;
-        if (nfree <= 2) {
+        if (nfree == 1) {   // one lookup (also two neighbouring factors folded into a joint table on the host)
+          const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0];
+          const TabT *t0 = tab + C.f_tab[0];
+#pragma unroll
+          for (int k = 0; k < DT_U; ++k) {
+            if (FULL || pk[k] != 0xffffffffu) {
+              const unsigned q0 = (pk[k] >> s0) & k0;
+              if constexpr (REALT) {
+                const double t = t0[q0];
+                if constexpr (REALW) wd[k] = fma(w0, t, wd[k]);
+                else {
+                  wd[k].x = fma(w0.x, t, wd[k].x);
+                  wd[k].y = fma(w0.y, t, wd[k].y);
+                }
+              } else {
+                dfma(wd[k], w0, t0[q0]);
+              }
+            }
+          }
+        } else if (nfree == 2) {
           const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0], s1 = C.f_sh[1], k1 = C.f_mask[1];
           const TabT *t0 = tab + C.f_tab[0], *t1 = tab + C.f_tab[1];
 #pragma unroll
@@ -264,9 +283,34 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
             }
           }
         }
-      } else if (nfree <= 2) {
+      } else if (nfree == 1) {   // one lookup (also two neighbouring factors folded into a joint table on the host)
         const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0];
-        const unsigned s1 = C.f_sh[1], k1 = C.f_mask[1];   // nfree == 1: mask 0 and a table holding the single entry 1
+        const TabT *t0 = tab + C.f_tab[0];
+#pragma unroll
+        for (int k = 0; k < DT_U; ++k) {
+          if (FULL || pk[k] != 0xffffffffu) {
+            const unsigned q0 = (pk[k] >> s0) & k0;
+            if constexpr (REALT) {
+              const double t = t0[q0];
+              if (t != 0.0) {
+                const double2 xv = xsrc[k * DT_THREADS];
+                if constexpr (REALW) {
+                  const double w = w0 * t;
+                  acc[k].x = fma(w, xv.x, acc[k].x);
+                  acc[k].y = fma(w, xv.y, acc[k].y);
+                } else {
+                  dfma(acc[k], make_double2(w0.x * t, w0.y * t), xv);
+                }
+              }
+            } else {
+              const double2 w = dmul(w0, t0[q0]);
+              if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xsrc[k * DT_THREADS]);
+            }
+          }
+        }
+      } else if (nfree == 2) {
+        const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0];
+        const unsigned s1 = C.f_sh[1], k1 = C.f_mask[1];
         const TabT *t0 = tab + C.f_tab[0], *t1 = tab + C.f_tab[1];
 #pragma unroll
         for (int k = 0; k < DT_U; ++k) {
@@ -707,6 +751,30 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
           }
         }
         r.delta = (int)delta;
+        if (r.nfree == 2) {
+          // two free factors whose digits are neighbours in the packed word (sites i, i+1 of a bond): one joint table
+          // indexed by both digits at once — one lookup instead of two lookups and a multiply
+          int fa[2], nf = 0;
+          for (size_t f = 0; f < c.axes.size(); ++f)
+            if (std::binary_search(fr.begin(), fr.end(), c.axes[f]) && nf < 2) fa[nf++] = (int)f;
+          const int a0 = c.axes[fa[0]], a1 = c.axes[fa[1]];
+          const int b0 = ax_bits[a0], b1 = ax_bits[a1];
+          if (ax_shift[a1] == ax_shift[a0] + b0 && b0 + b1 <= 8) {
+            std::vector<cplx> joint((size_t)1 << (b0 + b1), cplx(0.0, 0.0));
+            for (int64_t i1 = 0; i1 < dims[a1]; ++i1)
+              for (int64_t i0 = 0; i0 < dims[a0]; ++i0)
+                joint[(size_t)(i0 + (i1 << b0))] = c.table[fa[0]][(size_t)i0] * c.table[fa[1]][(size_t)i1];
+            const int off = add_table(joint);
+            if (off + (int)joint.size() <= 65535) {
+              r.nfree = 1;
+              r.f_sh[0] = (unsigned)ax_shift[a0];
+              r.f_mask[0] = (1u << (b0 + b1)) - 1u;
+              r.f_tab[0] = (unsigned short)off;
+              r.f_sh[1] = r.f_mask[1] = 0;
+              r.f_tab[1] = 0;
+            }
+          }
+        }
         bool diag = true;
         for (int sft : c.shift) diag &= sft == 0;
         r.pad0 = diag ? (r.nfree ? 1 : 2) : 0;   // ordering class
