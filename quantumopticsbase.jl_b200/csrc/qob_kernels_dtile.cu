@@ -24,6 +24,7 @@
 #define DT_MAXF 4        // factors per component (free + fixed each)
 #define DT_MAXAX 64      // tensor axes (incl. the batch axis)
 #define DT_THREADS 256
+#define DT_PTHREADS 512   // persistent variant: one CTA per SM, one sweep per tile
 #define DT_U 8           // outputs per thread and sweep
 #define DT_TILE_CAP 4096 // amplitudes per tile (64 KiB)
 
@@ -75,6 +76,263 @@ __device__ __forceinline__ void dfma(double2 &acc, double2 a, double2 b) {
 // 8-byte doubles (half the shared-memory wavefronts of a 16-byte lookup) and the weight product is real arithmetic.
 // REALW (needs REALT): the coefficients are real as well, so the whole weight is one double (2 DFMA per gather).
 // FULL: the tile is a multiple of the sweep (threads x outputs per thread), no range guards.
+// One sweep: NT threads x DT_U outputs per thread, element e_k = sweep + k*NT + tid (pk/eo: its packed digits / offset).
+template <bool REALT, bool REALW, bool FULL, int NT>
+__device__ __forceinline__ void dt_sweep(const DPassParams &P, const double2 *xs,
+                                         const typename std::conditional<REALT, double, double2>::type *tab,
+                                         const typename std::conditional<REALW, double, double2>::type *cw,
+                                         const DCompDev *comps, unsigned sweep, unsigned tid, long long base,
+                                         const unsigned (&pk)[DT_U], const unsigned (&eo)[DT_U], double2 *__restrict__ y) {
+  typedef typename std::conditional<REALT, double, double2>::type TabT;
+  typedef typename std::conditional<REALW, double, double2>::type WT;
+  double2 acc[DT_U];
+#pragma unroll
+  for (int k = 0; k < DT_U; ++k) acc[k] = make_double2(0.0, 0.0);
+  const unsigned e0 = sweep + tid;
+  // ---- diagonal components (source = the output element itself): their weights are summed first — one lookup and
+  // one multiply-add each — and applied with a single multiply per output; the ones without a free factor are
+  // uniform over the tile
+  if (P.n_off < P.ncomp) {
+    WT wu;
+    if constexpr (REALW) wu = 0.0;
+    else wu = make_double2(0.0, 0.0);
+    for (int c = P.n_off + P.n_dfree; c < P.ncomp; ++c) {
+      if constexpr (REALW) wu += cw[c];
+      else {
+        wu.x += cw[c].x;
+        wu.y += cw[c].y;
+      }
+    }
+    WT wd[DT_U];
+#pragma unroll
+    for (int k = 0; k < DT_U; ++k) wd[k] = wu;
+    for (int c = P.n_off; c < P.n_off + P.n_dfree; ++c) {
+      const DCompDev &C = comps[c];
+      const WT w0 = cw[c];
+      const int nfree = C.nfree;
+      if (nfree == 1) {   // one lookup (also two neighbouring factors folded into a joint table on the host)
+        const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0];
+        const TabT *t0 = tab + C.f_tab[0];
+#pragma unroll
+        for (int k = 0; k < DT_U; ++k) {
+          if (FULL || pk[k] != 0xffffffffu) {
+            const unsigned q0 = (pk[k] >> s0) & k0;
+            if constexpr (REALT) {
+              const double t = t0[q0];
+              if constexpr (REALW) wd[k] = fma(w0, t, wd[k]);
+              else {
+                wd[k].x = fma(w0.x, t, wd[k].x);
+                wd[k].y = fma(w0.y, t, wd[k].y);
+              }
+            } else {
+              dfma(wd[k], w0, t0[q0]);
+            }
+          }
+        }
+      } else if (nfree == 2) {
+        const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0], s1 = C.f_sh[1], k1 = C.f_mask[1];
+        const TabT *t0 = tab + C.f_tab[0], *t1 = tab + C.f_tab[1];
+#pragma unroll
+        for (int k = 0; k < DT_U; ++k) {
+          if (FULL || pk[k] != 0xffffffffu) {
+            const unsigned q0 = (pk[k] >> s0) & k0, q1 = (pk[k] >> s1) & k1;
+            if constexpr (REALT) {
+              const double t = t0[q0] * t1[q1];
+              if constexpr (REALW) wd[k] = fma(w0, t, wd[k]);
+              else {
+                wd[k].x = fma(w0.x, t, wd[k].x);
+                wd[k].y = fma(w0.y, t, wd[k].y);
+              }
+            } else {
+              dfma(wd[k], w0, dmul(t0[q0], t1[q1]));
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < DT_U; ++k) {
+          if (FULL || pk[k] != 0xffffffffu) {
+            double2 w;
+            if constexpr (REALW) w = make_double2(w0, 0.0);
+            else w = w0;
+#pragma unroll 1
+            for (int f = 0; f < nfree; ++f) {
+              const unsigned q = (pk[k] >> C.f_sh[f]) & C.f_mask[f];
+              if constexpr (REALT) {
+                const double t = tab[C.f_tab[f] + q];
+                w.x *= t;
+                w.y *= t;
+              } else {
+                w = dmul(w, tab[C.f_tab[f] + q]);
+              }
+            }
+            if constexpr (REALW) wd[k] += w.x;
+            else {
+              wd[k].x += w.x;
+              wd[k].y += w.y;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < DT_U; ++k) {
+      if (FULL || pk[k] != 0xffffffffu) {
+        if constexpr (REALW) {
+          if (wd[k] != 0.0) {
+            const double2 xv = xs[e0 + k * NT];
+            acc[k].x = fma(wd[k], xv.x, acc[k].x);
+            acc[k].y = fma(wd[k], xv.y, acc[k].y);
+          }
+        } else {
+          if (wd[k].x != 0.0 || wd[k].y != 0.0) dfma(acc[k], wd[k], xs[e0 + k * NT]);
+        }
+      }
+    }
+  }
+  for (int c = 0; c < P.n_off; ++c) {
+    const DCompDev &C = comps[c];
+    const WT w0 = cw[c];
+    const int delta = C.delta, nfree = C.nfree;
+    const double2 *xsrc = xs + (int)e0 + delta;
+    if (nfree == 0) {
+#pragma unroll
+      for (int k = 0; k < DT_U; ++k) {
+        if (FULL || pk[k] != 0xffffffffu) {
+          const double2 xv = xsrc[k * NT];
+          if constexpr (REALW) {
+            acc[k].x = fma(w0, xv.x, acc[k].x);
+            acc[k].y = fma(w0, xv.y, acc[k].y);
+          } else {
+            dfma(acc[k], w0, xv);
+          }
+        }
+      }
+    } else if (nfree == 1) {   // one lookup (also two neighbouring factors folded into a joint table on the host)
+      const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0];
+      const TabT *t0 = tab + C.f_tab[0];
+#pragma unroll
+      for (int k = 0; k < DT_U; ++k) {
+        if (FULL || pk[k] != 0xffffffffu) {
+          const unsigned q0 = (pk[k] >> s0) & k0;
+          if constexpr (REALT) {
+            const double t = t0[q0];
+            if (t != 0.0) {
+              const double2 xv = xsrc[k * NT];
+              if constexpr (REALW) {
+                const double w = w0 * t;
+                acc[k].x = fma(w, xv.x, acc[k].x);
+                acc[k].y = fma(w, xv.y, acc[k].y);
+              } else {
+                dfma(acc[k], make_double2(w0.x * t, w0.y * t), xv);
+              }
+            }
+          } else {
+            const double2 w = dmul(w0, t0[q0]);
+            if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xsrc[k * NT]);
+          }
+        }
+      }
+    } else if (nfree == 2) {
+      const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0];
+      const unsigned s1 = C.f_sh[1], k1 = C.f_mask[1];
+      const TabT *t0 = tab + C.f_tab[0], *t1 = tab + C.f_tab[1];
+#pragma unroll
+      for (int k = 0; k < DT_U; ++k) {
+        if (FULL || pk[k] != 0xffffffffu) {
+          const unsigned q0 = (pk[k] >> s0) & k0, q1 = (pk[k] >> s1) & k1;
+          if constexpr (REALT) {
+            const double t = t0[q0] * t1[q1];
+            if (t != 0.0) {
+              const double2 xv = xsrc[k * NT];
+              if constexpr (REALW) {
+                const double w = w0 * t;
+                acc[k].x = fma(w, xv.x, acc[k].x);
+                acc[k].y = fma(w, xv.y, acc[k].y);
+              } else {
+                dfma(acc[k], make_double2(w0.x * t, w0.y * t), xv);
+              }
+            }
+          } else {
+            const double2 w = dmul(w0, dmul(t0[q0], t1[q1]));
+            if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xsrc[k * NT]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < DT_U; ++k) {
+        if (FULL || pk[k] != 0xffffffffu) {
+          double2 w;
+          if constexpr (REALW) w = make_double2(w0, 0.0);
+          else w = w0;
+#pragma unroll 1
+          for (int f = 0; f < nfree; ++f) {
+            const unsigned q = (pk[k] >> C.f_sh[f]) & C.f_mask[f];
+            if constexpr (REALT) {
+              const double t = tab[C.f_tab[f] + q];
+              w.x *= t;
+              w.y *= t;
+            } else {
+              w = dmul(w, tab[C.f_tab[f] + q]);
+            }
+          }
+          if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xsrc[k * NT]);
+        }
+      }
+    }
+  }
+  // epilogue in batches of 4: the loads of y first (independent, in flight together), then the stores
+#pragma unroll
+  for (int kb = 0; kb < DT_U; kb += 4) {
+    long long goff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) goff[j] = (FULL || pk[kb + j] != 0xffffffffu) ? base + (long long)eo[kb + j] : -1;
+    if (P.mode) {
+      double2 yv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (FULL || goff[j] >= 0) yv[j] = y[goff[j]];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (FULL || goff[j] >= 0) {
+          double2 o = dmul(P.alpha, acc[kb + j]);
+          dfma(o, P.beta, yv[j]);
+          y[goff[j]] = o;
+        }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (FULL || goff[j] >= 0) y[goff[j]] = dmul(P.alpha, acc[kb + j]);
+    }
+  }
+}
+
+// the x tile -> shared memory (16-byte cp.async per amplitude, contiguous runs of R amplitudes); the y lines of a
+// read-modify-write pass are pulled into L2 at the same time
+template <bool FULL, int NT>
+__device__ __forceinline__ void dt_issue_loads(const DPassParams &P, double2 *xs, unsigned tid, long long base,
+                                               const double2 *__restrict__ x, const double2 *__restrict__ y) {
+  for (unsigned e0 = tid; e0 < (unsigned)P.tile; e0 += 8 * NT) {
+    unsigned eo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {   // the table lookups first (independent), then the copies
+      const unsigned e = e0 + j * NT;
+      eo[j] = (FULL || e < (unsigned)P.tile) ? __ldg(&P.etab[e]).y : 0xffffffffu;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const unsigned e = e0 + j * NT;
+      if (FULL || e < (unsigned)P.tile) {
+        const long long off = base + (long long)eo[j];
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(xs + e);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(x + off) : "memory");
+        if (P.mode && (off & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + off));
+      }
+    }
+  }
+}
+
 template <bool REALT, bool REALW, bool FULL>
 __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_constant__ DPassParams P,
                                                               const double2 *__restrict__ x, double2 *__restrict__ y) {
@@ -114,25 +372,7 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
   }
   __syncthreads();
   const long long base = s_base;
-  // ---- the tile of x (contiguous runs of R amplitudes); y lines are pulled into L2 for the read-modify-write epilogue
-  for (unsigned e0 = tid; e0 < (unsigned)P.tile; e0 += 8 * DT_THREADS) {
-    unsigned eo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {   // the table lookups first (independent), then the copies
-      const unsigned e = e0 + j * DT_THREADS;
-      eo[j] = (FULL || e < (unsigned)P.tile) ? __ldg(&P.etab[e]).y : 0xffffffffu;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const unsigned e = e0 + j * DT_THREADS;
-      if (FULL || e < (unsigned)P.tile) {
-        const long long off = base + (long long)eo[j];
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(xs + e);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(x + off) : "memory");
-        if (P.mode && (off & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + off));
-      }
-    }
-  }
+  dt_issue_loads<FULL, DT_THREADS>(P, xs, tid, base, x, y);
   // ---- per-component weight that is uniform over the tile: coefficient x diagonal factors on fixed axes
   for (int c = tid; c < P.ncomp; c += DT_THREADS) {
     const DCompDev &C = comps[c];
@@ -153,234 +393,118 @@ __global__ void __launch_bounds__(DT_THREADS, 3) dtile_kernel(const __grid_const
   __syncthreads();
 
   for (unsigned sweep = 0; sweep < (unsigned)P.tile; sweep += DT_THREADS * DT_U) {
-    double2 acc[DT_U];
     unsigned pk[DT_U], eo[DT_U];
 #pragma unroll
     for (int k = 0; k < DT_U; ++k) {
       const unsigned e = sweep + k * DT_THREADS + tid;
-      acc[k] = make_double2(0.0, 0.0);
       const uint2 t = (FULL || e < (unsigned)P.tile) ? __ldg(&P.etab[e]) : make_uint2(0xffffffffu, 0u);
-      pk[k] = t.x;   // 0xffffffff: out of range, no lookups (guards below)
+      pk[k] = t.x;   // 0xffffffff: out of range, no lookups (guards in dt_sweep)
       eo[k] = t.y;
     }
-    const unsigned e0 = sweep + tid;
-    // ---- diagonal components (source = the output element itself): their weights are summed first — one lookup and
-    // one multiply-add each — and applied with a single multiply per output; the ones without a free factor are
-    // uniform over the tile
-    if (P.n_off < P.ncomp) {
-      WT wu;
-      if constexpr (REALW) wu = 0.0;
-      else wu = make_double2(0.0, 0.0);
-      for (int c = P.n_off + P.n_dfree; c < P.ncomp; ++c) {
-        if constexpr (REALW) wu += cw[c];
-        else {
-          wu.x += cw[c].x;
-          wu.y += cw[c].y;
-        }
-      }
-      WT wd[DT_U];
+    dt_sweep<REALT, REALW, FULL, DT_THREADS>(P, xs, tab, cw, comps, sweep, tid, base, pk, eo, y);
+  }
+}
+
+// Persistent variant: one CTA of DT_PTHREADS threads per SM walks the tiles with TWO tile buffers — the copies of tile
+// t+1 (and the L2 prefetch of its y lines) are in flight while tile t is computed, so the memory pipe never waits for
+// the arithmetic and vice versa.  One sweep covers a tile (DT_PTHREADS x DT_U = 4096), so the per-element table entries
+// are loaded once per CTA and live in registers.  Per-tile data (base offset, uniform weights) rotates over three slots:
+// the slot of tile t+1 is written while laggard warps may still be reading the slot of tile t-1.
+template <bool REALT, bool REALW, bool FULL>
+__global__ void __launch_bounds__(DT_PTHREADS, 1) dtile_persist_kernel(const __grid_constant__ DPassParams P,
+                                                                       const double2 *__restrict__ x, double2 *__restrict__ y,
+                                                                       unsigned ntiles) {
+  typedef typename std::conditional<REALT, double, double2>::type TabT;
+  typedef typename std::conditional<REALW, double, double2>::type WT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *xs0 = reinterpret_cast<double2 *>(smem_raw);
+  double2 *cw2 = xs0 + 2 * (size_t)P.tile;
+  DCompDev *comps = reinterpret_cast<DCompDev *>(cw2 + 3 * (size_t)P.ncomp);
+  TabT *tab = reinterpret_cast<TabT *>(comps + P.ncomp);
+  __shared__ long long s_base[3];
+  const unsigned tid = threadIdx.x;
+
+  for (int i = tid; i < P.ntab; i += DT_PTHREADS) {
+    if constexpr (REALT) tab[i] = P.tables[i].x;
+    else tab[i] = P.tables[i];
+  }
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(P.comps);
+    uint4 *dst = reinterpret_cast<uint4 *>(comps);
+    const int n16 = P.ncomp * (int)(sizeof(DCompDev) / 16);
+    for (int i = tid; i < n16; i += DT_PTHREADS) dst[i] = src[i];
+  }
+  unsigned pk[DT_U], eo[DT_U];
 #pragma unroll
-      for (int k = 0; k < DT_U; ++k) wd[k] = wu;
-      for (int c = P.n_off; c < P.n_off + P.n_dfree; ++c) {
-        const DCompDev &C = comps[c];
-        const WT w0 = cw[c];
-        const int nfree = C.nfree;
-        if (nfree == 1) {   // one lookup (also two neighbouring factors folded into a joint table on the host)
-          const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0];
-          const TabT *t0 = tab + C.f_tab[0];
-#pragma unroll
-          for (int k = 0; k < DT_U; ++k) {
-            if (FULL || pk[k] != 0xffffffffu) {
-              const unsigned q0 = (pk[k] >> s0) & k0;
-              if constexpr (REALT) {
-                const double t = t0[q0];
-                if constexpr (REALW) wd[k] = fma(w0, t, wd[k]);
-                else {
-                  wd[k].x = fma(w0.x, t, wd[k].x);
-                  wd[k].y = fma(w0.y, t, wd[k].y);
-                }
-              } else {
-                dfma(wd[k], w0, t0[q0]);
-              }
-            }
-          }
-        } else if (nfree == 2) {
-          const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0], s1 = C.f_sh[1], k1 = C.f_mask[1];
-          const TabT *t0 = tab + C.f_tab[0], *t1 = tab + C.f_tab[1];
-#pragma unroll
-          for (int k = 0; k < DT_U; ++k) {
-            if (FULL || pk[k] != 0xffffffffu) {
-              const unsigned q0 = (pk[k] >> s0) & k0, q1 = (pk[k] >> s1) & k1;
-              if constexpr (REALT) {
-                const double t = t0[q0] * t1[q1];
-                if constexpr (REALW) wd[k] = fma(w0, t, wd[k]);
-                else {
-                  wd[k].x = fma(w0.x, t, wd[k].x);
-                  wd[k].y = fma(w0.y, t, wd[k].y);
-                }
-              } else {
-                dfma(wd[k], w0, dmul(t0[q0], t1[q1]));
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < DT_U; ++k) {
-            if (FULL || pk[k] != 0xffffffffu) {
-              double2 w;
-              if constexpr (REALW) w = make_double2(w0, 0.0);
-              else w = w0;
-#pragma unroll 1
-              for (int f = 0; f < nfree; ++f) {
-                const unsigned q = (pk[k] >> C.f_sh[f]) & C.f_mask[f];
-                if constexpr (REALT) {
-                  const double t = tab[C.f_tab[f] + q];
-                  w.x *= t;
-                  w.y *= t;
-                } else {
-                  w = dmul(w, tab[C.f_tab[f] + q]);
-                }
-              }
-              if constexpr (REALW) wd[k] += w.x;
-              else {
-                wd[k].x += w.x;
-                wd[k].y += w.y;
-              }
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < DT_U; ++k) {
-        if (FULL || pk[k] != 0xffffffffu) {
-          if constexpr (REALW) {
-            if (wd[k] != 0.0) {
-              const double2 xv = xs[e0 + k * DT_THREADS];
-              acc[k].x = fma(wd[k], xv.x, acc[k].x);
-              acc[k].y = fma(wd[k], xv.y, acc[k].y);
-            }
-          } else {
-            if (wd[k].x != 0.0 || wd[k].y != 0.0) dfma(acc[k], wd[k], xs[e0 + k * DT_THREADS]);
-          }
-        }
-      }
+  for (int k = 0; k < DT_U; ++k) {
+    const unsigned e = k * DT_PTHREADS + tid;
+    const uint2 t = (FULL || e < (unsigned)P.tile) ? __ldg(&P.etab[e]) : make_uint2(0xffffffffu, 0u);
+    pk[k] = t.x;
+    eo[k] = t.y;
+  }
+  __syncthreads();
+  // per-tile data into slot `slot`: base offset (warp 0) and the uniform weight of every component (one thread each,
+  // with its own digits of the fixed axes)
+  auto decode = [&](unsigned tile, int slot) {
+    if (tid < 32) {
+      long long part = 0;
+      for (unsigned a = tid; a < (unsigned)P.nfixed; a += 32)
+        part += (long long)((tile / P.fx_below[a]) % P.fx_dim[a]) * P.fx_stride[a];
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if (tid == 0) s_base[slot] = part;
     }
-    for (int c = 0; c < P.n_off; ++c) {
+    WT *cw = reinterpret_cast<WT *>(cw2 + (size_t)slot * P.ncomp);
+    for (int c = (int)tid - 32; c < P.ncomp; c += DT_PTHREADS - 32) {
+      if (c < 0) continue;
       const DCompDev &C = comps[c];
-      const WT w0 = cw[c];
-      const int delta = C.delta, nfree = C.nfree;
-      const double2 *xsrc = xs + (int)e0 + delta;
-      if (nfree == 0) {
-#pragma unroll
-        for (int k = 0; k < DT_U; ++k) {
-          if (FULL || pk[k] != 0xffffffffu) {
-            const double2 xv = xsrc[k * DT_THREADS];
-            if constexpr (REALW) {
-              acc[k].x = fma(w0, xv.x, acc[k].x);
-              acc[k].y = fma(w0, xv.y, acc[k].y);
-            } else {
-              dfma(acc[k], w0, xv);
-            }
-          }
-        }
-      } else if (nfree == 1) {   // one lookup (also two neighbouring factors folded into a joint table on the host)
-        const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0];
-        const TabT *t0 = tab + C.f_tab[0];
-#pragma unroll
-        for (int k = 0; k < DT_U; ++k) {
-          if (FULL || pk[k] != 0xffffffffu) {
-            const unsigned q0 = (pk[k] >> s0) & k0;
-            if constexpr (REALT) {
-              const double t = t0[q0];
-              if (t != 0.0) {
-                const double2 xv = xsrc[k * DT_THREADS];
-                if constexpr (REALW) {
-                  const double w = w0 * t;
-                  acc[k].x = fma(w, xv.x, acc[k].x);
-                  acc[k].y = fma(w, xv.y, acc[k].y);
-                } else {
-                  dfma(acc[k], make_double2(w0.x * t, w0.y * t), xv);
-                }
-              }
-            } else {
-              const double2 w = dmul(w0, t0[q0]);
-              if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xsrc[k * DT_THREADS]);
-            }
-          }
-        }
-      } else if (nfree == 2) {
-        const unsigned s0 = C.f_sh[0], k0 = C.f_mask[0];
-        const unsigned s1 = C.f_sh[1], k1 = C.f_mask[1];
-        const TabT *t0 = tab + C.f_tab[0], *t1 = tab + C.f_tab[1];
-#pragma unroll
-        for (int k = 0; k < DT_U; ++k) {
-          if (FULL || pk[k] != 0xffffffffu) {
-            const unsigned q0 = (pk[k] >> s0) & k0, q1 = (pk[k] >> s1) & k1;
-            if constexpr (REALT) {
-              const double t = t0[q0] * t1[q1];
-              if (t != 0.0) {
-                const double2 xv = xsrc[k * DT_THREADS];
-                if constexpr (REALW) {
-                  const double w = w0 * t;
-                  acc[k].x = fma(w, xv.x, acc[k].x);
-                  acc[k].y = fma(w, xv.y, acc[k].y);
-                } else {
-                  dfma(acc[k], make_double2(w0.x * t, w0.y * t), xv);
-                }
-              }
-            } else {
-              const double2 w = dmul(w0, dmul(t0[q0], t1[q1]));
-              if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xsrc[k * DT_THREADS]);
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < DT_U; ++k) {
-          if (FULL || pk[k] != 0xffffffffu) {
-            double2 w;
-            if constexpr (REALW) w = make_double2(w0, 0.0);
-            else w = w0;
-#pragma unroll 1
-            for (int f = 0; f < nfree; ++f) {
-              const unsigned q = (pk[k] >> C.f_sh[f]) & C.f_mask[f];
-              if constexpr (REALT) {
-                const double t = tab[C.f_tab[f] + q];
-                w.x *= t;
-                w.y *= t;
-              } else {
-                w = dmul(w, tab[C.f_tab[f] + q]);
-              }
-            }
-            if (w.x != 0.0 || w.y != 0.0) dfma(acc[k], w, xsrc[k * DT_THREADS]);
-          }
+      double2 w = P.coef[C.coef];
+      for (int f = 0; f < C.nfixed; ++f) {
+        const unsigned a = C.x_slot[f];
+        const unsigned dg = (tile / P.fx_below[a]) % P.fx_dim[a];
+        if constexpr (REALT) {
+          const double t = tab[C.x_tab[f] + dg];
+          w.x *= t;
+          w.y *= t;
+        } else {
+          w = dmul(w, tab[C.x_tab[f] + dg]);
         }
       }
+      if constexpr (REALW) cw[c] = w.x;
+      else cw[c] = w;
     }
-    // epilogue in batches of 4: the loads of y first (independent, in flight together), then the stores
+  };
+  auto issue = [&](int slot, double2 *xs) {
+    const long long base = s_base[slot];
 #pragma unroll
-    for (int kb = 0; kb < DT_U; kb += 4) {
-      long long goff[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) goff[j] = (FULL || pk[kb + j] != 0xffffffffu) ? base + (long long)eo[kb + j] : -1;
-      if (P.mode) {
-        double2 yv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (FULL || goff[j] >= 0) yv[j] = y[goff[j]];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (FULL || goff[j] >= 0) {
-            double2 o = dmul(P.alpha, acc[kb + j]);
-            dfma(o, P.beta, yv[j]);
-            y[goff[j]] = o;
-          }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (FULL || goff[j] >= 0) y[goff[j]] = dmul(P.alpha, acc[kb + j]);
+    for (int k = 0; k < DT_U; ++k) {
+      if (FULL || pk[k] != 0xffffffffu) {
+        const long long off = base + (long long)eo[k];
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(xs + k * DT_PTHREADS + tid);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(x + off) : "memory");
+        if (P.mode && (off & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(y + off));
       }
     }
+  };
+  unsigned tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  decode(tile, 0);
+  __syncthreads();
+  issue(0, xs0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int slot = 0, buf = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    const unsigned next = tile + gridDim.x;
+    const int nslot = slot == 2 ? 0 : slot + 1;
+    if (next < ntiles) decode(next, nslot);
+    __syncthreads();   // slot of the next tile is written; everyone is done with the other tile buffer
+    if (next < ntiles) issue(nslot, xs0 + (size_t)(buf ^ 1) * P.tile);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's copies of the current tile have landed
+    __syncthreads();   // ... and everybody else's
+    dt_sweep<REALT, REALW, FULL, DT_PTHREADS>(P, xs0 + (size_t)buf * P.tile, tab, reinterpret_cast<const WT *>(cw2 + (size_t)slot * P.ncomp),
+                                              comps, 0u, tid, s_base[slot], pk, eo, y);
+    slot = nslot;
+    buf ^= 1;
   }
 }
 
@@ -843,7 +967,7 @@ int dtile_launch(const DTileProgram &prog, cplx alpha, const void *x, cplx beta,
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     auto set = [](const void *f) {
-      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     };
     set((const void *)dtile_kernel<true, true, true>);
     set((const void *)dtile_kernel<true, true, false>);
@@ -851,8 +975,19 @@ int dtile_launch(const DTileProgram &prog, cplx alpha, const void *x, cplx beta,
     set((const void *)dtile_kernel<true, false, false>);
     set((const void *)dtile_kernel<false, false, true>);
     set((const void *)dtile_kernel<false, false, false>);
+    set((const void *)dtile_persist_kernel<true, true, true>);
+    set((const void *)dtile_persist_kernel<true, true, false>);
+    set((const void *)dtile_persist_kernel<true, false, true>);
+    set((const void *)dtile_persist_kernel<true, false, false>);
+    set((const void *)dtile_persist_kernel<false, false, true>);
+    set((const void *)dtile_persist_kernel<false, false, false>);
   });
   if (attr_err != cudaSuccess) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+  // QOB_DTILE_PERSIST: 0 = one CTA per tile, 1 (default) = persistent CTAs when there are enough tiles, 2 = always
+  const char *pm = getenv("QOB_DTILE_PERSIST");
+  const int persist_mode = pm && *pm ? atoi(pm) : 1;
+  int dev = 0, sm_count = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   bool first = true;
   for (auto &pp : H.passes) {
     DPassHost &Pz = *pp;
@@ -863,14 +998,22 @@ int dtile_launch(const DTileProgram &prog, cplx alpha, const void *x, cplx beta,
     P.beta = make_double2(b.real(), b.imag());
     P.mode = (b == cplx(0.0, 0.0)) ? 0 : 1;
     first = false;
-    const bool full = Pz.tile % (DT_THREADS * DT_U) == 0;
     const unsigned grid = (unsigned)Pz.ntiles;
     const double2 *xp = (const double2 *)x;
     double2 *yp = (double2 *)y;
-#define DT_GO(RT, RW)                                                                       \
-  do {                                                                                      \
-    if (full) dtile_kernel<RT, RW, true><<<grid, DT_THREADS, Pz.smem, s>>>(P, xp, yp);      \
-    else dtile_kernel<RT, RW, false><<<grid, DT_THREADS, Pz.smem, s>>>(P, xp, yp);          \
+    // persistent double-buffered variant: worth it when every SM gets several tiles
+    const size_t psmem = Pz.smem + (size_t)Pz.tile * 16 + (size_t)Pz.params.ncomp * 32;
+    const bool persist = persist_mode != 0 && Pz.tile <= DT_PTHREADS * DT_U && psmem <= 220 * 1024 &&
+                         (persist_mode == 2 || Pz.ntiles >= 8ll * sm_count);
+    const bool full = persist ? Pz.tile == DT_PTHREADS * DT_U : Pz.tile % (DT_THREADS * DT_U) == 0;
+#define DT_GO(RT, RW)                                                                                              \
+  do {                                                                                                             \
+    if (persist) {                                                                                                 \
+      const unsigned pg = (unsigned)std::min<int64_t>(Pz.ntiles, sm_count);                                        \
+      if (full) dtile_persist_kernel<RT, RW, true><<<pg, DT_PTHREADS, psmem, s>>>(P, xp, yp, grid);                \
+      else dtile_persist_kernel<RT, RW, false><<<pg, DT_PTHREADS, psmem, s>>>(P, xp, yp, grid);                    \
+    } else if (full) dtile_kernel<RT, RW, true><<<grid, DT_THREADS, Pz.smem, s>>>(P, xp, yp);                      \
+    else dtile_kernel<RT, RW, false><<<grid, DT_THREADS, Pz.smem, s>>>(P, xp, yp);                                 \
   } while (0)
     if (Pz.real_tables && H.coefs_real) DT_GO(true, true);
     else if (Pz.real_tables) DT_GO(true, false);

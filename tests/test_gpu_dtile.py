@@ -12,11 +12,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 
-@pytest.fixture()
-def Q(monkeypatch):
+@pytest.fixture(params=["one-cta-per-tile", "persistent"])
+def Q(monkeypatch, request):
+    """every test runs with both launch schemes: one CTA per tile, and the persistent double-buffered CTAs (forced on
+    here; by default they are used once there are >= 8 tiles per SM)"""
     import qob200
 
     monkeypatch.setenv("QOB_DTILE_MIN_ELEMS", "1")
+    monkeypatch.setenv("QOB_DTILE_PERSIST", "2" if request.param == "persistent" else "0")
     return qob200
 
 
@@ -68,7 +71,7 @@ def test_random_mixed_radix_lazysum(Q, seed):
 
 def test_random_sweep_mostly_used_the_tile_passes():
     """(runs after the sweep) single terms that expand into > 64 components are declined, the rest of the sum is taken"""
-    assert len(_USED) == 12 and sum(_USED) >= 10, _USED
+    assert len(_USED) == 24 and sum(_USED) >= 20, _USED
 
 
 @pytest.mark.parametrize("sites,cutoff", [(6, 4), (4, 9), (7, 7)])
@@ -158,13 +161,15 @@ def test_heavy_term_beside_tile_terms(Q):
     H.check_mul(s, dims, dims, rng, tol=TOL, nbatch=3)
 
 
-def test_large_state_default_threshold(monkeypatch):
-    """no override: a 2^21-amplitude Bose-Hubbard state takes the tile passes by default; Hermiticity + linearity +
-    agreement with the gather kernel (QOB_DISABLE_DTILE=1) on the full vector"""
+@pytest.mark.parametrize("sites", [7, 8])
+def test_large_state_default_threshold(monkeypatch, sites):
+    """no override: a 2^21 / 2^24-amplitude Bose-Hubbard state takes the tile passes by default (8 sites: 4096 tiles per
+    pass, the persistent CTAs); Hermiticity + agreement with the gather kernel (QOB_DISABLE_DTILE=1) on the full vector"""
     import qob200 as Q
 
     monkeypatch.delenv("QOB_DTILE_MIN_ELEMS", raising=False)
-    sites, cutoff = 7, 7
+    monkeypatch.delenv("QOB_DTILE_PERSIST", raising=False)
+    cutoff = 7
     f = Q.FockBasis(cutoff)
     B = Q.tensor(*[f] * sites)
     a, ad, n = Q.destroy(f), Q.create(f), Q.number(f)
