@@ -574,9 +574,15 @@ int dtile_build(DTileProgram &prog, const std::vector<int64_t> &dims, const std:
   H.dims = dims;
   const int n = (int)dims.size();
   if (n > DT_MAXAX) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: more than %d axes", DT_MAXAX);
-  for (int64_t d : dims) {
-    if (d < 1 || d > 4096) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: axis dimension %lld", (long long)d);
-    H.total *= d;
+  {
+    std::vector<char> has_factor((size_t)n, 0);   // axes without factors (e.g. the batch) may be long: they are never free
+    for (const OrientedTerm &T : terms)
+      for (int a : T.axes) has_factor[(size_t)a] = 1;
+    for (int a = 0; a < n; ++a) {
+      const int64_t d = dims[a];
+      if (d < 1 || d > (has_factor[a] ? 4096 : 0x7FFFFFFFll)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dtile: axis dimension %lld", (long long)d);
+      H.total *= d;
+    }
   }
   // ---- components of every term
   std::vector<std::vector<DComp>> comps(terms.size());

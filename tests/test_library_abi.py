@@ -226,6 +226,12 @@ def test_mixed_radix_tile_planner(Q, monkeypatch):
     assert sum(int(s.split(" ")[0]) for s in d.split("components:")[1:]) == 22 and d.count(" real}") == 3, d
     # X*op with 96 rows: the batch becomes two leading axes (32 x 3), 8 tensor axes in all
     assert "dtile[axes=10," in Q.describe(_bose_hubbard(Q, 8, 7), "right", 96, ctx=ctx)
+    # op*rho with more columns than a tile holds: the batch axis is never free, one contiguous pass does it all
+    d = Q.describe(_bose_hubbard(Q, 4, 7), "left", 5000, ctx=ctx)
+    assert "dtile[axes=5,passes=1]" in d and "run:4096" in d, d
+    # rho*op with 5000 rows: 50 x 100; a prime number of rows cannot be split and stays with the gather kernel
+    assert "run:50 " in Q.describe(_bose_hubbard(Q, 4, 7), "right", 5000, ctx=ctx)
+    assert "gather[" in Q.describe(_bose_hubbard(Q, 4, 7), "right", 4099, ctx=ctx)
     # below the size threshold, or switched off: the generic gather kernel
     assert "gather[" in Q.describe(_bose_hubbard(Q, 4, 3), ctx=ctx)
     monkeypatch.setenv("QOB_DISABLE_DTILE", "1")
