@@ -432,7 +432,14 @@ int TensorGroup::compile(int side, int64_t batch, Compiled **out) {
       }
     }
     for (int k = 0; k < n; ++k) dd.push_back(c.dims_out[k]);
-    if (side == QOB_SIDE_LEFT && batch > 1) dd.push_back(batch);
+    if (side == QOB_SIDE_LEFT && batch > 1) {
+      // a small system on many columns: a few whole columns per tile (the batch axis carries no factor and may be split)
+      int64_t lo = 1;
+      for (int64_t v = std::min<int64_t>(batch, 4096 / std::max<int64_t>(1, c.d_out)); v > 1 && lo == 1; --v)
+        if (batch % v == 0) lo = v;
+      if (lo > 1) dd.push_back(lo);
+      if (batch / lo > 1) dd.push_back(batch / lo);
+    }
     if (ok) {
       std::vector<OrientedTerm> shifted = gterms;
       for (auto &o : shifted)

@@ -161,6 +161,40 @@ def test_heavy_term_beside_tile_terms(Q):
     H.check_mul(s, dims, dims, rng, tol=TOL, nbatch=3)
 
 
+def test_density_matrix_commutator_default_threshold(monkeypatch):
+    """-i[H, rho] for a 3-site Bose-Hubbard H (D = 512) on a dense 512 x 512 rho as the two mul! calls of a master
+    equation: 2^18 amplitudes, so both sides take the tile passes with the default settings (rho*H: the 512 rows are the
+    fastest axis, split 64 x 8)"""
+    import qob200 as Q
+
+    monkeypatch.delenv("QOB_DTILE_MIN_ELEMS", raising=False)
+    monkeypatch.delenv("QOB_DTILE_PERSIST", raising=False)
+    rng = np.random.default_rng(61)
+    sites, cutoff = 3, 7
+    d = cutoff + 1
+    dims = (d,) * sites
+    a, ad, num = O.destroy(cutoff).data, O.create(cutoff).data, O.number(cutoff).data
+    pairs, coefs = [], []
+    for i in range(1, sites):
+        pairs += [H.lazytensor(dims, dims, [i, i + 1], [ad, a]), H.lazytensor(dims, dims, [i, i + 1], [a, ad])]
+        coefs += [-1.0, -1.0]
+    for i in range(1, sites + 1):
+        pairs.append(H.lazytensor(dims, dims, [i], [sp.csc_matrix(num @ num - num)]))
+        coefs.append(0.5)
+    s = H.lazysum(dims, dims, coefs, pairs)
+    D = d ** sites
+    assert "dtile" in Q.describe(s.q, "left", D) and "dtile" in Q.describe(s.q, "right", D)
+    rho = H.rnd(rng, D, D)
+    st = H.denseop(dims, dims, rho)
+    r = H.denseop(dims, dims, np.full((D, D), np.nan + 0j))
+    ro = H.denseop(dims, dims, np.zeros((D, D), dtype=complex))
+    O.mul(ro.o, s.o, st.o, -1j, 0.0)
+    O.mul(ro.o, st.o, s.o, 1j, 1.0)
+    Q.mul_(r.q, s.q, st.q, -1j, 0.0)
+    Q.mul_(r.q, st.q, s.q, 1j, 1.0)
+    assert H.rel_err(r.q.to_host(), ro.o.data) <= TOL
+
+
 @pytest.mark.parametrize("sites", [7, 8])
 def test_large_state_default_threshold(monkeypatch, sites):
     """no override: a 2^21 / 2^24-amplitude Bose-Hubbard state takes the tile passes by default (8 sites: 4096 tiles per
