@@ -55,20 +55,66 @@ def measured_peaks():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML from a background thread (a sample every
+    ~2 ms: the timed region of the default run is well under 100 ms, shorter than one `nvidia-smi -lms` period);
+    `nvidia-smi` polling is the fallback when the NVML binding is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
+        self.p = self.f = self.thread = None
+        self.sm, self.mx, self.bits = [], 0.0, 0
+        try:
+            import threading
+
+            import pynvml
+
+            pynvml.nvmlInit()
+            handle = None
+            try:
+                import torch
+
+                pr = torch.cuda.get_device_properties(gpu_index)
+                bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+                handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self._stop = threading.Event()
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                        self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.002)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            if self.sm:
+                out = {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.mx,
+                       "reasons": sorted(nm for bit, nm in self.REASONS.items() if self.bits & bit), "samples": len(self.sm),
+                       "source": "nvml"}
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -94,7 +140,8 @@ class ClockSampler:
                     reasons.add(nm)
         os.unlink(self.f.name)
         if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                   "source": "nvidia-smi"}
         return out
 
 
