@@ -158,7 +158,9 @@ def run_reference(args, rank, world):
 
     from oracle import qob_oracle as O
 
-    n = 28 if world == 1 else 33
+    # the same chain the product arm runs: N=28 on one GPU; sharded, the largest that fits three slabs per GPU of 180 GB
+    # (N=33 from 4 GPUs on, N=32 on 2)
+    n = 28 if world == 1 else (32 if world == 2 else 33)
     nterms = 3 * n
     total = args.steps + args.warmup
     pa = [np.array([[0, 1], [1, 0]], dtype=complex), np.array([[0, -1j], [1j, 0]], dtype=complex),
