@@ -251,3 +251,59 @@ def test_mixed_radix_tile_planner(Q, monkeypatch):
     light = Q.LazyTensor(Bg, [3, 4], (Q.Operator(g, g, np.diag(np.arange(9.0)) + 0j), Q.Operator(g, g, np.eye(9, k=1) + 0j)))
     d = Q.describe(Q.LazySum([1.0, 2.0], [heavy, light]), ctx=ctx)
     assert "dtile[" in d and "terms:1 components:1" in d and "gather[terms=1," in d, d
+
+
+def test_mixed_radix_planner_fuzz_accounts_for_every_term(Q, monkeypatch):
+    """Planning only, 150 random systems (dims 2..9 and a few large axes, 1-3 factor terms, shifted / diagonal / general
+    sparse / small dense factors, both sides, random batch): the planner terminates, every term lands in exactly one tile
+    pass or in the gather kernel, tiles stay within 4096 amplitudes."""
+    import re
+
+    import numpy as np
+    import scipy.sparse as sp
+
+    monkeypatch.setenv("QOB_DTILE_MIN_ELEMS", "1")
+    ctx = Q.context(-1)
+    rng = np.random.default_rng(2024)
+
+    def factor(b, d):
+        kind = rng.integers(0, 5)
+        if kind == 0:
+            m = sp.diags(rng.standard_normal(d)).tocsc()
+        elif kind == 1:
+            k = int(rng.integers(1, d)) * (1 if rng.random() < 0.5 else -1)
+            m = sp.diags(rng.standard_normal(d - abs(k)) + 1.5, k, shape=(d, d)).tocsc()
+        elif kind == 2:
+            m = sp.random(d, d, density=min(1.0, 2.0 / d), random_state=np.random.RandomState(int(rng.integers(1 << 30))), format="csc")
+        elif kind == 3 and d <= 4:
+            m = rng.standard_normal((d, d))
+        else:
+            m = (sp.diags(np.ones(d - 1), 1) + sp.diags(np.ones(d - 1), -1)).tocsc()
+        return Q.Operator(b, b, m.astype(complex) if sp.issparse(m) else m + 0j)
+
+    seen_dtile = seen_gather = 0
+    for it in range(150):
+        n = int(rng.integers(2, 9))
+        dims = [int(rng.choice([2, 3, 4, 5, 7, 8, 9])) for _ in range(n)]
+        if rng.random() < 0.15:
+            dims[int(rng.integers(0, n))] = int(rng.choice([64, 300, 2100, 5000]))
+        bases = [Q.GenericBasis(d) for d in dims]
+        B = Q.tensor(*bases) if n > 1 else bases[0]
+        nterms = int(rng.integers(1, 10))
+        terms = []
+        for _ in range(nterms):
+            k = int(rng.integers(1, min(3, n) + 1))
+            idx = sorted(int(v) + 1 for v in rng.choice(n, size=k, replace=False))
+            terms.append(Q.LazyTensor(B, idx, tuple(factor(bases[i - 1], dims[i - 1]) for i in idx)))
+        S = Q.LazySum([1.0] * nterms, terms)
+        side = "left" if rng.random() < 0.6 else "right"
+        batch = int(rng.choice([1, 1, 3, 8, 96, 97, 640, 5000]))
+        d = Q.describe(S, side, batch, ctx=ctx)
+        in_tiles = sum(int(v) for v in re.findall(r" terms:(\d+) components", d))
+        in_gather = sum(int(v) for v in re.findall(r"gather\[terms=(\d+),", d))
+        in_seq = sum(int(v) for v in re.findall(r"seq\[terms=(\d+):", d))
+        assert in_tiles + in_gather + in_seq == nterms, (dims, side, batch, d)
+        assert all(int(v) <= 4096 for v in re.findall(r" tile:(\d+) ", d)), d
+        seen_dtile += "dtile[" in d
+        seen_gather += "gather[" in d
+    assert seen_dtile >= 100 and seen_gather >= 5, (seen_dtile, seen_gather)
