@@ -859,3 +859,56 @@ def state_at(seed, index, scale=1.0):
     out = np.zeros(2)
     lib().orc_state_at(ctypes.c_uint64(seed), ctypes.c_double(scale), ctypes.c_int64(index), _p(out))
     return complex(out[0], out[1])
+
+
+# ------------------------------------------------------------------------------------ next rows of SURVEY §8(f)
+# Restated ahead of the device implementation (round 2): the oracle comes first.  Nothing in the product uses these.
+def ptrace_op(dims_l, dims_r, data, indices):
+    """ptrace(a::DataOperator, indices) — src/operators_dense.jl:191-196, 311-342: sum over equal values of the traced
+    subsystems on both sides, result[J_l, J_r] = sum_t a[(J_l, t), (J_r, t)] (subsystem 1 fastest, 1-based indices).
+    Returns (dims_l kept, dims_r kept, matrix)."""
+    idx = sorted(int(i) - 1 for i in (indices if hasattr(indices, "__iter__") else [indices]))
+    n = len(dims_l)
+    if len(idx) == 0 or len(idx) >= n or len(set(idx)) != len(idx) or idx[0] < 0 or idx[-1] >= n:
+        raise ArgumentError("ptrace: indices must select some but not all subsystems")   # check_ptrace_arguments
+    for i in idx:
+        if dims_l[i] != dims_r[i]:
+            raise ArgumentError("ptrace: traced subsystems need equal left and right dimensions")
+    a = np.asarray(_dense_data(data) if not isinstance(data, np.ndarray) else data)
+    # column-major composite index: axis k of the reshaped tensor (order="F") is subsystem k+1
+    t = a.reshape(tuple(dims_l) + tuple(dims_r), order="F")
+    keep = [k for k in range(n) if k not in idx]
+    letters = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
+    left = [letters[k] for k in range(n)]
+    right = [letters[k] if k in idx else letters[n + k] for k in range(n)]
+    out = "".join(left[k] for k in keep) + "".join(right[k] for k in keep)
+    r = np.einsum("".join(left) + "".join(right) + "->" + out, t)
+    kl, kr = tuple(dims_l[k] for k in keep), tuple(dims_r[k] for k in keep)
+    return kl, kr, np.asfortranarray(r.reshape(int(np.prod(kl)), int(np.prod(kr)), order="F"))
+
+
+def ptrace_ket(dims, psi, indices):
+    """ptrace(psi::Ket, indices) — src/operators_dense.jl:199-206, 344-362: result[J_l, J_r] = sum_t psi[(J_l,t)] conj(psi[(J_r,t)])"""
+    v = np.asarray(psi).reshape(-1)
+    return ptrace_op(dims, dims, np.outer(v, np.conj(v)), indices)
+
+
+def ptrace_bra(dims, psi, indices):
+    """ptrace(psi::Bra, indices) — src/operators_dense.jl:208-215, 364-383: result[J_l, J_r] = sum_t conj(psi[(J_l,t)]) psi[(J_r,t)]"""
+    v = np.asarray(psi).reshape(-1)
+    return ptrace_op(dims, dims, np.outer(np.conj(v), v), indices)
+
+
+def lindblad_rhs(H, J, rho, rates=None):
+    """The master-equation right-hand side as the mul! call pattern of test/test_sciml_broadcast_interfaces.jl:36-43 builds
+    it, -i[H, rho] + sum_k g_k (J_k rho J_k^+ - (J_k^+ J_k rho + rho J_k^+ J_k)/2), with dense matrices (the fused device
+    kernel of round 2 will be checked against this)."""
+    H = np.asarray(H if isinstance(H, np.ndarray) else dense(H))
+    rho = np.asarray(rho)
+    out = -1j * (H @ rho - rho @ H)
+    for k, Jk in enumerate(J):
+        Jm = np.asarray(Jk if isinstance(Jk, np.ndarray) else dense(Jk))
+        g = 1.0 if rates is None else rates[k]
+        JdJ = Jm.conj().T @ Jm
+        out += g * (Jm @ rho @ Jm.conj().T - 0.5 * (JdJ @ rho + rho @ JdJ))
+    return out

@@ -268,3 +268,96 @@ def test_generator_is_deterministic():
     assert np.array_equal(a[32:], b)
     assert O.state_at(9, 40, 0.5) == a[40]
     assert np.all(np.abs(a.real) <= 0.5) and np.all(np.abs(a.imag) <= 0.5)
+
+
+# ------------------------------------------------------------------ SURVEY §8(f) rows restated ahead of the device code
+def _kron(*ms):
+    """a (x) b (x) c with subsystem 1 fastest = kron(c, kron(b, a)) in numpy's convention"""
+    out = np.array([[1.0 + 0j]])
+    for m in ms:
+        out = np.kron(m, out)
+    return out
+
+
+def test_ptrace_identities():
+    """test/test_abstractdata.jl:198-219: ptrace(op1 (x) op2 (x) op3, k) == (the others) * tr(op_k); argument errors."""
+    rng = np.random.default_rng(7)
+    dl, dr = (2, 3, 4), (2, 3, 4)
+    o1, o2, o3 = H.rnd(rng, 2, 2), H.rnd(rng, 3, 3), H.rnd(rng, 4, 4)
+    o123 = _kron(o1, o2, o3)
+    cases = {(3,): _kron(o1, o2) * np.trace(o3), (2,): _kron(o1, o3) * np.trace(o2), (1,): _kron(o2, o3) * np.trace(o1),
+             (2, 3): o1 * np.trace(o2) * np.trace(o3), (1, 3): o2 * np.trace(o1) * np.trace(o3),
+             (1, 2): o3 * np.trace(o1) * np.trace(o2)}
+    for idx, ref in cases.items():
+        kl, kr, r = O.ptrace_op(dl, dr, o123, list(idx))
+        assert r.shape == ref.shape and np.allclose(r, ref, rtol=1e-13, atol=1e-13)
+        assert kl == tuple(d for k, d in enumerate(dl) if k + 1 not in idx)
+    with pytest.raises(O.ArgumentError):
+        O.ptrace_op(dl, dr, o123, [1, 2, 3])
+    with pytest.raises(O.ArgumentError):
+        O.ptrace_op((2, 3), (2, 4), H.rnd(rng, 6, 8), [2])      # traced subsystem with unequal dimensions
+    # rectangular kept subsystems are fine: trace subsystem 1 of a (2*3) x (2*5) operator
+    a = H.rnd(rng, 6, 10)
+    _, _, r = O.ptrace_op((2, 3), (2, 5), a, [1])
+    ref = sum(a[t::2, t::2] for t in range(2))
+    assert np.allclose(r, ref)
+    # definition by explicit loops on a random (non-product) operator
+    a = H.rnd(rng, 24, 24)
+    _, _, r = O.ptrace_op(dl, dr, a, [2])
+    ref = np.zeros((8, 8), dtype=complex)
+    for i1 in range(2):
+        for i3 in range(4):
+            for j1 in range(2):
+                for j3 in range(4):
+                    for t in range(3):
+                        ref[i1 + 2 * i3, j1 + 2 * j3] += a[i1 + 2 * t + 6 * i3, j1 + 2 * t + 6 * j3]
+    assert np.allclose(r, ref, rtol=1e-13, atol=1e-13)
+
+
+def test_ptrace_states_and_expect():
+    """test/test_abstractdata.jl:233-234: expect(k, op, psi) == expect(op, ptrace(psi, others)); bra = conj of ket"""
+    rng = np.random.default_rng(8)
+    dims = (2, 3, 4)
+    psi = H.rnd(rng, 24)
+    psi /= np.linalg.norm(psi)
+    o2 = H.rnd(rng, 3, 3)
+    full = _kron(np.eye(2), o2, np.eye(4))
+    _, _, rho2 = O.ptrace_ket(dims, psi, [1, 3])
+    assert np.isclose(np.trace(o2 @ rho2), np.vdot(psi, full @ psi))
+    assert np.isclose(np.trace(rho2), 1.0) and np.allclose(rho2, rho2.conj().T)
+    _, _, rb = O.ptrace_bra(dims, psi.conj(), [1, 3])
+    assert np.allclose(rb, rho2)
+
+
+def test_lindblad_rhs_equals_the_mul_call_pattern():
+    """test/test_sciml_broadcast_interfaces.jl:36-43: the six mul! calls of a master-equation step, through the oracle's own
+    mul (sparse H and J on a dense rho), equal the closed form; trace preserving and Hermiticity preserving."""
+    rng = np.random.default_rng(9)
+    nc = 6
+    nf = nc + 1
+    a, ad = O.destroy(nc).data, O.create(nc).data
+    sm, sp_ = O.sigmam().data, O.sigmap().data
+    i2, inf = sp.identity(2, format="csc"), sp.identity(nf, format="csc")
+    Hm = (sp.kron(i2, ad @ a) + 0.3 * (sp.kron(sp_, a) + sp.kron(sm, ad))).tocsc()
+    Jm = [np.sqrt(0.7) * sp.kron(i2, a).tocsc(), np.sqrt(0.2) * sp.kron(sm, inf).tocsc()]
+    D = 2 * nf
+    dims = (nf, 2)
+    x = H.rnd(rng, D, D)
+    rho = x @ x.conj().T
+    rho /= np.trace(rho)
+    ref = O.lindblad_rhs(Hm.toarray(), [j.toarray() for j in Jm], rho)
+    assert abs(np.trace(ref)) < 1e-13 and np.allclose(ref, ref.conj().T)
+    Ho = O.Op(dims, dims, Hm)
+    st = O.Op(dims, dims, np.asfortranarray(rho))
+    out = O.Op(dims, dims, np.zeros((D, D), dtype=complex, order="F"))
+    tmp = O.Op(dims, dims, np.zeros((D, D), dtype=complex, order="F"))
+    O.mul(out, Ho, st, -1j, 0.0)
+    O.mul(out, st, Ho, 1j, 1.0)
+    for j in Jm:
+        Jo, Jd = O.Op(dims, dims, j), O.Op(dims, dims, sp.csc_matrix(j.conj().T))
+        JdJ = O.Op(dims, dims, sp.csc_matrix(j.conj().T @ j))
+        O.mul(tmp, Jo, st, 1.0, 0.0)
+        O.mul(out, tmp, Jd, 1.0, 1.0)
+        O.mul(out, JdJ, st, -0.5, 1.0)
+        O.mul(out, st, JdJ, -0.5, 1.0)
+    assert H.rel_err(out.data, ref) <= 1e-13
