@@ -144,6 +144,17 @@ int qob_op_describe(qob_op *op, int32_t side, int64_t batch, char *buf, int64_t 
 int qob_profile_enable(int32_t on);
 int qob_profile_read(int32_t max_entries, float *ms, int32_t *pass_index, double *alg_bytes, int32_t *count);
 
+/* Fused master-equation right-hand side (no single reference function — the reference builds
+ * it from six mul! calls per step, test/test_sciml_broadcast_interfaces.jl:36-43):
+ *   drho = alpha * ( -i (H rho - rho H) + sum_k r_k ( J_k rho J_k^+ - 1/2 (J_k^+ J_k rho + rho J_k^+ J_k) ) ) + beta * drho
+ * H, J_k: square D x D factors (CSC as SparseOperator holds them, or dense); rates r_k >= 0 (NULL: all 1).
+ * rho, drho: device pointers to D x D ComplexF64, column-major; they must not alias.  alpha == 0 leaves only the beta update,
+ * beta == 0 never reads drho.  qob_lindblad_dense writes one of the assembled host matrices (0: H - i/2 sum r_k J_k^+ J_k,
+ * 1: H + i/2 sum r_k J_k^+ J_k, 2+k: sqrt(r_k) J_k) as a dense column-major D x D array (tests, introspection). */
+int qob_lindblad_create(qob_ctx *ctx, const qob_factor *H, int32_t nJ, const qob_factor *J, const double *rates, qob_op **out);
+int qob_lindblad_apply(qob_op *L, qob_c64 alpha, const void *rho, qob_c64 beta, void *drho, void *stream);
+int qob_lindblad_dense(qob_op *L, int32_t which, qob_c64 *out);
+
 /* Counter-based synthetic input generator shared with the oracle (oracle/qob_oracle.c:orc_fill_state):
  * x[i] = scale * (u(seed, 2i), u(seed, 2i+1)), u uniform in [-1, 1) from splitmix64. */
 int qob_fill_state(void *x, int64_t offset, int64_t n, uint64_t seed, double scale, void *stream);

@@ -92,6 +92,9 @@ _sigs = {
     "qob_lazysum_create": (C.c_int, [_vp, _i64, _i64, _i32, C.POINTER(c64), C.POINTER(_vp), C.POINTER(_vp)]),
     "qob_lazysum_set_coefs": (C.c_int, [_vp, _i32, C.POINTER(c64)]),
     "qob_lazyproduct_create": (C.c_int, [_vp, _i32, C.POINTER(_vp), c64, C.POINTER(_vp)]),
+    "qob_lindblad_create": (C.c_int, [_vp, C.POINTER(Factor), _i32, C.POINTER(Factor), C.POINTER(C.c_double), C.POINTER(_vp)]),
+    "qob_lindblad_apply": (C.c_int, [_vp, c64, _vp, c64, _vp, _vp]),
+    "qob_lindblad_dense": (C.c_int, [_vp, _i32, _vp]),
     "qob_op_destroy": (C.c_int, [_vp]),
     "qob_op_dims": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "qob_op_apply": (C.c_int, [_vp, _i32, c64, _vp, c64, _vp, _i64, _vp]),

@@ -185,7 +185,7 @@ void qob_ctx::clear_scratch() {
 static std::atomic<int> g_slot_counter{1000};
 
 // ============================================================================ operator handles
-enum OpKind { OP_LAZYTENSOR, OP_SPARSE, OP_DENSE, OP_LAZYSUM, OP_LAZYPRODUCT };
+enum OpKind { OP_LAZYTENSOR, OP_SPARSE, OP_DENSE, OP_LAZYSUM, OP_LAZYPRODUCT, OP_LINDBLAD };
 
 struct qob_op {
   qob_ctx *ctx;
@@ -860,6 +860,161 @@ int qob_dense_create(qob_ctx *ctx, const qob_factor *f, qob_op **out) {
   QOB_TRY(qob_lazytensor_create(ctx, 1, &dl, &dr, 1, &site, f, one, &o));
   o->kind = OP_DENSE;
   *out = o;
+  return QOB_STATUS_OK;
+}
+
+// ---------------------------------------------------------------------------- fused master-equation right-hand side
+// (kernel in qob_kernels_lindblad.cu).  Host side: Heff = H - i/2 sum_k r_k J_k^+ J_k by rows,
+// G = H + i/2 sum_k r_k J_k^+ J_k by columns, sqrt(r_k) J_k by rows.
+typedef std::map<std::pair<int64_t, int64_t>, cplx> Coo;   // ordered by (first, second)
+static void coo_add(Coo &c, const HostMat &m, cplx scale, bool key_by_column) {
+  auto put = [&](int64_t r, int64_t col, cplx v) { c[key_by_column ? std::make_pair(col, r) : std::make_pair(r, col)] += scale * v; };
+  if (m.kind == QOB_FACTOR_CSC) {
+    for (int64_t col = 0; col < m.cols; ++col)
+      for (int64_t p = m.colptr[col]; p < m.colptr[col + 1]; ++p) put(m.rowidx[p], col, m.vals[p]);
+  } else if (m.kind == QOB_FACTOR_DENSE) {
+    for (int64_t col = 0; col < m.cols; ++col)
+      for (int64_t r = 0; r < m.rows; ++r) {
+        const cplx v = m.dense[(size_t)(r + col * m.rows)];
+        if (v != ZERO) put(r, col, v);
+      }
+  } else {
+    for (int64_t i = 0; i < std::min(m.rows, m.cols); ++i) put(i, i, ONE);
+  }
+}
+static void coo_compress(const Coo &c, int64_t n, std::vector<int32_t> &ptr, std::vector<int32_t> &idx, std::vector<cplx> &val) {
+  ptr.assign((size_t)n + 1, 0);
+  idx.clear();
+  val.clear();
+  for (const auto &kv : c) {
+    ++ptr[(size_t)kv.first.first + 1];
+    idx.push_back((int32_t)kv.first.second);
+    val.push_back(kv.second);
+  }
+  for (int64_t i = 0; i < n; ++i) ptr[(size_t)i + 1] += ptr[(size_t)i];
+}
+
+struct LindbladOp : qob_op {
+  LindbladDev dev;
+  // host copies (introspection / tests)
+  std::vector<int32_t> h_ptr, h_col, g_ptr, g_row, j_ptr, j_col;
+  std::vector<cplx> h_val, g_val, j_val;
+  int nJ = 0;
+  LindbladOp(qob_ctx *c) : qob_op(c, OP_LINDBLAD) {}
+  int apply(int, cplx, const void *, cplx, void *, int64_t, cudaStream_t) override {
+    QOB_FAIL(QOB_STATUS_UNSUPPORTED, "a Lindblad right-hand side is applied with qob_lindblad_apply");
+  }
+  std::string describe(int, int64_t) override {
+    return "lindblad " + std::to_string(dl) + "x" + std::to_string(dl) + " Heff nnz=" + std::to_string(h_val.size()) + " jumps=" +
+           std::to_string(nJ) + " (nnz=" + std::to_string(j_val.size()) + ") fused{one kernel, one output element per thread}";
+  }
+};
+
+int qob_lindblad_create(qob_ctx *ctx, const qob_factor *H, int32_t nJ, const qob_factor *J, const double *rates, qob_op **out) {
+  if (!ctx || !H || !out || nJ < 0 || (nJ > 0 && !J)) QOB_FAIL(QOB_STATUS_INVALID_ARG, "bad Lindblad arguments");
+  PlanningScope ps(ctx->device < 0);
+  auto op = std::make_unique<LindbladOp>(ctx);
+  HostMat h;
+  QOB_TRY(hostmat_from_factor(H, h));
+  if (h.rows != h.cols) QOB_FAIL(QOB_STATUS_DIM_MISMATCH, "the Hamiltonian must be square, got %lldx%lld", (long long)h.rows, (long long)h.cols);
+  const int64_t D = h.rows;
+  if (D > 0x7FFFFFF0ll) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "dimension too large");
+  op->dl = op->dr = D;
+  op->nJ = nJ;
+  Coo jdj;   // sum_k r_k J_k^+ J_k, keyed (row, col)
+  op->j_ptr.assign((size_t)nJ * (size_t)(D + 1), 0);
+  for (int k = 0; k < nJ; ++k) {
+    HostMat jm;
+    QOB_TRY(hostmat_from_factor(&J[k], jm));
+    if (jm.rows != D || jm.cols != D)
+      QOB_FAIL(QOB_STATUS_DIM_MISMATCH, "jump operator %d is %lldx%lld, expected %lldx%lld", k + 1, (long long)jm.rows, (long long)jm.cols,
+               (long long)D, (long long)D);
+    const double r = rates ? rates[k] : 1.0;
+    if (!(r >= 0.0)) QOB_FAIL(QOB_STATUS_INVALID_ARG, "rate %d must be >= 0", k + 1);
+    Coo jk;
+    coo_add(jk, jm, cplx(std::sqrt(r), 0.0), false);
+    std::vector<int32_t> ptr, col;
+    std::vector<cplx> val;
+    coo_compress(jk, D, ptr, col, val);
+    const int32_t base = (int32_t)op->j_col.size();
+    if ((size_t)base + col.size() > 0x7FFFFFF0ull) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "too many nonzeros in the jump operators");
+    for (int64_t i = 0; i <= D; ++i) op->j_ptr[(size_t)k * (size_t)(D + 1) + (size_t)i] = base + ptr[(size_t)i];
+    op->j_col.insert(op->j_col.end(), col.begin(), col.end());
+    op->j_val.insert(op->j_val.end(), val.begin(), val.end());
+    // (J^+ J)[a, b] = sum_r conj(J[r, a]) J[r, b]: pairs of entries of every row (the sqrt(r) factors multiply to r)
+    for (int64_t row = 0; row < D; ++row)
+      for (int32_t p = ptr[(size_t)row]; p < ptr[(size_t)row + 1]; ++p)
+        for (int32_t q = ptr[(size_t)row]; q < ptr[(size_t)row + 1]; ++q)
+          jdj[std::make_pair((int64_t)col[(size_t)p], (int64_t)col[(size_t)q])] += std::conj(val[(size_t)p]) * val[(size_t)q];
+  }
+  Coo heff, g;   // Heff by rows: key (row, col); G by columns: key (col, row)
+  coo_add(heff, h, ONE, false);
+  coo_add(g, h, ONE, true);
+  for (const auto &kv : jdj) {
+    heff[kv.first] += cplx(0.0, -0.5) * kv.second;
+    g[std::make_pair(kv.first.second, kv.first.first)] += cplx(0.0, 0.5) * kv.second;
+  }
+  coo_compress(heff, D, op->h_ptr, op->h_col, op->h_val);
+  coo_compress(g, D, op->g_ptr, op->g_row, op->g_val);
+  auto up_i = [](DevArray<int32_t> &d, std::vector<int32_t> v) {
+    if (v.empty()) v.push_back(0);
+    return d.upload(v);
+  };
+  auto up_v = [](DevArray<double2> &d, const std::vector<cplx> &v) {
+    std::vector<double2> t(std::max<size_t>(1, v.size()), make_double2(0.0, 0.0));
+    for (size_t i = 0; i < v.size(); ++i) t[i] = make_double2(v[i].real(), v[i].imag());
+    return d.upload(t);
+  };
+  op->dev.D = D;
+  op->dev.nJ = nJ;
+  QOB_TRY(up_i(op->dev.h_ptr, op->h_ptr));
+  QOB_TRY(up_i(op->dev.h_col, op->h_col));
+  QOB_TRY(up_v(op->dev.h_val, op->h_val));
+  QOB_TRY(up_i(op->dev.g_ptr, op->g_ptr));
+  QOB_TRY(up_i(op->dev.g_row, op->g_row));
+  QOB_TRY(up_v(op->dev.g_val, op->g_val));
+  QOB_TRY(up_i(op->dev.j_ptr, op->j_ptr));
+  QOB_TRY(up_i(op->dev.j_col, op->j_col));
+  QOB_TRY(up_v(op->dev.j_val, op->j_val));
+  *out = op.release();
+  return QOB_STATUS_OK;
+}
+
+int qob_lindblad_apply(qob_op *L, qob_c64 alpha, const void *rho, qob_c64 beta, void *drho, void *stream) {
+  if (!L || L->kind != OP_LINDBLAD) QOB_FAIL(QOB_STATUS_INVALID_ARG, "not a Lindblad handle");
+  LindbladOp *op = static_cast<LindbladOp *>(L);
+  const int64_t n = op->dl * op->dl;
+  if (n == 0) return QOB_STATUS_OK;
+  if (!rho || !drho) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null data pointer");
+  QOB_TRY(check_alias(rho, n, drho, n));
+  if (op->ctx->device < 0) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
+  QOB_CUDA(cudaSetDevice(op->ctx->device));
+  if (C(alpha) == ZERO) return launch_scale(drho, n, C(beta), (cudaStream_t)stream);   // only the beta update, like mul!
+  return launch_lindblad(op->dev, C(alpha), rho, C(beta), drho, (cudaStream_t)stream);
+}
+
+int qob_lindblad_dense(qob_op *L, int32_t which, qob_c64 *out) {
+  if (!L || L->kind != OP_LINDBLAD || !out) QOB_FAIL(QOB_STATUS_INVALID_ARG, "not a Lindblad handle");
+  LindbladOp *op = static_cast<LindbladOp *>(L);
+  const int64_t D = op->dl;
+  if (which < 0 || which > 1 + op->nJ) QOB_FAIL(QOB_STATUS_INVALID_ARG, "matrix index out of range");
+  for (int64_t i = 0; i < D * D; ++i) out[i].re = out[i].im = 0.0;
+  auto put = [&](int64_t r, int64_t c, cplx v) {
+    out[r + c * D].re += v.real();
+    out[r + c * D].im += v.imag();
+  };
+  if (which == 0) {
+    for (int64_t r = 0; r < D; ++r)
+      for (int32_t p = op->h_ptr[(size_t)r]; p < op->h_ptr[(size_t)r + 1]; ++p) put(r, op->h_col[(size_t)p], op->h_val[(size_t)p]);
+  } else if (which == 1) {
+    for (int64_t c = 0; c < D; ++c)
+      for (int32_t p = op->g_ptr[(size_t)c]; p < op->g_ptr[(size_t)c + 1]; ++p) put(op->g_row[(size_t)p], c, op->g_val[(size_t)p]);
+  } else {
+    const size_t k = (size_t)(which - 2);
+    for (int64_t r = 0; r < D; ++r)
+      for (int32_t p = op->j_ptr[k * (size_t)(D + 1) + (size_t)r]; p < op->j_ptr[k * (size_t)(D + 1) + (size_t)r + 1]; ++p)
+        put(r, op->j_col[(size_t)p], op->j_val[(size_t)p]);
+  }
   return QOB_STATUS_OK;
 }
 

@@ -142,6 +142,17 @@ int launch_spmm_left(const SparseDev &csr, int64_t m, int64_t k, int64_t n, cplx
 int launch_spmm_right(const SparseDev &csc, int64_t q, int64_t m, int64_t n, cplx alpha, const void *B, cplx beta,
                       void *R, cudaStream_t s);
 
+// Fused master-equation right-hand side (qob_kernels_lindblad.cu): Heff = H - i/2 sum_k J_k^+ J_k as CSR rows,
+// G = H + i/2 sum_k J_k^+ J_k by columns (CSC), the jump operators (times sqrt(rate)) as CSR rows sharing one index / value
+// array, row pointers of operator k at k*(D+1).
+struct LindbladDev {
+  int64_t D = 0;
+  int nJ = 0;
+  DevArray<int32_t> h_ptr, h_col, g_ptr, g_row, j_ptr, j_col;
+  DevArray<double2> h_val, g_val, j_val;
+};
+int launch_lindblad(const LindbladDev &L, cplx alpha, const void *rho, cplx beta, void *drho, cudaStream_t s);
+
 // Generic fused gather program --------------------------------------------------------------
 struct GatherProgram {
   // host description

@@ -546,6 +546,73 @@ def _refresh_coefs(op: LazySum):
             _refresh_coefs(o)
 
 
+class LindbladRHS:
+    """Fused master-equation right-hand side on a dense device rho:
+
+        drho = alpha * ( -i (H rho - rho H) + sum_k r_k ( J_k rho J_k^+ - (J_k^+ J_k rho + rho J_k^+ J_k) / 2 ) ) + beta * drho
+
+    i.e. what the six-mul!-per-jump call pattern of test/test_sciml_broadcast_interfaces.jl:36-43 computes, in ONE kernel
+    (`qob_lindblad_create` / `qob_lindblad_apply`).  H and the J_k are `Operator`s with sparse or host-dense data on the same
+    basis; `rates` are non-negative reals (default 1)."""
+
+    def __init__(self, H, J=(), rates=None, ctx=None):
+        J = list(J)
+        for o in [H] + J:
+            if not isinstance(o, Operator) or o.is_device_dense:
+                raise MethodError("LindbladRHS needs Operators with sparse or host-dense data")
+            if not (o.basis_l == H.basis_l and o.basis_r == H.basis_r):
+                raise IncompatibleBases("LindbladRHS: H and the jump operators must share their bases")
+        if not (H.basis_l == H.basis_r):
+            raise IncompatibleBases("LindbladRHS: the Hamiltonian must map a basis to itself")
+        if rates is not None and len(rates) != len(J):
+            raise ArgumentError("LindbladRHS: one rate per jump operator")
+        self.H, self.J, self.rates = H, J, None if rates is None else [float(r) for r in rates]
+        self.basis_l = self.basis_r = H.basis_l
+        ctx = _lib.context() if ctx is None else ctx
+        keep = []
+        hf = _factor_struct(H.data, keep)
+        n = len(J)
+        jf = (_lib.Factor * max(n, 1))()
+        for k, o in enumerate(J):
+            jf[k] = _factor_struct(o.data, keep)
+        rt = None if self.rates is None else (C.c_double * max(n, 1))(*self.rates)
+        h = C.c_void_p()
+        _lib.check(lib.qob_lindblad_create(ctx, C.byref(hf), n, jf, rt, C.byref(h)))
+        self._handle, self._handle_ctx = h, ctx
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                lib.qob_op_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    def apply_(self, drho, rho, alpha=1.0, beta=0.0):
+        """drho <- alpha * L(rho) + beta * drho; both are dense device Operators on the Hamiltonian's basis."""
+        for o in (drho, rho):
+            if not isinstance(o, Operator) or not o.is_device_dense:
+                raise MethodError("LindbladRHS.apply_ needs dense device Operators")
+            if not (o.basis_l == self.basis_l and o.basis_r == self.basis_r):
+                raise IncompatibleBases("LindbladRHS.apply_: rho and drho must live on the Hamiltonian's basis")
+        _lib.check(lib.qob_lindblad_apply(self._handle, c64.of(alpha), C.c_void_p(rho.data.data_ptr()), c64.of(beta),
+                                          C.c_void_p(drho.data.data_ptr()), _stream()))
+        return drho
+
+    def assembled(self, which):
+        """host matrices the kernel works from: 0: H - i/2 sum r_k J_k^+ J_k, 1: H + i/2 sum r_k J_k^+ J_k, 2+k: sqrt(r_k) J_k"""
+        D = len(self.basis_l)
+        out = np.zeros((D, D), dtype=C128, order="F")
+        _lib.check(lib.qob_lindblad_dense(self._handle, int(which), C.c_void_p(out.ctypes.data)))
+        return out
+
+    def describe(self):
+        buf = C.create_string_buffer(1 << 12)
+        _lib.check(lib.qob_op_describe(self._handle, _lib.SIDE_LEFT, 1, buf, len(buf)))
+        return buf.value.decode()
+
+
 def describe(op, side="left", batch=1, ctx=None):
     """Text description of the device plan chosen for `op` (kernels, passes, tiles)."""
     buf = C.create_string_buffer(1 << 16)

@@ -307,3 +307,46 @@ def test_mixed_radix_planner_fuzz_accounts_for_every_term(Q, monkeypatch):
         seen_dtile += "dtile[" in d
         seen_gather += "gather[" in d
     assert seen_dtile >= 100 and seen_gather >= 5, (seen_dtile, seen_gather)
+
+
+def test_lindblad_host_assembly(Q):
+    """Planning only: the matrices the fused master-equation kernel works from — Heff = H - i/2 sum r_k J_k^+ J_k (by rows),
+    G = H + i/2 sum r_k J_k^+ J_k (by columns), sqrt(r_k) J_k — against numpy, for a NON-Hermitian H, sparse and host-dense
+    jump operators; the closed form -i(Heff rho - rho G) + sum J rho J^+ equals the reference's call pattern."""
+    import numpy as np
+    import scipy.sparse as sp
+
+    from oracle import qob_oracle as O
+
+    ctx = Q.context(-1)
+    rng = np.random.default_rng(12)
+    D = 23
+    bas = Q.GenericBasis(D)
+
+    def sprand(density):
+        m = sp.random(D, D, density=density, random_state=np.random.RandomState(int(rng.integers(1 << 30))), format="csc").astype(complex)
+        m.data = rng.standard_normal(m.nnz) + 1j * rng.standard_normal(m.nnz)
+        return m
+
+    Hm, J1, J2 = sprand(0.15), sprand(0.1), sprand(0.08)
+    J3 = (rng.standard_normal((D, D)) + 1j * rng.standard_normal((D, D))) * (rng.uniform(0, 1, (D, D)) < 0.1)
+    rates = [0.7, 0.0, 2.5]
+    L = Q.LindbladRHS(Q.Operator(bas, bas, Hm), [Q.Operator(bas, bas, j) for j in (J1, J2, J3)], rates, ctx=ctx)
+    Jd = [J1.toarray(), J2.toarray(), J3]
+    JdJ = sum(r * (j.conj().T @ j) for r, j in zip(rates, Jd))
+    Hd = Hm.toarray()
+    assert np.abs(L.assembled(0) - (Hd - 0.5j * JdJ)).max() <= 1e-13
+    assert np.abs(L.assembled(1) - (Hd + 0.5j * JdJ)).max() <= 1e-13
+    for k in range(3):
+        assert np.abs(L.assembled(2 + k) - np.sqrt(rates[k]) * Jd[k]).max() <= 1e-14
+    rho = rng.standard_normal((D, D)) + 1j * rng.standard_normal((D, D))
+    closed = -1j * (L.assembled(0) @ rho - rho @ L.assembled(1)) + sum(L.assembled(2 + k) @ rho @ L.assembled(2 + k).conj().T for k in range(3))
+    assert np.abs(closed - O.lindblad_rhs(Hd, Jd, rho, rates)).max() <= 1e-12
+    assert "lindblad 23x23" in L.describe() and "jumps=3" in L.describe()
+    # errors: non-square H, mismatched jump operator, negative rate; no GPU -> apply refuses (no CPU fallback)
+    with pytest.raises(Q.IncompatibleBases):
+        Q.LindbladRHS(Q.Operator(bas, Q.GenericBasis(D + 1), sp.csc_matrix((D, D + 1), dtype=complex)), ctx=ctx)
+    with pytest.raises(Q.ArgumentError):
+        Q.LindbladRHS(Q.Operator(bas, bas, Hm), [Q.Operator(bas, bas, J1)], [-0.1], ctx=ctx)
+    st = Q.lib.qob_lindblad_apply(L._handle, Q._lib.c64.of(1), ctypes.c_void_p(4096), Q._lib.c64.of(0), ctypes.c_void_p(1 << 40), None)
+    assert st == 5 and b"no CPU fallback" in Q.lib.qob_last_error()
