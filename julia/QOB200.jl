@@ -211,4 +211,33 @@ mul!(result::Ket{B1,<:DevVec}, M::HostSparseOrDense{B1,B2}, b::Ket{B2,<:DevVec},
 mul!(result::Bra{B2,<:DevVec}, b::Bra{B1,<:DevVec}, M::HostSparseOrDense{B1,B2}, alpha, beta) where {B1,B2} =
     (apply!(result.data, M, SIDE_RIGHT, b.data, alpha, beta, 1); result)
 
+# ---- fused master-equation right-hand side (include/qob200.h: qob_lindblad_*; no single reference function — it replaces the
+# mul! sequence of test/test_sciml_broadcast_interfaces.jl:36-43 / QuantumOptics.jl's dmaster_h!)
+struct LindbladRHS
+    handle::Handle
+    keep::Vector{Any}
+end
+function LindbladRHS(H::HostSparseOrDense{B,B}, J::Vector; rates=nothing) where B
+    keep = Any[]
+    fH = factor(H.data); push!(keep, H.data)
+    fJ = QobFactor[]
+    for j in J
+        push!(fJ, factor(j.data)); push!(keep, j.data)
+    end
+    r = rates === nothing ? C_NULL : convert(Vector{Float64}, rates)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep fJ r begin
+        check(ccall((:qob_lindblad_create, libqob200), Cint,
+                    (Ptr{Cvoid}, Ref{QobFactor}, Int32, Ptr{QobFactor}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                    context(), Ref(fH), Int32(length(fJ)), fJ, r, h))
+    end
+    LindbladRHS(Handle(h[]), keep)
+end
+"drho = alpha * L(rho) + beta * drho on device-resident dense operators"
+function apply!(drho::DevOp{B,B}, L::LindbladRHS, rho::DevOp{B,B}, alpha=true, beta=false) where B
+    check(ccall((:qob_lindblad_apply, libqob200), Cint, (Ptr{Cvoid}, C64, CuPtr{Cvoid}, C64, CuPtr{Cvoid}, Ptr{Cvoid}),
+                L.handle.ptr, C64(alpha), pointer(rho.data), C64(beta), pointer(drho.data), CUDA.stream().handle))
+    drho
+end
+
 end # module
