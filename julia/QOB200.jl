@@ -219,10 +219,11 @@ struct LindbladRHS
 end
 function LindbladRHS(H::HostSparseOrDense{B,B}, J::Vector; rates=nothing) where B
     keep = Any[]
-    fH = factor(H.data); push!(keep, H.data)
+    fH, kH = factor(H.data); push!(keep, kH)
     fJ = QobFactor[]
     for j in J
-        push!(fJ, factor(j.data)); push!(keep, j.data)
+        f, k = factor(j.data)
+        push!(fJ, f); push!(keep, k)
     end
     r = rates === nothing ? C_NULL : convert(Vector{Float64}, rates)
     h = Ref{Ptr{Cvoid}}(C_NULL)
