@@ -273,6 +273,8 @@ struct TensorGroup {
   std::vector<std::unique_ptr<Compiled>> cache;
   std::vector<cplx> last_coefs;  // coefficients the cached programs were last loaded with
   bool coefs_dirty = true;
+  std::recursive_mutex mu;       // guards the compiled-program cache and the coefficient upload: handles may be applied
+                                 // from several host threads (the reference is reentrant per task, operators_lazytensor.jl:233)
 
   int compile(int side, int64_t batch, Compiled **out);
   int apply(int side, cplx alpha, const void *x, cplx beta, void *y, int64_t batch, const std::vector<cplx> &coefs,
@@ -282,6 +284,7 @@ struct TensorGroup {
 static const int GATHER_MAXF = 4;
 
 int TensorGroup::compile(int side, int64_t batch, Compiled **out) {
+  std::lock_guard<std::recursive_mutex> lk(mu);
   for (auto &c : cache)
     if (c->side == side && c->batch == batch) {
       *out = c.get();
@@ -481,6 +484,7 @@ int TensorGroup::apply(int side, cplx alpha, const void *x, cplx beta, void *y, 
   Compiled *cp = nullptr;
   QOB_TRY(compile(side, batch, &cp));
   Compiled &c = *cp;
+  std::unique_lock<std::recursive_mutex> lk(mu);
   if (coefs_dirty || coefs != last_coefs) {
     for (auto &cc : cache) {
       if (cc->has_qtile) QOB_TRY(qtile_set_coefs(cc->qtile, coefs, s));
@@ -490,6 +494,7 @@ int TensorGroup::apply(int side, cplx alpha, const void *x, cplx beta, void *y, 
     last_coefs = coefs;
     coefs_dirty = false;
   }
+  lk.unlock();
   const int64_t pre = side == QOB_SIDE_LEFT ? 1 : batch, post = side == QOB_SIDE_LEFT ? batch : 1;
   bool first = true;
   auto beta_now = [&]() {
