@@ -257,8 +257,9 @@ struct Compiled {
   int64_t batch;
   std::vector<int64_t> dims_out, dims_in;
   int64_t d_out = 1, d_in = 1;
-  bool has_qtile = false, has_gather = false, has_dtile = false;
+  bool has_qtile = false, has_gather = false, has_dtile = false, has_qreg = false;
   QTileProgram qtile;
+  QRegProgram qreg;
   DTileProgram dtile;
   GatherProgram gather;
   std::vector<std::unique_ptr<SeqTerm>> seq;
@@ -307,7 +308,7 @@ int TensorGroup::compile(int side, int64_t batch, Compiled **out) {
     all_same &= c.dims_out[k] == c.dims_in[k];
   }
   const int dense_min = env_i("QOB_AXIS_MIN_DIM", 16);
-  const int qt_min_bits = env_i("QOB_QTILE_MIN_BITS", 18);
+  const int qt_min_bits = std::min(env_i("QOB_QTILE_MIN_BITS", 18), env_i("QOB_QREG_MIN_BITS", 20));
   const bool qt_batch_ok = is_pow2(batch);
   const int nbits = n + (qt_batch_ok ? ilog2(batch) : 0);
   const bool qt_ok = all2 && qt_batch_ok && nbits >= qt_min_bits && nbits <= 62 && !env_i("QOB_DISABLE_QTILE", 0);
@@ -400,7 +401,13 @@ int TensorGroup::compile(int side, int64_t batch, Compiled **out) {
       gterms.push_back(std::move(o));
     }
   }
-  if (!qterms.empty()) {
+  if (!qterms.empty() && nbits >= env_i("QOB_QREG_MIN_BITS", 20) && !env_i("QOB_DISABLE_QREG", 0)) {
+    // large states: register-blocked tile passes staged by TMA, pairs of passes chained through L2 (qob_kernels_qreg.cu)
+    const int st = qreg_build(c.qreg, nbits, 0, qterms, ctx->sm_count);
+    if (st == QOB_STATUS_OK) c.has_qreg = true;
+    else if (st != QOB_STATUS_UNSUPPORTED) return st;
+  }
+  if (!qterms.empty() && !c.has_qreg) {
     const int st = qtile_build(c.qtile, nbits, 0, qterms, ctx->sm_count);
     if (st == QOB_STATUS_UNSUPPORTED) {
       // the tile planner declined (selector bits too scattered, too many shared-mask lookups, ...): the generic fused
@@ -464,6 +471,7 @@ int TensorGroup::compile(int side, int64_t batch, Compiled **out) {
     c.has_gather = true;
   }
   c.text = std::string(side == QOB_SIDE_LEFT ? "left" : "right") + " batch=" + std::to_string(batch) + ":";
+  if (c.has_qreg) c.text += " " + c.qreg.describe;
   if (c.has_qtile) c.text += " " + c.qtile.describe;
   if (c.has_dtile) c.text += " " + c.dtile.describe;
   if (c.has_gather) c.text += " " + c.gather.describe;
@@ -487,6 +495,7 @@ int TensorGroup::apply(int side, cplx alpha, const void *x, cplx beta, void *y, 
   std::unique_lock<std::recursive_mutex> lk(mu);
   if (coefs_dirty || coefs != last_coefs) {
     for (auto &cc : cache) {
+      if (cc->has_qreg) QOB_TRY(qreg_set_coefs(cc->qreg, coefs, s));
       if (cc->has_qtile) QOB_TRY(qtile_set_coefs(cc->qtile, coefs, s));
       if (cc->has_dtile) QOB_TRY(dtile_set_coefs(cc->dtile, coefs, s));
       if (cc->has_gather) QOB_TRY(gather_program_set_coefs(cc->gather, coefs, s));
@@ -502,6 +511,7 @@ int TensorGroup::apply(int side, cplx alpha, const void *x, cplx beta, void *y, 
     first = false;
     return b;
   };
+  if (c.has_qreg) QOB_TRY(qreg_launch(c.qreg, alpha, x, beta_now(), y, s));
   if (c.has_qtile) QOB_TRY(qtile_launch(c.qtile, alpha, x, beta_now(), y, s));
   if (c.has_dtile) QOB_TRY(dtile_launch(c.dtile, alpha, x, beta_now(), y, s));
   if (c.has_gather) QOB_TRY(gather_program_launch(c.gather, pre, post, alpha, x, beta_now(), y, s));

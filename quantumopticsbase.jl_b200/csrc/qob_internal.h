@@ -214,6 +214,23 @@ int qtile_set_chunk_bits(QTileProgram &p, uint64_t chunk_mask);
 int qtile_launch(const QTileProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s,
                  const QLaunchOpts *opts = nullptr);
 
+// Register-blocked, TMA-staged, L2-chained tile program (qob_kernels_qreg.cu): the single-GPU path for >= 2^20 amplitudes
+struct QRegProgramHost;
+struct QRegProgram {
+  std::shared_ptr<QRegProgramHost> h;
+  std::string describe;
+  int npasses = 0;
+};
+// Returns QOB_STATUS_UNSUPPORTED when the terms do not fit the scheme (the caller then uses the qtile kernel).
+int qreg_build(QRegProgram &p, int nbits, uint64_t hi_value, const std::vector<QTerm> &terms, int sm_count);
+int qreg_set_coefs(QRegProgram &p, const std::vector<cplx> &coefs, cudaStream_t s);
+int qreg_launch(const QRegProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s);
+
+// per-launch event timing of the tile kernels (qob_profile_enable / qob_profile_read); thread safe
+bool qprof_enabled();
+void *qprof_begin(cudaStream_t s, int pass, double alg_bytes);
+void qprof_end(cudaStream_t s, void *token);
+
 // Mixed-radix tile program (any subsystem dimensions, large states) --------------------------
 struct DTileProgramHost;
 struct DTileProgram {

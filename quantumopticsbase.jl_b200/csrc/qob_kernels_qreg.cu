@@ -1,0 +1,1331 @@
+// qob_kernels_qreg.cu — round-2 kernel of the fused LazySum apply on 2-dimensional subsystems (BASELINE configs 4, 5):
+// register-blocked tile passes, staged by tensor-map TMA, with pairs of passes chained through L2.
+//
+// Reference behaviour replaced: one full pass over the state per TERM, src/operators_lazysum.jl:189-200 calling the scalar
+// recursion src/operators_lazytensor.jl:652-685.  As in qob_kernels_qtile.cu the sum is regrouped by flip mask,
+//     (H x)[i] = sum_c w_c(bits of i) * x[i XOR mask_c],
+// and a pass applies every component whose mask fits the 12 free index bits of its 4096-amplitude tile.  What is new:
+//
+//  * ONE persistent, warp-specialised CTA per SM.  A producer thread walks an ordered tile queue and stages tiles with
+//    cp.async.bulk.tensor (SASS UTMALDG): one instruction per 64 KiB tile, whatever its shape — the contiguous low block
+//    and the window of high bits are box dimensions of a tensor map over the state.  y of a read-modify-write pass is
+//    staged the same way, so neither x nor y costs the LSU any global-load wavefronts (ncu, round 1: the LSU data pipe
+//    was the limiter at 88-90 %).
+//  * Each of the 256 consumer threads owns 16 amplitudes = 4 index bits ("R bits") and keeps x and the accumulators in
+//    registers.  A bond whose mask lies inside the R bits costs no shared-memory access at all; weights that depend on
+//    R bits are hoisted into <= 4 registers per (component, tile); the others cost one LDS.128 gather per amplitude.
+//  * Two passes whose free bits span <= 20 index bits are CHAINED: the tile queue runs chunk by chunk (a chunk = all
+//    amplitudes that share the index bits outside the union, <= 16 MiB of x), pass-2 tiles of chunk c queued one chunk
+//    behind pass-1 tiles and released by a per-chunk counter, so pass 2 finds x and y of its chunk in the 126 MB L2.
+//    Heisenberg N=28: 3 tile passes but 80 B/amplitude of DRAM traffic instead of 128 (tools/ubench_l2.cu measures the
+//    mechanism in isolation: 3.12 -> 2.12 ms for a 2-pass sweep of 2^28 amplitudes).
+//
+// Index bits: bit b of the flat (column-major) index <-> subsystem b+1 (src/states.jl:105).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "qob_internal.h"
+
+#define QR_T 12
+#define QR_TILE (1 << QR_T)
+#define QR_TILE_BYTES (QR_TILE * 16)
+#define QR_CTHREADS 256                 // consumer threads (8 warps), 16 amplitudes each
+#define QR_THREADS (QR_CTHREADS + 32)   // + one producer warp
+#define QR_MAXC 40                      // lookup records per pass (kernel parameter space)
+#define QR_MAXSEG 8
+#define QR_DIAG_WINDOW 6
+
+// classes of lookup records; records of a pass are sorted by class
+enum { QR_PRE = 0, QR_DIAGR = 1, QR_INREG = 2, QR_GATHER = 3, QR_GATHER_SLOW = 4 };
+
+struct QRComp {       // 80 bytes
+  uint32_t kind;      // class | SELR << 4 | M << 8   (SELR: which of the 4 R bits select the weight; M: flip mask inside R)
+  uint32_t tabE;      // first entry of the weight table inside the pass table
+  uint32_t sel;       // bit-field runs (<= 3) of the selector bits OUTSIDE R in the flat index: 9 bits each: shift (6) | width (3)
+  uint32_t xorT;      // gather: XOR applied to the thread's byte offset inside the tile (mask bits on thread positions)
+  uint32_t goff[16];  // gather: byte offset of the R part of the partner of amplitude u (= uoffB[u ^ M])
+};
+
+struct QRPass {
+  uint32_t uoffB[16];             // byte offset inside the staged tile of amplitude u of a thread
+  unsigned long long ugoff[16];   // element offset in global memory of amplitude u of a thread
+  unsigned char tpos[8];          // consumer-thread bit b -> tile-local bit position
+  unsigned char tgbit[8];         // consumer-thread bit b -> flat-index bit
+  int nfixed_seg;                 // compact tile id -> element offset of the tile
+  unsigned char xs_l[QR_MAXSEG], xs_n[QR_MAXSEG], xs_g[QR_MAXSEG];
+  int rank;                       // tensor-map rank; coordinate d = ((tile >> tshift) & (2^tbits - 1)) << boxlog
+  unsigned char dim_tshift[5], dim_tbits[5], dim_boxlog[5];
+  int n_pre, n_diagr, n_inreg, n_gather;  // records: [pre | diagR | in-register | gather]
+  unsigned long long hi_or;       // index bits above the local address (rank of a sharded state), already shifted
+  uint32_t tab_smem_off;          // byte offset of this pass's tables inside the shared-memory table area
+  uint32_t tab_bytes;
+  const unsigned char *tab;       // device copy of the tables
+  int mode;                       // 0: y = a*acc ; 1: y = a*acc + beta*y ; 2: y = a*acc + y
+  int signal;                     // 1: count finished tiles per chunk (first pass of a chained pair)
+  int wait;                       // 1: tiles wait for their chunk's counter (second pass of a chained pair)
+  int stream_out;                 // 1: last use of x and y in this launch: L2 evict_first on loads and stores
+  // chained launches: compact tile id = deposit(chunk id, cs_*) | deposit(tile within chunk, js_*)
+  int ncs, njs;
+  unsigned char cs_l[4], cs_n[4], cs_d[4], js_l[4], js_n[4], js_d[4];
+  QRComp comps[QR_MAXC];
+};
+
+struct QRLaunch {
+  int npass;             // 1, or 2 chained passes
+  unsigned tpc_log2;     // log2(tiles per chunk and pass)
+  unsigned nchunks, lag; // chunks; pass 2 runs `lag` chunks behind pass 1
+  unsigned total_items;
+  unsigned *queue;       // work counter
+  unsigned *done;        // per chunk: finished pass-1 tiles
+  double2 alpha, beta;
+  QRPass pass[2];
+};
+
+// ------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ unsigned qr_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void qr_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void qr_mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void qr_mbar_expect(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void qr_mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void qr_tma_load(unsigned dst, const CUtensorMap *map, unsigned bar, int rank, const int *c,
+                                            unsigned long long pol) {
+  const unsigned long long m = (unsigned long long)map;
+  switch (rank) {
+    case 1:
+      asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3}], [%2], %4;\n" ::"r"(dst),
+                   "l"(m), "r"(bar), "r"(c[0]), "l"(pol)
+                   : "memory");
+      break;
+    case 2:
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(dst),
+                   "l"(m), "r"(bar), "r"(c[0]), "r"(c[1]), "l"(pol)
+                   : "memory");
+      break;
+    case 3:
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;\n" ::"r"(dst),
+                   "l"(m), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "l"(pol)
+                   : "memory");
+      break;
+    case 4:
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n" ::"r"(dst),
+                   "l"(m), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "l"(pol)
+                   : "memory");
+      break;
+    default:
+      asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;\n" ::"r"(dst),
+                   "l"(m), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "l"(pol)
+                   : "memory");
+      break;
+  }
+}
+
+__host__ __device__ constexpr int qr_popc(int v) { return (v & 1) + ((v >> 1) & 1) + ((v >> 2) & 1) + ((v >> 3) & 1); }
+__host__ __device__ constexpr int qr_pext(int u, int sel) {
+  int r = 0, k = 0;
+  for (int b = 0; b < 4; ++b)
+    if ((sel >> b) & 1) {
+      r |= ((u >> b) & 1) << k;
+      ++k;
+    }
+  return r;
+}
+
+__device__ __forceinline__ unsigned long long qr_expand(unsigned v, int nseg, const unsigned char *sl, const unsigned char *sn,
+                                                        const unsigned char *sg) {
+  unsigned long long a = 0;
+#pragma unroll
+  for (int s = 0; s < QR_MAXSEG; ++s)
+    if (s < nseg) a |= (unsigned long long)((v >> sl[s]) & ((1u << sn[s]) - 1u)) << sg[s];
+  return a;
+}
+__device__ __forceinline__ unsigned qr_deposit(unsigned v, int nseg, const unsigned char *sl, const unsigned char *sn,
+                                               const unsigned char *sd) {
+  unsigned a = 0;
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+    if (s < nseg) a |= ((v >> sl[s]) & ((1u << sn[s]) - 1u)) << sd[s];
+  return a;
+}
+
+// table index (in entries) of the selector bits outside R: up to three bit-field runs of the 64-bit flat index
+__device__ __forceinline__ unsigned qr_run(unsigned sel, int r, unsigned lo, unsigned hi, unsigned pos) {
+  const unsigned sh = (sel >> (9 * r)) & 63u, w = (sel >> (9 * r + 6)) & 7u;
+  const unsigned v = sh < 32 ? __funnelshift_r(lo, hi, sh) : (hi >> (sh & 31));
+  return (v & ((1u << w) - 1u)) << pos;
+}
+__device__ __forceinline__ unsigned qr_field(unsigned sel, unsigned lo, unsigned hi) {
+  unsigned idx = qr_run(sel, 0, lo, hi, 0);
+  if (sel >> 9) {
+    const unsigned w0 = (sel >> 6) & 7u, w1 = (sel >> 15) & 7u;
+    idx |= qr_run(sel, 1, lo, hi, w0);
+    if (sel >> 18) idx |= qr_run(sel, 2, lo, hi, w0 + w1);
+  }
+  return idx;
+}
+
+// weights: REALW tables hold 8-byte reals (2 DFMA per product), otherwise (re, im) pairs (4 DFMA)
+template <bool REALW>
+struct QRW {
+  double re, im;
+  __device__ __forceinline__ void load(const unsigned char *p) {
+    if (REALW) {
+      re = *reinterpret_cast<const double *>(p);
+      im = 0.0;
+    } else {
+      const double2 t = *reinterpret_cast<const double2 *>(p);
+      re = t.x;
+      im = t.y;
+    }
+  }
+  __device__ __forceinline__ void fma_into(double2 &acc, const double2 v) const {
+    if (REALW) {
+      acc.x = fma(re, v.x, acc.x);
+      acc.y = fma(re, v.y, acc.y);
+    } else {
+      acc.x = fma(re, v.x, acc.x);
+      acc.x = fma(-im, v.y, acc.x);
+      acc.y = fma(re, v.y, acc.y);
+      acc.y = fma(im, v.x, acc.y);
+    }
+  }
+};
+
+// bond inside the thread's 16 amplitudes: no shared-memory access at all
+template <bool REALW, int SELR, int M>
+__device__ __forceinline__ void qr_inreg(double2 (&acc)[16], const double2 (&xr)[16], const unsigned char *wt) {
+  constexpr int NW = 1 << qr_popc(SELR);
+  QRW<REALW> w[NW];
+#pragma unroll
+  for (int v = 0; v < NW; ++v) w[v].load(wt + v * (REALW ? 8 : 16));
+#pragma unroll
+  for (int u = 0; u < 16; ++u) w[qr_pext(u, SELR)].fma_into(acc[u], xr[u ^ M]);
+}
+// bond that leaves the thread: one LDS.128 per amplitude, weights hoisted
+template <bool REALW, int SELR>
+__device__ __forceinline__ void qr_gather(double2 (&acc)[16], const unsigned char *xt, const uint32_t (&goff)[16],
+                                          const unsigned char *wt) {
+  constexpr int NW = 1 << qr_popc(SELR);
+  QRW<REALW> w[NW];
+#pragma unroll
+  for (int v = 0; v < NW; ++v) w[v].load(wt + v * (REALW ? 8 : 16));
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    double2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const double2 *>(xt + goff[8 * h + u]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w[qr_pext(8 * h + u, SELR)].fma_into(acc[8 * h + u], v[u]);
+  }
+}
+// any selector pattern: weight looked up per amplitude
+template <bool REALW>
+__device__ __forceinline__ void qr_gather_slow(double2 (&acc)[16], const unsigned char *xt, const uint32_t (&goff)[16],
+                                               const unsigned char *wt, unsigned selr) {
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    unsigned r = 0, k = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if ((selr >> b) & 1u) {
+        r |= ((u >> b) & 1u) << k;
+        ++k;
+      }
+    QRW<REALW> w;
+    w.load(wt + r * (REALW ? 8 : 16));
+    const double2 v = *reinterpret_cast<const double2 *>(xt + goff[u]);
+    w.fma_into(acc[u], v);
+  }
+}
+
+struct QRItem {
+  int pass;        // -1: no more work
+  unsigned tile;   // compact tile id
+  unsigned chunk;
+  unsigned pad;
+};
+
+// work item -> (pass, chunk, tile within chunk); false when the queue is exhausted
+__device__ __forceinline__ bool qr_decode(const QRLaunch &L, unsigned item, int &p, unsigned &c, unsigned &j) {
+  if (item >= L.total_items) return false;
+  if (L.npass == 1) {
+    p = 0;
+    c = 0;
+    j = item;
+    return true;
+  }
+  const unsigned b = item >> L.tpc_log2, C = L.nchunks, lag = L.lag;
+  j = item & ((1u << L.tpc_log2) - 1u);
+  if (C <= lag) {
+    p = b < C ? 0 : 1;
+    c = b < C ? b : b - C;
+  } else if (b < lag) {
+    p = 0;
+    c = b;
+  } else {
+    const unsigned b1 = b - lag, mid = 2u * (C - lag);
+    if (b1 < mid) {
+      p = (int)(b1 & 1u);
+      c = p ? (b1 >> 1) : lag + (b1 >> 1);
+    } else {
+      p = 1;
+      c = C - lag + (b1 - mid);
+    }
+  }
+  return true;
+}
+
+template <bool REALW>
+__global__ void __launch_bounds__(QR_THREADS, 1)
+    qreg_kernel(const __grid_constant__ QRLaunch L, const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUtensorMap my0,
+                const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap my1, double2 *__restrict__ y) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *smem = smem_raw + ((128u - (qr_smem(smem_raw) & 127u)) & 127u);  // TMA destinations: 128-byte aligned
+  unsigned char *xs0 = smem;                              // two x stages
+  unsigned char *ysb = smem + 2 * QR_TILE_BYTES;          // y of a read-modify-write tile
+  unsigned char *tabs = smem + 3 * QR_TILE_BYTES;         // weight tables of the pass(es)
+  const unsigned tab_total = L.pass[0].tab_bytes + (L.npass > 1 ? L.pass[1].tab_bytes : 0u);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(tabs + ((tab_total + 15u) & ~15u));
+  // bars[0,1]: x full; [2,3]: x empty; [4]: y full; [5]: y empty
+  QRItem *slots = reinterpret_cast<QRItem *>(bars + 8);
+  const unsigned tid = threadIdx.x;
+  constexpr int WB = REALW ? 8 : 16;
+
+  if (tid == 0) {
+    qr_mbar_init(qr_smem(bars + 0), 1);
+    qr_mbar_init(qr_smem(bars + 1), 1);
+    qr_mbar_init(qr_smem(bars + 2), QR_CTHREADS / 32);
+    qr_mbar_init(qr_smem(bars + 3), QR_CTHREADS / 32);
+    qr_mbar_init(qr_smem(bars + 4), 1);
+    qr_mbar_init(qr_smem(bars + 5), QR_CTHREADS / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+  }
+  for (int p = 0; p < L.npass; ++p) {
+    const int4 *g4 = reinterpret_cast<const int4 *>(L.pass[p].tab);
+    int4 *t4 = reinterpret_cast<int4 *>(tabs + L.pass[p].tab_smem_off);
+    for (unsigned i = tid; i < L.pass[p].tab_bytes / 16u; i += QR_THREADS) t4[i] = g4[i];
+  }
+  __syncthreads();
+
+  if (tid >= QR_CTHREADS) {
+    // ------------------------------------------------------------------ producer (one thread)
+    if (tid == QR_CTHREADS) {
+      unsigned long long pol_keep, pol_stream;
+      asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+      unsigned stage = 0, xphase = 0, yphase = 0;  // bit s of xphase: parity of the next wait on x-empty[s]
+      while (true) {
+        const unsigned item = atomicAdd(L.queue, 1u);
+        int p = 0;
+        unsigned c = 0, j = 0;
+        const bool more = qr_decode(L, item, p, c, j);
+        qr_mbar_wait(qr_smem(bars + 2 + stage), ((xphase >> stage) & 1u) ^ 1u);
+        xphase ^= 1u << stage;
+        QRItem it;
+        it.pass = more ? p : -1;
+        it.chunk = c;
+        it.pad = 0;
+        if (!more) {
+          it.tile = 0;
+          slots[stage] = it;
+          qr_mbar_arrive(qr_smem(bars + stage));
+          break;
+        }
+        const QRPass &P = L.pass[p];
+        const unsigned t = L.npass == 1 ? j : (qr_deposit(c, P.ncs, P.cs_l, P.cs_n, P.cs_d) | qr_deposit(j, P.njs, P.js_l, P.js_n, P.js_d));
+        it.tile = t;
+        slots[stage] = it;
+        if (P.wait) {
+          const unsigned need = 1u << L.tpc_log2;
+          unsigned have;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(L.done + c) : "memory");
+            if (have < need) __nanosleep(64);
+          } while (have < need);
+          asm volatile("fence.proxy.async;\n" ::: "memory");  // the tiles written by other CTAs are read by the async proxy
+        }
+        int co[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) co[d] = (int)(((t >> P.dim_tshift[d]) & ((1u << P.dim_tbits[d]) - 1u)) << P.dim_boxlog[d]);
+        const unsigned long long pol = P.stream_out ? pol_stream : pol_keep;
+        qr_mbar_expect(qr_smem(bars + stage), QR_TILE_BYTES);
+        qr_tma_load(qr_smem(xs0 + stage * QR_TILE_BYTES), p ? &mx1 : &mx0, qr_smem(bars + stage), P.rank, co, pol);
+        if (P.mode != 0) {
+          qr_mbar_wait(qr_smem(bars + 5), (yphase & 1u) ^ 1u);
+          yphase ^= 1u;
+          qr_mbar_expect(qr_smem(bars + 4), QR_TILE_BYTES);
+          qr_tma_load(qr_smem(ysb), p ? &my1 : &my0, qr_smem(bars + 4), P.rank, co, pol);
+        }
+        stage ^= 1u;
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  unsigned long long pol_stream;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  unsigned stage = 0, xphase = 0, yphase = 0;
+#pragma unroll 1
+  while (true) {
+    qr_mbar_wait(qr_smem(bars + stage), (xphase >> stage) & 1u);
+    xphase ^= 1u << stage;
+    const QRItem it = slots[stage];
+    if (it.pass < 0) break;
+    const QRPass &P = L.pass[it.pass];
+    const unsigned char *xs = xs0 + stage * QR_TILE_BYTES;
+    const unsigned char *tb = tabs + P.tab_smem_off;
+    // thread part of the tile-local byte offset and of the global element offset
+    unsigned so = 0;
+    unsigned long long go = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+      if ((tid >> b) & 1u) {
+        so |= 16u << P.tpos[b];
+        go |= 1ull << P.tgbit[b];
+      }
+    const unsigned long long tbase = qr_expand(it.tile, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g);
+    const unsigned long long gidx = tbase | go | P.hi_or;
+    const unsigned g_lo = (unsigned)gidx, g_hi = (unsigned)(gidx >> 32);
+
+    double2 acc[16];
+    {
+      double2 xr[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) xr[u] = *reinterpret_cast<const double2 *>(xs + so + P.uoffB[u]);
+      int c = 0;
+      if (P.n_pre + P.n_diagr > 0) {
+        // diagonal weight: tables whose selector bits are fixed for the thread, plus tables indexed by the R bits
+        double dre = 0.0, dim = 0.0;
+        for (; c < P.n_pre; ++c) {
+          const QRComp &cd = P.comps[c];
+          QRW<REALW> w;
+          w.load(tb + (size_t)(cd.tabE + qr_field(cd.sel, g_lo, g_hi)) * WB);
+          dre += w.re;
+          dim += w.im;
+        }
+        QRW<REALW> d[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          d[u].re = dre;
+          d[u].im = dim;
+        }
+        for (; c < P.n_pre + P.n_diagr; ++c) {
+          const QRComp &cd = P.comps[c];
+          const unsigned char *wt = tb + (size_t)(cd.tabE + qr_field(cd.sel, g_lo, g_hi) * 16u) * WB;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            QRW<REALW> w;
+            w.load(wt + u * WB);
+            d[u].re += w.re;
+            d[u].im += w.im;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          if (REALW) acc[u] = make_double2(d[u].re * xr[u].x, d[u].re * xr[u].y);
+          else acc[u] = make_double2(d[u].re * xr[u].x - d[u].im * xr[u].y, d[u].re * xr[u].y + d[u].im * xr[u].x);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc[u] = make_double2(0.0, 0.0);
+      }
+      const int c_in_end = P.n_pre + P.n_diagr + P.n_inreg;
+      for (; c < c_in_end; ++c) {
+        const QRComp &cd = P.comps[c];
+        const unsigned sr = __popc((cd.kind >> 4) & 15u);
+        const unsigned char *wt = tb + (size_t)(cd.tabE + (qr_field(cd.sel, g_lo, g_hi) << sr)) * WB;
+        switch (cd.kind >> 4) {  // SELR | M << 4, SELR == M
+#define QR_IN(MM) \
+  case (MM | (MM << 4)): qr_inreg<REALW, MM, MM>(acc, xr, wt); break;
+          QR_IN(1) QR_IN(2) QR_IN(4) QR_IN(8) QR_IN(3) QR_IN(5) QR_IN(6) QR_IN(9) QR_IN(10) QR_IN(12)
+#undef QR_IN
+          default: break;
+        }
+      }
+    }
+    {
+      const int c0 = P.n_pre + P.n_diagr + P.n_inreg, c1 = c0 + P.n_gather;
+      for (int c = c0; c < c1; ++c) {
+        const QRComp &cd = P.comps[c];
+        const unsigned selr = (cd.kind >> 4) & 15u;
+        const unsigned sr = __popc(selr);
+        const unsigned char *wt = tb + (size_t)(cd.tabE + (qr_field(cd.sel, g_lo, g_hi) << sr)) * WB;
+        const unsigned char *xt = xs + (so ^ cd.xorT);
+        if ((cd.kind & 15u) == QR_GATHER) {
+          switch (selr) {
+#define QR_GA(SS) \
+  case SS: qr_gather<REALW, SS>(acc, xt, cd.goff, wt); break;
+            QR_GA(0) QR_GA(1) QR_GA(2) QR_GA(4) QR_GA(8) QR_GA(3) QR_GA(5) QR_GA(6) QR_GA(9) QR_GA(10) QR_GA(12)
+#undef QR_GA
+            default: break;
+          }
+        } else {
+          qr_gather_slow<REALW>(acc, xt, cd.goff, wt, selr);
+        }
+      }
+    }
+    // all reads of this x stage are done
+    __syncwarp();
+    if ((tid & 31u) == 0) qr_mbar_arrive(qr_smem(bars + 2 + stage));
+
+    // ---- epilogue
+    double2 *yt = y + tbase + go;
+    if (P.mode != 0) {
+      qr_mbar_wait(qr_smem(bars + 4), yphase & 1u);
+      yphase ^= 1u;
+      double2 yo[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) yo[u] = *reinterpret_cast<const double2 *>(ysb + so + P.uoffB[u]);
+      __syncwarp();
+      if ((tid & 31u) == 0) qr_mbar_arrive(qr_smem(bars + 5));
+      if (P.mode == 1) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          yo[u] = make_double2(L.beta.x * yo[u].x - L.beta.y * yo[u].y, L.beta.x * yo[u].y + L.beta.y * yo[u].x);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        acc[u] = make_double2(fma(L.alpha.x, acc[u].x, fma(-L.alpha.y, acc[u].y, yo[u].x)),
+                              fma(L.alpha.x, acc[u].y, fma(L.alpha.y, acc[u].x, yo[u].y)));
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        acc[u] = make_double2(L.alpha.x * acc[u].x - L.alpha.y * acc[u].y, L.alpha.x * acc[u].y + L.alpha.y * acc[u].x);
+    }
+    if (P.stream_out) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(yt + P.ugoff[u]), "d"(acc[u].x), "d"(acc[u].y), "l"(pol_stream)
+                     : "memory");
+    } else {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) yt[P.ugoff[u]] = acc[u];
+    }
+    if (P.signal) {
+      asm volatile("bar.sync 1, %0;\n" ::"n"(QR_CTHREADS) : "memory");
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(L.done + it.chunk, 1u);
+      }
+    }
+    stage ^= 1u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+struct QRCompHost {
+  uint64_t mask = 0;
+  std::vector<int> sel;  // selector bit positions (flat index), ascending
+  struct Contrib {
+    int coef_index;
+    cplx scalar;
+    std::vector<cplx> unit;  // 2^nsel
+  };
+  std::vector<Contrib> contribs;
+  int pass = -1;
+};
+struct QRTableHost {
+  std::vector<int> bits;  // flat-index bit behind each bit of the table index (lowest first)
+  struct Member {
+    int comp;
+    std::vector<int> pos;  // for each selector bit of the component: its position inside `bits`
+  };
+  std::vector<Member> members;
+  uint32_t tab_off = 0;  // entries
+};
+struct QRPassHost {
+  std::vector<int> free_bits;  // ascending, QR_T of them
+  std::vector<int> rpos;       // the 4 tile-local positions that form R (ascending)
+  std::vector<QRTableHost> tables;
+  QRPass params;
+  std::vector<cplx> h_tab;
+  DevArray<unsigned char> d_tab;
+  size_t tab_entries = 0;
+  // tensor map geometry (elements are doubles)
+  int rank = 0;
+  uint64_t gdim[5], gstride[5];
+  uint32_t box[5];
+  // cached tensor maps
+  const void *map_x_ptr = nullptr, *map_y_ptr = nullptr;
+  alignas(64) CUtensorMap map_x, map_y;
+  int n_work = 0;
+};
+struct QRegProgramHost {
+  int nbits = 0;
+  uint64_t hi_value = 0;
+  std::vector<QRCompHost> comps;
+  std::vector<std::unique_ptr<QRPassHost>> passes;   // execution order
+  struct Group {
+    int first, count;          // passes [first, first+count) run in one launch
+    unsigned tpc_log2 = 0, nchunks = 1, lag = 0;
+  };
+  std::vector<Group> groups;
+  bool real_tables = false;
+  std::mutex mu;
+  std::map<cudaStream_t, unsigned *> sync_bufs;      // per stream: work counter + per-chunk counters
+  size_t sync_words = 0;
+  ~QRegProgramHost() {
+    for (auto &kv : sync_bufs)
+      if (kv.second) cudaFree(kv.second);
+  }
+};
+
+static int qr_env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+static void qr_segments(const std::vector<int> &bits, unsigned char *sl, unsigned char *sn, unsigned char *sg, int &nseg) {
+  nseg = 0;
+  size_t i = 0;
+  while (i < bits.size()) {
+    size_t j = i;
+    while (j + 1 < bits.size() && bits[j + 1] == bits[j] + 1) ++j;
+    if (nseg < QR_MAXSEG) {
+      sl[nseg] = (unsigned char)i;
+      sn[nseg] = (unsigned char)(j - i + 1);
+      sg[nseg] = (unsigned char)bits[i];
+    }
+    ++nseg;
+    i = j + 1;
+  }
+}
+static bool qr_pack_runs(const std::vector<int> &bits, uint32_t &sel) {
+  sel = 0;
+  int r = 0;
+  size_t i = 0;
+  while (i < bits.size()) {
+    size_t j = i;
+    while (j + 1 < bits.size() && bits[j + 1] == bits[j] + 1) ++j;
+    const int w = (int)(j - i + 1);
+    if (r >= 3 || w > 7 || bits[i] > 63) return false;
+    sel |= ((uint32_t)bits[i] | ((uint32_t)w << 6)) << (9 * r);
+    ++r;
+    i = j + 1;
+  }
+  return true;
+}
+
+static cplx qr_comp_value(const QRCompHost &c, const std::vector<cplx> &coefs, size_t r) {
+  cplx w = 0.0;
+  for (const auto &ct : c.contribs) {
+    cplx f = ct.scalar;
+    if (ct.coef_index >= 0) f *= coefs[ct.coef_index];
+    w += f * ct.unit[r];
+  }
+  return w;
+}
+
+static void qr_fill_tables(QRegProgramHost &h, const std::vector<cplx> &coefs) {
+  bool real = true;
+  for (auto &pp : h.passes) {
+    QRPassHost &p = *pp;
+    std::fill(p.h_tab.begin(), p.h_tab.end(), cplx(0.0, 0.0));
+    for (const QRTableHost &t : p.tables) {
+      const size_t n = (size_t)1 << t.bits.size();
+      for (const auto &m : t.members) {
+        const QRCompHost &c = h.comps[m.comp];
+        std::vector<cplx> cv((size_t)1 << c.sel.size());
+        for (size_t r = 0; r < cv.size(); ++r) cv[r] = qr_comp_value(c, coefs, r);
+        for (size_t r = 0; r < n; ++r) {
+          size_t ci = 0;
+          for (size_t b = 0; b < m.pos.size(); ++b) ci |= ((r >> m.pos[b]) & 1) << b;
+          p.h_tab[t.tab_off + r] += cv[ci];
+        }
+      }
+    }
+    for (const cplx &z : p.h_tab) real &= (z.imag() == 0.0);
+  }
+  h.real_tables = real && !getenv("QOB_QTILE_NO_REALW");
+}
+
+// tile-local bit positions -> the thread / amplitude split and every offset table of a pass
+static void qr_layout(QRPassHost &ph, int nbits, uint64_t hi_value) {
+  QRPass &P = ph.params;
+  const std::vector<int> &fb = ph.free_bits;
+  for (int u = 0; u < 16; ++u) {
+    uint32_t o = 0;
+    unsigned long long g = 0;
+    for (int k = 0; k < 4; ++k)
+      if ((u >> k) & 1) {
+        o |= 16u << ph.rpos[k];
+        g |= 1ull << fb[ph.rpos[k]];
+      }
+    P.uoffB[u] = o;
+    P.ugoff[u] = g;
+  }
+  int b = 0;
+  for (int pos = 0; pos < QR_T; ++pos) {
+    if (std::find(ph.rpos.begin(), ph.rpos.end(), pos) != ph.rpos.end()) continue;
+    P.tpos[b] = (unsigned char)pos;
+    P.tgbit[b] = (unsigned char)fb[pos];
+    ++b;
+  }
+  std::vector<int> fixed;
+  for (int i = 0; i < nbits; ++i)
+    if (std::find(fb.begin(), fb.end(), i) == fb.end()) fixed.push_back(i);
+  qr_segments(fixed, P.xs_l, P.xs_n, P.xs_g, P.nfixed_seg);
+  P.hi_or = (nbits >= 64) ? 0ull : (hi_value << nbits);
+}
+
+// Tensor map of a pass: every run of free bits, merged with the run of fixed bits above it, is one dimension whose box
+// extent covers only the free part; runs of more than 8 bits (256 elements) are split.  Elements are doubles (2 per amplitude).
+static bool qr_tensor_geometry(QRPassHost &ph, int nbits) {
+  const std::vector<int> &fb = ph.free_bits;
+  std::vector<int> fixed;
+  for (int i = 0; i < nbits; ++i)
+    if (std::find(fb.begin(), fb.end(), i) == fb.end()) fixed.push_back(i);
+  auto fixed_rank = [&](int bit) {  // compact position of a fixed bit
+    return (int)(std::find(fixed.begin(), fixed.end(), bit) - fixed.begin());
+  };
+  QRPass &P = ph.params;
+  int rank = 0;
+  size_t i = 0;
+  if (fb.empty() || fb[0] != 0) return false;
+  while (i < fb.size()) {
+    size_t j = i;
+    while (j + 1 < fb.size() && fb[j + 1] == fb[j] + 1) ++j;
+    int lo = fb[i], n = (int)(j - i + 1);            // run of free bits [lo, lo+n)
+    int top = lo + n;                                // fixed bits [top, next free run or nbits)
+    int nfix = 0;
+    while (top + nfix < nbits && std::find(fb.begin(), fb.end(), top + nfix) == fb.end()) ++nfix;
+    // split the free run into pieces of <= 8 bits (7 for the first run: 2 doubles per amplitude)
+    int done = 0;
+    while (done < n) {
+      const int cap = (lo == 0 && done == 0) ? 7 : 8;
+      const int piece = std::min(cap, n - done);
+      const bool last = done + piece == n;
+      if (rank >= 5) return false;
+      const int start = lo + done;
+      const int el = (start == 0) ? 1 : 0;           // the first dimension counts doubles
+      ph.box[rank] = 1u << (piece + el);
+      ph.gdim[rank] = 1ull << (piece + el + (last ? nfix : 0));
+      ph.gstride[rank] = 16ull << start;             // bytes (unused for dimension 0)
+      P.dim_boxlog[rank] = (unsigned char)(piece + el);
+      P.dim_tshift[rank] = (unsigned char)((last && nfix) ? fixed_rank(top) : 0);
+      P.dim_tbits[rank] = (unsigned char)(last ? nfix : 0);
+      if (ph.gstride[rank] >= (1ull << 40)) return false;
+      ++rank;
+      done += piece;
+    }
+    i = j + 1;
+  }
+  ph.rank = rank;
+  P.rank = rank;
+  for (int d = rank; d < 5; ++d) P.dim_boxlog[d] = P.dim_tshift[d] = P.dim_tbits[d] = 0;
+  return true;
+}
+
+typedef CUresult (*qr_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static qr_encode_fn qr_get_encode() {
+  static qr_encode_fn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (qr_encode_fn)p;
+  });
+  return fn;
+}
+static int qr_encode_map(const QRPassHost &ph, const void *base, CUtensorMap *out) {
+  qr_encode_fn enc = qr_get_encode();
+  if (!enc) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t box[5], estr[5];
+  for (int d = 0; d < ph.rank; ++d) {
+    gdim[d] = ph.gdim[d];
+    box[d] = ph.box[d];
+    estr[d] = 1;
+    if (d > 0) gstr[d - 1] = ph.gstride[d];
+  }
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)ph.rank, const_cast<void *>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return QOB_STATUS_OK;
+}
+
+// merge diagonal components whose selector bits avoid R into tables over windows of <= QR_DIAG_WINDOW bits
+static void qr_merge_pre(const QRegProgramHost &h, std::vector<int> ids, std::vector<QRTableHost> &out) {
+  std::sort(ids.begin(), ids.end(), [&](int a, int b) {
+    const auto &sa = h.comps[a].sel, &sb = h.comps[b].sel;
+    int la = sa.empty() ? -1 : sa.front(), lb = sb.empty() ? -1 : sb.front();
+    if (la != lb) return la < lb;
+    return sa < sb;
+  });
+  std::vector<bool> used(ids.size(), false);
+  for (size_t i = 0; i < ids.size(); ++i) {
+    if (used[i]) continue;
+    QRTableHost t;
+    std::vector<int> bits = h.comps[ids[i]].sel;
+    std::vector<size_t> mem = {i};
+    used[i] = true;
+    for (size_t j = i + 1; j < ids.size(); ++j) {
+      if (used[j]) continue;
+      std::vector<int> u = bits;
+      for (int b : h.comps[ids[j]].sel)
+        if (std::find(u.begin(), u.end(), b) == u.end()) u.push_back(b);
+      std::sort(u.begin(), u.end());
+      uint32_t dummy;
+      if ((int)u.size() <= QR_DIAG_WINDOW && qr_pack_runs(u, dummy)) {
+        bits = u;
+        mem.push_back(j);
+        used[j] = true;
+      }
+    }
+    t.bits = bits;
+    for (size_t m : mem) {
+      QRTableHost::Member mm;
+      mm.comp = ids[m];
+      for (int b : h.comps[ids[m]].sel) mm.pos.push_back((int)(std::find(bits.begin(), bits.end(), b) - bits.begin()));
+      t.members.push_back(mm);
+    }
+    out.push_back(std::move(t));
+  }
+}
+
+int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vector<QTerm> &terms, int sm_count) {
+  (void)sm_count;
+  auto h = std::make_shared<QRegProgramHost>();
+  h->nbits = nbits;
+  h->hi_value = hi_value;
+  const int T = QR_T;
+  if (nbits < T) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg needs at least %d index bits (got %d)", T, nbits);
+  if (nbits - T > 31) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: too many tiles");
+  const int L = 3;
+
+  // ---- expand every term into flip / no-flip components, merged by (mask, selector bits)
+  std::map<std::pair<uint64_t, std::vector<int>>, int> index;
+  for (const QTerm &t : terms) {
+    const int k = (int)t.bits.size();
+    if (k > 3) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: term on %d sites (max 3)", k);
+    for (int S = 0; S < (1 << k); ++S) {
+      std::vector<cplx> unit((size_t)1 << k);
+      bool any = false;
+      for (int r = 0; r < (1 << k); ++r) {
+        cplx w = 1.0;
+        for (int f = 0; f < k; ++f) {
+          const int i = (r >> f) & 1, j = ((S >> f) & 1) ? 1 - i : i;
+          w *= t.m[4 * f + 2 * i + j];
+        }
+        unit[r] = w;
+        any |= (w != cplx(0.0, 0.0));
+      }
+      if (!any) continue;
+      uint64_t mask = 0;
+      for (int f = 0; f < k; ++f)
+        if ((S >> f) & 1) {
+          if (t.bits[f] >= nbits) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: off-diagonal factor on a non-local bit %d", t.bits[f]);
+          mask |= 1ull << t.bits[f];
+        }
+      auto key = std::make_pair(mask, t.bits);
+      auto it = index.find(key);
+      int id;
+      if (it == index.end()) {
+        id = (int)h->comps.size();
+        index[key] = id;
+        QRCompHost c;
+        c.mask = mask;
+        c.sel = t.bits;
+        h->comps.push_back(c);
+      } else {
+        id = it->second;
+      }
+      h->comps[id].contribs.push_back({t.coef_index, t.scalar, unit});
+    }
+  }
+
+  // ---- cover the distinct masks with passes of T free bits: pass 0 = the lowest T bits (contiguous tiles), every other
+  // pass = the low block of L bits (128-byte runs) plus a window of high bits, chosen greedily from the lowest uncovered bit
+  std::vector<uint64_t> masks;
+  for (auto &c : h->comps)
+    if (c.mask && std::find(masks.begin(), masks.end(), c.mask) == masks.end()) masks.push_back(c.mask);
+  std::vector<uint64_t> free_sets;
+  {
+    free_sets.push_back((1ull << T) - 1);
+    std::vector<uint64_t> remaining;
+    for (uint64_t m : masks)
+      if (m & ~free_sets[0]) remaining.push_back(m);
+    const uint64_t lowL = (1ull << L) - 1;
+    auto min_high = [&](uint64_t m) { uint64_t hgh = m & ~lowL; return hgh ? __builtin_ctzll(hgh) : 64; };
+    std::sort(remaining.begin(), remaining.end(), [&](uint64_t a, uint64_t b) {
+      const int ha = min_high(a), hb = min_high(b);
+      if (ha != hb) return ha < hb;
+      return a < b;
+    });
+    while (!remaining.empty()) {
+      uint64_t fr = lowL;
+      std::vector<uint64_t> rest;
+      for (uint64_t m : remaining) {
+        const uint64_t u = fr | m;
+        if (__builtin_popcountll(u) <= T) fr = u;
+        else rest.push_back(m);
+      }
+      if (fr == lowL) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: a term does not fit one tile");
+      for (int b = 0; b < nbits && __builtin_popcountll(fr) < T; ++b) fr |= 1ull << b;  // spare bits widen the low block
+      std::vector<uint64_t> rest2;
+      for (uint64_t m : rest)
+        if (m & ~fr) rest2.push_back(m);
+      remaining.swap(rest2);
+      free_sets.push_back(fr);
+    }
+  }
+  const int np = (int)free_sets.size();
+  std::vector<std::vector<int>> fbits(np);
+  for (int p = 0; p < np; ++p)
+    for (int b = 0; b < nbits; ++b)
+      if (free_sets[p] >> b & 1) fbits[p].push_back(b);
+
+  // ---- the R bits of every pass: the 4 tile-local positions (>= 3, so that 8 consecutive lanes read one 128-byte line)
+  // that make the most masks of the pass register-resident (mask inside R, <= 2 bits, selectors == mask bits)
+  auto in_reg_ok = [&](const QRCompHost &c, uint64_t rbits) {
+    if (!c.mask || (c.mask & ~rbits) || __builtin_popcountll(c.mask) > 2) return false;
+    uint64_t sb = 0;
+    for (int b : c.sel) sb |= 1ull << b;
+    return (sb & rbits) == c.mask;
+  };
+  std::vector<std::vector<int>> rpos(np);
+  std::vector<uint64_t> rbits(np, 0);
+  for (int p = 0; p < np; ++p) {
+    int best_score = -1;
+    std::vector<int> best;
+    for (int a = 3; a < T; ++a)
+      for (int b = a + 1; b < T; ++b)
+        for (int c = b + 1; c < T; ++c)
+          for (int d = c + 1; d < T; ++d) {
+            const uint64_t rb = (1ull << fbits[p][a]) | (1ull << fbits[p][b]) | (1ull << fbits[p][c]) | (1ull << fbits[p][d]);
+            int score = 0;
+            std::vector<uint64_t> seen;
+            for (auto &cc : h->comps) {
+              if (!cc.mask || (cc.mask & ~free_sets[p])) continue;
+              if (in_reg_ok(cc, rb) && std::find(seen.begin(), seen.end(), cc.mask) == seen.end()) {
+                seen.push_back(cc.mask);
+                // a mask that only this pass can take counts double
+                int ncand = 0;
+                for (int q = 0; q < np; ++q) ncand += ((cc.mask & ~free_sets[q]) == 0);
+                score += ncand == 1 ? 4 : 3;
+              }
+            }
+            score = score * 16 + (a + b + c + d) / 4;  // ties: the highest positions
+            if (score > best_score) {
+              best_score = score;
+              best = {a, b, c, d};
+            }
+          }
+    rpos[p] = best;
+    for (int k : best) rbits[p] |= 1ull << fbits[p][k];
+  }
+
+  // ---- assign components to passes.  Diagonal weights go to pass 0.  A mask goes where it is register-resident if that
+  // is possible, otherwise to the candidate with the fewest gathers so far (masks with one candidate are placed first).
+  {
+    std::vector<int> load(np, 0);
+    std::map<uint64_t, int> mask_pass;
+    for (int movable = 0; movable < 2; ++movable)
+      for (auto &c : h->comps) {
+        if (!c.mask) {
+          c.pass = 0;
+          continue;
+        }
+        std::vector<int> cand;
+        for (int p = 0; p < np; ++p)
+          if ((c.mask & ~free_sets[p]) == 0) cand.push_back(p);
+        if (cand.empty()) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: internal planner error (uncovered mask)");
+        if ((cand.size() > 1) != (movable == 1)) continue;
+        auto it = mask_pass.find(c.mask);
+        if (it != mask_pass.end()) {
+          c.pass = it->second;
+          continue;
+        }
+        int best = -1;
+        for (int p : cand)
+          if (in_reg_ok(c, rbits[p])) {
+            best = p;
+            break;
+          }
+        if (best < 0) {
+          best = cand[0];
+          for (int p : cand)
+            if (load[p] < load[best] || (load[p] == load[best] && p > best)) best = p;
+          load[best]++;
+        }
+        c.pass = best;
+        mask_pass[c.mask] = best;
+      }
+  }
+
+  // ---- records and tables of every pass
+  for (int p = 0; p < np; ++p) {
+    auto ph = std::make_unique<QRPassHost>();
+    ph->free_bits = fbits[p];
+    ph->rpos = rpos[p];
+    QRPass &P = ph->params;
+    memset(&P, 0, sizeof(P));
+    qr_layout(*ph, nbits, hi_value);
+    if (!qr_tensor_geometry(*ph, nbits)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: tile shape needs a tensor map of rank > 5");
+    std::vector<int> rg;  // flat-index bits of R, ascending
+    for (int k : ph->rpos) rg.push_back(ph->free_bits[k]);
+    std::vector<int> pre_ids, diagr_ids, inreg_ids, gather_ids;
+    for (size_t id = 0; id < h->comps.size(); ++id) {
+      const QRCompHost &c = h->comps[id];
+      if (c.pass != p) continue;
+      uint64_t sb = 0;
+      for (int b : c.sel) sb |= 1ull << b;
+      if (!c.mask) ((sb & rbits[p]) ? diagr_ids : pre_ids).push_back((int)id);
+      else if (in_reg_ok(c, rbits[p])) inreg_ids.push_back((int)id);
+      else gather_ids.push_back((int)id);
+    }
+    ph->n_work = (int)(pre_ids.size() + diagr_ids.size() + inreg_ids.size() + gather_ids.size());
+    std::vector<QRComp> recs;
+    uint32_t tab_off = 0;
+    auto selr_of = [&](const std::vector<int> &bits) {
+      unsigned s = 0;
+      for (int k = 0; k < 4; ++k)
+        if (std::find(bits.begin(), bits.end(), rg[k]) != bits.end()) s |= 1u << k;
+      return s;
+    };
+    // (a) diagonal tables without R bits
+    {
+      std::vector<QRTableHost> tabs;
+      qr_merge_pre(*h, pre_ids, tabs);
+      for (auto &t : tabs) {
+        QRComp r;
+        memset(&r, 0, sizeof r);
+        r.kind = QR_PRE;
+        if (!qr_pack_runs(t.bits, r.sel)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
+        r.tabE = tab_off;
+        t.tab_off = tab_off;
+        tab_off += 1u << t.bits.size();
+        recs.push_back(r);
+        ph->tables.push_back(t);
+      }
+      P.n_pre = (int)tabs.size();
+    }
+    // (b) diagonal tables indexed by all 4 R bits (low index bits) and <= 4 selector bits outside R
+    {
+      std::vector<bool> used(diagr_ids.size(), false);
+      int n = 0;
+      for (size_t i = 0; i < diagr_ids.size(); ++i) {
+        if (used[i]) continue;
+        std::vector<int> outside;
+        std::vector<size_t> mem;
+        for (size_t j = i; j < diagr_ids.size(); ++j) {
+          if (used[j]) continue;
+          std::vector<int> u = outside;
+          for (int b : h->comps[diagr_ids[j]].sel)
+            if (std::find(rg.begin(), rg.end(), b) == rg.end() && std::find(u.begin(), u.end(), b) == u.end()) u.push_back(b);
+          std::sort(u.begin(), u.end());
+          uint32_t dummy;
+          if (u.size() <= 4 && qr_pack_runs(u, dummy)) {
+            outside = u;
+            mem.push_back(j);
+            used[j] = true;
+          }
+        }
+        if (mem.empty()) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
+        QRTableHost t;
+        t.bits = rg;
+        for (int b : outside) t.bits.push_back(b);
+        for (size_t m : mem) {
+          QRTableHost::Member mm;
+          mm.comp = diagr_ids[m];
+          for (int b : h->comps[diagr_ids[m]].sel) mm.pos.push_back((int)(std::find(t.bits.begin(), t.bits.end(), b) - t.bits.begin()));
+          t.members.push_back(mm);
+        }
+        QRComp r;
+        memset(&r, 0, sizeof r);
+        r.kind = QR_DIAGR | (15u << 4);
+        if (!qr_pack_runs(outside, r.sel)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
+        r.tabE = tab_off;
+        t.tab_off = tab_off;
+        tab_off += 1u << t.bits.size();
+        recs.push_back(r);
+        ph->tables.push_back(t);
+        ++n;
+      }
+      P.n_diagr = n;
+    }
+    // (c, d) off-diagonal records: table index = [selector bits inside R, ascending | selector bits outside R, ascending]
+    auto flip_record = [&](int id, int cls) -> int {
+      const QRCompHost &c = h->comps[id];
+      std::vector<int> inside, outside;
+      for (int b : c.sel) ((std::find(rg.begin(), rg.end(), b) != rg.end()) ? inside : outside).push_back(b);
+      QRTableHost t;
+      t.bits = inside;
+      for (int b : outside) t.bits.push_back(b);
+      QRTableHost::Member mm;
+      mm.comp = id;
+      for (int b : c.sel) mm.pos.push_back((int)(std::find(t.bits.begin(), t.bits.end(), b) - t.bits.begin()));
+      t.members.push_back(mm);
+      QRComp r;
+      memset(&r, 0, sizeof r);
+      const unsigned selr = selr_of(c.sel);
+      unsigned mR = 0, lmaskT = 0;
+      for (int k = 0; k < 4; ++k)
+        if (c.mask >> rg[k] & 1) mR |= 1u << k;
+      for (int pos = 0; pos < QR_T; ++pos)
+        if ((c.mask >> ph->free_bits[pos] & 1) && std::find(ph->rpos.begin(), ph->rpos.end(), pos) == ph->rpos.end())
+          lmaskT |= 1u << pos;
+      if (cls == QR_GATHER && __builtin_popcount(selr) > 2) cls = QR_GATHER_SLOW;
+      r.kind = (uint32_t)cls | (selr << 4) | (mR << 8);
+      if (!qr_pack_runs(outside, r.sel)) return QOB_STATUS_UNSUPPORTED;
+      r.xorT = lmaskT * 16u;
+      for (int u = 0; u < 16; ++u) r.goff[u] = P.uoffB[u ^ mR];
+      r.tabE = tab_off;
+      t.tab_off = tab_off;
+      tab_off += 1u << t.bits.size();
+      recs.push_back(r);
+      ph->tables.push_back(t);
+      return QOB_STATUS_OK;
+    };
+    for (int id : inreg_ids)
+      if (flip_record(id, QR_INREG) != QOB_STATUS_OK) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
+    P.n_inreg = (int)inreg_ids.size();
+    for (int id : gather_ids)
+      if (flip_record(id, QR_GATHER) != QOB_STATUS_OK) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
+    P.n_gather = (int)gather_ids.size();
+    if (recs.size() > QR_MAXC) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: %d lookup records in one pass (max %d)", (int)recs.size(), QR_MAXC);
+    for (size_t i = 0; i < recs.size(); ++i) P.comps[i] = recs[i];
+    ph->tab_entries = std::max<uint32_t>(tab_off, 1u);
+    ph->h_tab.assign(ph->tab_entries, cplx(0.0, 0.0));
+    if (ph->tab_entries * 16 > 12 * 1024) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: weight tables too large");
+    h->passes.push_back(std::move(ph));
+  }
+  // drop passes without work (keep pass 0 when nothing at all is left: it carries the beta update)
+  {
+    std::vector<std::unique_ptr<QRPassHost>> keep;
+    for (auto &pp : h->passes)
+      if (pp->n_work > 0) keep.push_back(std::move(pp));
+    h->passes.swap(keep);
+  }
+  if (h->passes.empty()) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: no work");
+
+  // ---- group consecutive passes into chained launches: the union of their free bits must span <= chain_bits index bits
+  const int chain_bits = qr_env_int("QOB_QREG_CHAIN_BITS", 20);
+  for (size_t i = 0; i < h->passes.size();) {
+    QRegProgramHost::Group g;
+    g.first = (int)i;
+    g.count = 1;
+    if (i + 1 < h->passes.size() && chain_bits >= QR_T) {
+      uint64_t u = 0;
+      for (int b : h->passes[i]->free_bits) u |= 1ull << b;
+      for (int b : h->passes[i + 1]->free_bits) u |= 1ull << b;
+      const int ub = __builtin_popcountll(u);
+      if (ub <= chain_bits) {
+        g.count = 2;
+        g.tpc_log2 = (unsigned)(ub - QR_T);
+        g.nchunks = 1u << (nbits - ub);
+        const unsigned tpc = 1u << g.tpc_log2;
+        g.lag = std::max(1u, (unsigned)((qr_env_int("QOB_QREG_LAG_TILES", 192) + tpc - 1) / tpc));
+        // chunk / in-chunk split of the compact tile id of both passes
+        for (int q = 0; q < 2; ++q) {
+          QRPassHost &ph = *h->passes[i + q];
+          QRPass &P = ph.params;
+          std::vector<int> fixed;
+          for (int b = 0; b < nbits; ++b)
+            if (std::find(ph.free_bits.begin(), ph.free_bits.end(), b) == ph.free_bits.end()) fixed.push_back(b);
+          // walk the fixed bits in compact order; bits outside the union number the chunk, bits inside it the tile in the chunk
+          int ci = 0, ji = 0;
+          P.ncs = P.njs = 0;
+          int prev_kind = -1;
+          for (size_t k = 0; k < fixed.size(); ++k) {
+            const int kind = (u >> fixed[k] & 1) ? 1 : 0;  // 1: inside the union
+            unsigned char *sl = kind ? P.js_l : P.cs_l, *sn = kind ? P.js_n : P.cs_n, *sd = kind ? P.js_d : P.cs_d;
+            int &ns = kind ? P.njs : P.ncs;
+            int &src = kind ? ji : ci;
+            if (kind == prev_kind) {
+              sn[ns - 1]++;
+            } else {
+              if (ns >= 4) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: chunk structure too scattered");
+              sl[ns] = (unsigned char)src;
+              sn[ns] = 1;
+              sd[ns] = (unsigned char)k;
+              ++ns;
+            }
+            ++src;
+            prev_kind = kind;
+          }
+        }
+      }
+    }
+    h->groups.push_back(g);
+    i += g.count;
+  }
+  size_t maxchunks = 1;
+  for (auto &g : h->groups) maxchunks = std::max<size_t>(maxchunks, g.nchunks);
+  h->sync_words = 32 + maxchunks;
+
+  prog.h = h;
+  prog.npasses = (int)h->passes.size();
+  char buf[320];
+  snprintf(buf, sizeof buf, "qreg[bits=%d,T=%d,passes=%d,launches=%d,components=%d]", nbits, T, prog.npasses, (int)h->groups.size(),
+           (int)h->comps.size());
+  prog.describe = buf;
+  for (auto &g : h->groups) {
+    prog.describe += g.count == 2 ? " {chained" : " {single";
+    if (g.count == 2) {
+      snprintf(buf, sizeof buf, " chunks=%u x %u tiles, lag=%u:", g.nchunks, 1u << g.tpc_log2, g.lag);
+      prog.describe += buf;
+    }
+    for (int q = 0; q < g.count; ++q) {
+      const QRPassHost &ph = *h->passes[g.first + q];
+      prog.describe += " [free:";
+      unsigned char sl[QR_MAXSEG], sn[QR_MAXSEG], sg[QR_MAXSEG];
+      int ns = 0;
+      qr_segments(ph.free_bits, sl, sn, sg, ns);
+      for (int s = 0; s < ns && s < QR_MAXSEG; ++s) {
+        snprintf(buf, sizeof buf, "%s%d-%d", s ? "," : "", sg[s], sg[s] + sn[s] - 1);
+        prog.describe += buf;
+      }
+      snprintf(buf, sizeof buf, " R:%d,%d,%d,%d diag:%d+%d in-register:%d gathers:%d rank:%d]", ph.free_bits[ph.rpos[0]],
+               ph.free_bits[ph.rpos[1]], ph.free_bits[ph.rpos[2]], ph.free_bits[ph.rpos[3]], ph.params.n_pre, ph.params.n_diagr,
+               ph.params.n_inreg, ph.params.n_gather, ph.rank);
+      prog.describe += buf;
+    }
+    prog.describe += "}";
+  }
+  return QOB_STATUS_OK;
+}
+
+int qreg_set_coefs(QRegProgram &prog, const std::vector<cplx> &coefs, cudaStream_t s) {
+  QRegProgramHost &h = *prog.h;
+  for (auto &c : h.comps)
+    for (auto &ct : c.contribs)
+      if (ct.coef_index >= (int)coefs.size()) QOB_FAIL(QOB_STATUS_INVALID_ARG, "coefficient index out of range");
+  qr_fill_tables(h, coefs);
+  for (auto &pp : h.passes) {
+    // device format: 8-byte reals when every weight of every pass is real, (re, im) pairs otherwise; padded to 16 bytes
+    const size_t wb = h.real_tables ? 8 : 16;
+    std::vector<unsigned char> raw(((pp->tab_entries * wb) + 15) & ~(size_t)15, 0);
+    for (size_t i = 0; i < pp->tab_entries; ++i) {
+      if (h.real_tables) {
+        const double v = pp->h_tab[i].real();
+        memcpy(raw.data() + i * 8, &v, 8);
+      } else {
+        const double v[2] = {pp->h_tab[i].real(), pp->h_tab[i].imag()};
+        memcpy(raw.data() + i * 16, v, 16);
+      }
+    }
+    pp->params.tab_bytes = (uint32_t)raw.size();
+    if (pp->d_tab.n < ((pp->tab_entries * 16 + 15) & ~(size_t)15)) {
+      std::vector<unsigned char> full((pp->tab_entries * 16 + 15) & ~(size_t)15, 0);
+      memcpy(full.data(), raw.data(), raw.size());
+      QOB_TRY(pp->d_tab.upload(full));
+    } else {
+      QOB_TRY(pp->d_tab.upload_async(raw, s));
+    }
+    pp->params.tab = pp->d_tab.ptr;
+  }
+  return QOB_STATUS_OK;
+}
+
+static int g_qreg_sm_count = 0;
+
+int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s) {
+  QRegProgramHost &h = *prog.h;
+  int dev = 0, sms = 148;
+  QOB_CUDA(cudaGetDevice(&dev));
+  QOB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  (void)g_qreg_sm_count;
+  unsigned *sync = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(h.mu);
+    auto it = h.sync_bufs.find(s);
+    if (it == h.sync_bufs.end()) {
+      QOB_CUDA(cudaMalloc(&sync, h.sync_words * sizeof(unsigned)));
+      h.sync_bufs[s] = sync;
+    } else {
+      sync = it->second;
+    }
+  }
+  bool first = true;
+  int gi = 0;
+  for (const auto &g : h.groups) {
+    // algorithmic bytes of this launch at DRAM level: x read + y written once (+ y read when it accumulates), however many
+    // tile passes are chained inside it
+    void *prof_token = qprof_enabled() ? qprof_begin(s, gi, (double)(1ull << h.nbits) * ((first && beta == cplx(0.0, 0.0)) ? 32.0 : 48.0))
+                                       : nullptr;
+    ++gi;
+    QRLaunch Lp;
+    memset(&Lp, 0, sizeof Lp);
+    Lp.npass = g.count;
+    Lp.alpha = make_double2(alpha.real(), alpha.imag());
+    Lp.beta = make_double2(beta.real(), beta.imag());
+    Lp.queue = sync;
+    Lp.done = sync + 32;
+    const unsigned ntiles = 1u << (h.nbits - QR_T);
+    Lp.tpc_log2 = g.tpc_log2;
+    Lp.nchunks = g.nchunks;
+    Lp.lag = g.lag;
+    Lp.total_items = ntiles * (unsigned)g.count;
+    alignas(64) CUtensorMap maps[4];
+    uint32_t tab_off = 0;
+    for (int q = 0; q < g.count; ++q) {
+      QRPassHost &ph = *h.passes[g.first + q];
+      {
+        std::lock_guard<std::mutex> lk(h.mu);
+        if (ph.map_x_ptr != x) {
+          QOB_TRY(qr_encode_map(ph, x, &ph.map_x));
+          ph.map_x_ptr = x;
+        }
+        if (ph.map_y_ptr != y) {
+          QOB_TRY(qr_encode_map(ph, y, &ph.map_y));
+          ph.map_y_ptr = y;
+        }
+        maps[2 * q] = ph.map_x;
+        maps[2 * q + 1] = ph.map_y;
+      }
+      Lp.pass[q] = ph.params;
+      QRPass &P = Lp.pass[q];
+      P.mode = first ? (beta == cplx(0.0, 0.0) ? 0 : 1) : 2;
+      first = false;
+      P.signal = (g.count == 2 && q == 0) ? 1 : 0;
+      P.wait = (g.count == 2 && q == 1) ? 1 : 0;
+      P.stream_out = (q == g.count - 1) ? 1 : 0;
+      P.tab_smem_off = tab_off;
+      tab_off += (P.tab_bytes + 15u) & ~15u;
+    }
+    if (g.count == 1) {
+      maps[2] = maps[0];
+      maps[3] = maps[1];
+    }
+    const size_t smem = 3 * (size_t)QR_TILE_BYTES + tab_off + 16 + 64 + 2 * sizeof(QRItem) + 64 + 128;
+    QOB_CUDA(cudaMemsetAsync(sync, 0, (32 + (size_t)g.nchunks) * sizeof(unsigned), s));
+    const unsigned grid = std::min<unsigned>((unsigned)sms, ntiles * (unsigned)g.count);
+    auto launch = [&](auto kern) -> int {
+      QOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, QR_THREADS, smem, s>>>(Lp, maps[0], maps[1], maps[2], maps[3], (double2 *)y);
+      QOB_LAUNCHED();
+      QOB_CUDA(cudaGetLastError());
+      return QOB_STATUS_OK;
+    };
+    if (h.real_tables) QOB_TRY(launch(qreg_kernel<true>));
+    else QOB_TRY(launch(qreg_kernel<false>));
+    qprof_end(s, prof_token);
+  }
+  return QOB_STATUS_OK;
+}

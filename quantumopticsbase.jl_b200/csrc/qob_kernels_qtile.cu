@@ -971,15 +971,42 @@ struct ProfEntry {
   int pass;
   double bytes;
 };
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
 static std::vector<ProfEntry> g_prof;
+bool qprof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+void *qprof_begin(cudaStream_t s, int pass, double alg_bytes) {
+  if (!qprof_enabled()) return nullptr;
+  ProfEntry *pe = new ProfEntry;
+  cudaEventCreate(&pe->a);
+  cudaEventCreate(&pe->b);
+  pe->pass = pass;
+  pe->bytes = alg_bytes;
+  cudaEventRecord(pe->a, s);
+  return pe;
+}
+void qprof_end(cudaStream_t s, void *token) {
+  if (!token) return;
+  ProfEntry *pe = (ProfEntry *)token;
+  cudaEventRecord(pe->b, s);
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(*pe);
+  }
+  delete pe;
+}
 extern "C" int qob_profile_enable(int32_t on) {
-  g_prof_on = on != 0;
+  g_prof_on.store(on != 0);
   return QOB_STATUS_OK;
 }
 extern "C" int qob_profile_read(int32_t max_entries, float *ms, int32_t *pass_index, double *alg_bytes, int32_t *count) {
+  std::vector<ProfEntry> taken;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    taken.swap(g_prof);
+  }
   int n = 0;
-  for (ProfEntry &e : g_prof) {
+  for (ProfEntry &e : taken) {
     cudaEventSynchronize(e.b);
     float t = 0.f;
     cudaEventElapsedTime(&t, e.a, e.b);
@@ -992,7 +1019,6 @@ extern "C" int qob_profile_read(int32_t max_entries, float *ms, int32_t *pass_in
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
   }
-  g_prof.clear();
   if (count) *count = n;
   return QOB_STATUS_OK;
 }
@@ -1033,16 +1059,12 @@ int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta,
   for (size_t pi = 0; pi < run.size(); ++pi) {
     const QPassHost *pp = run[pi];
     const bool first = pi == 0;
-    ProfEntry pe;
-    if (g_prof_on) {
-      cudaEventCreate(&pe.a);
-      cudaEventCreate(&pe.b);
-      pe.pass = (int)pi;
-      pe.bytes = ((double)(1ull << h.nbits) * ((first && beta == cplx(0.0, 0.0)) ? 32.0 : 48.0) +
-                  ((o.zadd && pi + 1 == run.size()) ? 16.0 * (double)(1ull << h.nbits) : 0.0)) /
-                 (double)std::max(1, o.nchunks);
-      cudaEventRecord(pe.a, s);
-    }
+    void *prof_token = nullptr;
+    if (qprof_enabled())
+      prof_token = qprof_begin(s, (int)pi,
+                               ((double)(1ull << h.nbits) * ((first && beta == cplx(0.0, 0.0)) ? 32.0 : 48.0) +
+                                ((o.zadd && pi + 1 == run.size()) ? 16.0 * (double)(1ull << h.nbits) : 0.0)) /
+                                   (double)std::max(1, o.nchunks));
     QPassParams P = pp->params;
     P.alpha = make_double2(alpha.real(), alpha.imag());
     P.beta = make_double2(beta.real(), beta.imag());
@@ -1103,10 +1125,7 @@ int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta,
       default: QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: unsupported tile size %d", h.T);
     }
 #undef QT_CASE
-    if (g_prof_on) {
-      cudaEventRecord(pe.b, s);
-      g_prof.push_back(pe);
-    }
+    qprof_end(s, prof_token);
   }
   return QOB_STATUS_OK;
 }

@@ -69,7 +69,7 @@ def test_heisenberg_spot_oracle_and_properties(Q, n):
     rng = np.random.default_rng(100 + n)
     B, Hs, spec = heisenberg(Q, n, rng)
     desc = Q.describe(Hs)
-    assert "qtile" in desc
+    assert "qtile" in desc or "qreg" in desc
     seed, scale = 1234, 2.0 ** (-n / 2)
     x = Q.Ket(B)
     Q.fill_state(x.data, seed, scale)
@@ -113,6 +113,7 @@ def test_tile_kernel_vs_gather_kernel_full_vector(Q, monkeypatch, n, T, L):
     coefs = list(rng.uniform(0.5, 1.5, 3 * n))
     monkeypatch.setenv("QOB_QTILE_T", str(T))
     monkeypatch.setenv("QOB_QTILE_L", str(L))
+    monkeypatch.setenv("QOB_DISABLE_QREG", "1")   # this test pins the round-1 tile kernel; tests/test_gpu_qreg.py covers the new one
     B, Ht, _ = heisenberg(Q, n, rng, coefs)
     x = Q.randstate(B, seed=5)
     yt = Q.Ket(B)

@@ -89,9 +89,31 @@ def chain(Q, n, kind="heis"):
     return B, Q.LazySum([1.0] * len(terms), terms)
 
 
-def test_planner_pass_structure(Q):
-    """N=28 Heisenberg chain: 28 bonds need 3 tile passes at T=12/L=3 (11 + 8 + 8 + wrap), 28 distinct flip masks."""
+def test_planner_pass_structure(Q, monkeypatch):
+    """N=28 Heisenberg chain: 28 bonds need 3 tile passes of 12 free bits (11 + 8 + 8 + wrap), 28 distinct flip masks.
+    Round-2 kernel (qreg): passes 1 and 2 are chained through L2 in one launch (their free bits span 20 index bits =
+    256 chunks of 256 tiles), 3 bonds per pass are register-resident, 19 gathers in total."""
     ctx = Q.context(-1)
+    _, Hs = chain(Q, 28)
+    d = Q.describe(Hs, ctx=ctx)
+    assert "qreg[bits=28,T=12,passes=3,launches=2,components=56]" in d, d
+    assert "{chained chunks=256 x 256 tiles, lag=1: [free:0-11 R:8,9,10,11" in d and "[free:0-2,11-19 R:16,17,18,19" in d, d
+    assert "{single [free:0-2,19-27 R:24,25,26,27" in d, d
+    assert sum(int(v) for v in re.findall(r"in-register:(\d+)", d)) == 9
+    assert sum(int(v) for v in re.findall(r"gathers:(\d+)", d)) == 19
+    # the per-GPU slab of config 5 (2^30 amplitudes): 4 tile passes in 2 chained launches = 2 trips through DRAM
+    _, H30 = chain(Q, 30)
+    d30 = Q.describe(H30, ctx=ctx)
+    assert "qreg[bits=30,T=12,passes=4,launches=2" in d30 and d30.count("{chained") == 2, d30
+    # density-matrix apply: 2N index bits, left terms on the low N, right terms (transposed) on the high N
+    _, Hd = chain(Q, 10)
+    assert "qreg[bits=20" in Q.describe(Hd, "left", 1 << 10, ctx=ctx)
+    assert "qreg[bits=20" in Q.describe(Hd, "right", 1 << 10, ctx=ctx)
+    assert "gather" in Q.describe(Hd, "left", 3, ctx=ctx)  # non power-of-two batch -> generic kernel
+    _, Ht = chain(Q, 12, "tfim")
+    assert "gather[terms=24,maxfac=2]" in Q.describe(Ht, ctx=ctx)
+    # the round-1 tile kernel stays behind it (sharded layouts, states below 2^20 amplitudes)
+    monkeypatch.setenv("QOB_DISABLE_QREG", "1")
     _, Hs = chain(Q, 28)
     d = Q.describe(Hs, ctx=ctx)
     assert "qtile[bits=28,T=12,L=3,passes=3,components=56]" in d, d
@@ -100,13 +122,9 @@ def test_planner_pass_structure(Q):
     assert "lookups:1 diag+0 multi+" in d and ", 5 per thread" in d, d
     assert sum(int(v) for v in re.findall(r"multi\+(\d+) single", d)) == 28
     assert "{free:0-11" in d and "free:0-2,11-19" in d and "free:0-2,19-27" in d
-    _, Ht = chain(Q, 12, "tfim")
-    assert "gather[terms=24,maxfac=2]" in Q.describe(Ht, ctx=ctx)
-    # density-matrix apply: 2N index bits, left terms on the low N, right terms (transposed) on the high N
     _, Hd = chain(Q, 10)
     assert "qtile[bits=20" in Q.describe(Hd, "left", 1 << 10, ctx=ctx)
     assert "qtile[bits=20" in Q.describe(Hd, "right", 1 << 10, ctx=ctx)
-    assert "gather" in Q.describe(Hd, "left", 3, ctx=ctx)  # non power-of-two batch -> generic kernel
 
 
 def test_planner_routes_dense_factors_to_dmma(Q):
