@@ -21,6 +21,19 @@ struct PlanningScope {
   ~PlanningScope() { t_planning_only = prev; }
 };
 
+int qob_device_sm_count() {
+  static std::atomic<int> cache[QOB_MAX_DEVICES];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  const bool cached = dev >= 0 && dev < QOB_MAX_DEVICES;
+  int n = cached ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (cached) cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 static thread_local char t_err[1024] = "";
 void qob_set_error(const char *fmt, ...) {
   va_list ap;
@@ -126,6 +139,7 @@ int hostmat_from_factor(const qob_factor *f, HostMat &out) {
     for (int64_t j = 0; j <= f->ncols; ++j) m.colptr[j] = f->colptr[j] - 1;
     int64_t nnz = m.colptr[f->ncols];
     if (m.colptr[0] != 0 || nnz < 0) QOB_FAIL(QOB_STATUS_INVALID_ARG, "CSC colptr must be 1-based and monotone");
+    if (nnz > 0 && (!f->rowval || !f->nzval)) QOB_FAIL(QOB_STATUS_INVALID_ARG, "CSC factor with %lld stored entries but no rowval / nzval", (long long)nnz);
     m.rowidx.resize(nnz);
     m.vals.resize(nnz);
     for (int64_t j = 0; j < f->ncols; ++j)
@@ -193,9 +207,12 @@ struct qob_op {
   int64_t dl = 0, dr = 0;
   std::atomic<int> refs{1};
   int slot_base;  // scratch slots [slot_base, slot_base+8) belong to this handle
-  qob_op(qob_ctx *c, OpKind k) : ctx(c), kind(k), slot_base(g_slot_counter.fetch_add(8)) {}
+  qob_op(qob_ctx *c, OpKind k) : ctx(c), kind(k), slot_base(g_slot_counter.fetch_add(8)) {
+    if (ctx) ctx->live_ops.fetch_add(1);
+  }
   virtual ~qob_op() {
     if (!ctx) return;
+    ctx->live_ops.fetch_sub(1);
     std::lock_guard<std::mutex> lk(ctx->mu);
     for (auto it = ctx->scratch.begin(); it != ctx->scratch.end();) {
       if (it->first.second >= slot_base && it->first.second < slot_base + 8) {
@@ -212,6 +229,27 @@ struct qob_op {
   virtual int apply(int side, cplx alpha, const void *x, cplx beta, void *y, int64_t batch, cudaStream_t s) = 0;
   virtual std::string describe(int side, int64_t batch) = 0;
 };
+// Switch to the context's device for the duration of an entry point and restore the caller's current device afterwards.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) {
+      err = cudaSetDevice(device);
+      changed = err == cudaSuccess;
+    }
+  }
+  ~DeviceGuard() {
+    if (changed && prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define QOB_DEVICE(dev)                                                                                       \
+  DeviceGuard device_guard__(dev);                                                                            \
+  if (device_guard__.err != cudaSuccess)                                                                      \
+  QOB_FAIL(QOB_STATUS_CUDA_ERROR, "cudaSetDevice(%d) failed: %s", (int)(dev), cudaGetErrorString(device_guard__.err))
+
 static void op_retain(qob_op *o) { o->refs.fetch_add(1); }
 static void op_release(qob_op *o) {
   if (o->refs.fetch_sub(1) == 1) delete o;
@@ -274,8 +312,19 @@ struct TensorGroup {
   std::vector<std::unique_ptr<Compiled>> cache;
   std::vector<cplx> last_coefs;  // coefficients the cached programs were last loaded with
   bool coefs_dirty = true;
-  std::recursive_mutex mu;       // guards the compiled-program cache and the coefficient upload: handles may be applied
-                                 // from several host threads (the reference is reentrant per task, operators_lazytensor.jl:233)
+  std::recursive_mutex mu;       // guards the compiled-program cache, the coefficient upload AND the launches that read the
+                                 // tables: handles may be applied from several host threads and streams (the reference is
+                                 // reentrant per task, operators_lazytensor.jl:233).  The weight tables are one device buffer
+                                 // per program, so an upload has to be ordered against kernels on OTHER streams too:
+  cudaEvent_t ev_upload = nullptr;                 // recorded after the last table upload, on `upload_stream`
+  cudaStream_t upload_stream = nullptr;
+  bool uploaded_once = false;
+  std::map<cudaStream_t, cudaEvent_t> ev_use;      // per stream: recorded after its last launch that read the tables
+  ~TensorGroup() {
+    if (ev_upload) cudaEventDestroy(ev_upload);
+    for (auto &kv : ev_use)
+      if (kv.second) cudaEventDestroy(kv.second);
+  }
 
   int compile(int side, int64_t batch, Compiled **out);
   int apply(int side, cplx alpha, const void *x, cplx beta, void *y, int64_t batch, const std::vector<cplx> &coefs,
@@ -492,8 +541,16 @@ int TensorGroup::apply(int side, cplx alpha, const void *x, cplx beta, void *y, 
   Compiled *cp = nullptr;
   QOB_TRY(compile(side, batch, &cp));
   Compiled &c = *cp;
+  // The lock is held until every launch of this apply is enqueued: the kernels' variant flags (real weight tables) are
+  // read consistently with the tables they were computed from, and the event bookkeeping below is atomic per apply.
   std::unique_lock<std::recursive_mutex> lk(mu);
+  const bool on_device = !t_planning_only && ctx && ctx->device >= 0;
   if (coefs_dirty || coefs != last_coefs) {
+    if (on_device) {
+      // kernels still reading the old tables on other streams must finish before the tables are overwritten
+      for (auto &kv : ev_use)
+        if (kv.first != s && kv.second) QOB_CUDA(cudaStreamWaitEvent(s, kv.second, 0));
+    }
     for (auto &cc : cache) {
       if (cc->has_qreg) QOB_TRY(qreg_set_coefs(cc->qreg, coefs, s));
       if (cc->has_qtile) QOB_TRY(qtile_set_coefs(cc->qtile, coefs, s));
@@ -502,8 +559,26 @@ int TensorGroup::apply(int side, cplx alpha, const void *x, cplx beta, void *y, 
     }
     last_coefs = coefs;
     coefs_dirty = false;
+    if (on_device) {
+      if (!ev_upload) QOB_CUDA(cudaEventCreateWithFlags(&ev_upload, cudaEventDisableTiming));
+      QOB_CUDA(cudaEventRecord(ev_upload, s));
+      upload_stream = s;
+      uploaded_once = true;
+    }
   }
-  lk.unlock();
+  // a launch on another stream than the one that uploaded the tables waits for that upload
+  if (on_device && uploaded_once && s != upload_stream) QOB_CUDA(cudaStreamWaitEvent(s, ev_upload, 0));
+  struct UseMark {  // record "tables in use" on this stream when the apply is done enqueueing
+    TensorGroup *g;
+    cudaStream_t s;
+    bool on;
+    ~UseMark() {
+      if (!on) return;
+      cudaEvent_t &e = g->ev_use[s];
+      if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      if (e) cudaEventRecord(e, s);
+    }
+  } use_mark{this, s, on_device};
   const int64_t pre = side == QOB_SIDE_LEFT ? 1 : batch, post = side == QOB_SIDE_LEFT ? batch : 1;
   bool first = true;
   auto beta_now = [&]() {
@@ -594,6 +669,7 @@ struct SparseOp : qob_op {
 
 struct LazySumOp : qob_op {
   std::vector<cplx> coefs;
+  std::mutex coef_mu;                  // qob_lazysum_set_coefs may race with an apply on another host thread
   std::vector<qob_op *> terms;
   std::unique_ptr<TensorGroup> group;  // fused LazyTensor children
   std::vector<int> group_coef_index;   // child index of every group term
@@ -613,13 +689,18 @@ struct LazySumOp : qob_op {
     const int64_t n_out = (side == QOB_SIDE_LEFT ? dl : dr) * batch;
     // empty sum or alpha == 0: only _zero_op_mul! (src/operators_lazysum.jl:190-192)
     if (terms.empty() || alpha == ZERO) return launch_scale(y, n_out, beta, s);
+    std::vector<cplx> cf;
+    {
+      std::lock_guard<std::mutex> lk(coef_mu);
+      cf = coefs;   // snapshot: one consistent coefficient set per apply
+    }
     bool first = true;
     if (group) {
-      QOB_TRY(group->apply(side, alpha, x, beta, y, batch, coefs, s));
+      QOB_TRY(group->apply(side, alpha, x, beta, y, batch, cf, s));
       first = false;
     }
     for (int i : others) {
-      QOB_TRY(terms[i]->apply(side, alpha * coefs[i], x, first ? beta : ONE, y, batch, s));
+      QOB_TRY(terms[i]->apply(side, alpha * cf[i], x, first ? beta : ONE, y, batch, s));
       first = false;
     }
     return QOB_STATUS_OK;
@@ -720,6 +801,9 @@ int qob_ctx_create(int device, qob_ctx **out) {
 }
 int qob_ctx_destroy(qob_ctx *ctx) {
   if (!ctx) return QOB_STATUS_OK;
+  // handles keep a pointer to their context (scratch pool, streams): destroying it under them would be a use-after-free
+  if (ctx->live_ops.load() > 0)
+    QOB_FAIL(QOB_STATUS_INVALID_ARG, "context still has %d live operator handle(s): destroy them first", ctx->live_ops.load());
   ctx->clear_scratch();
   for (cudaStream_t st : ctx->pipe_streams)
     if (st) cudaStreamDestroy(st);
@@ -1003,7 +1087,7 @@ int qob_lindblad_apply(qob_op *L, qob_c64 alpha, const void *rho, qob_c64 beta, 
   if (!rho || !drho) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null data pointer");
   QOB_TRY(check_alias(rho, n, drho, n));
   if (op->ctx->device < 0) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
-  QOB_CUDA(cudaSetDevice(op->ctx->device));
+  QOB_DEVICE(op->ctx->device);
   if (C(alpha) == ZERO) return launch_scale(drho, n, C(beta), (cudaStream_t)stream);   // only the beta update, like mul!
   return launch_lindblad(op->dev, C(alpha), rho, C(beta), drho, (cudaStream_t)stream);
 }
@@ -1041,6 +1125,7 @@ int qob_lazysum_create(qob_ctx *ctx, int64_t dim_l, int64_t dim_r, int32_t nterm
   op->dr = dim_r;
   for (int i = 0; i < nterms; ++i) {
     if (!terms[i]) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null term %d", i);
+    if (terms[i]->ctx != ctx) QOB_FAIL(QOB_STATUS_INVALID_ARG, "LazySum term %d belongs to another context (device)", i + 1);
     // _check_bases (src/operators_lazysum.jl:6-11): IncompatibleBases -> dimension mismatch here
     if (terms[i]->dl != dim_l || terms[i]->dr != dim_r)
       QOB_FAIL(QOB_STATUS_DIM_MISMATCH, "LazySum term %d has dimensions %lldx%lld, expected %lldx%lld", i + 1,
@@ -1079,6 +1164,8 @@ int qob_lazysum_set_coefs(qob_op *sum, int32_t nterms, const qob_c64 *coefs) {
   if (!sum || sum->kind != OP_LAZYSUM) QOB_FAIL(QOB_STATUS_INVALID_ARG, "not a LazySum handle");
   LazySumOp *s = static_cast<LazySumOp *>(sum);
   if ((size_t)nterms != s->coefs.size()) QOB_FAIL(QOB_STATUS_INVALID_ARG, "LazySum has %d terms, got %d coefficients", (int)s->coefs.size(), nterms);
+  if (!coefs && nterms > 0) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null coefficient array");
+  std::lock_guard<std::mutex> lk(s->coef_mu);
   for (int i = 0; i < nterms; ++i) s->coefs[i] = C(coefs[i]);
   return QOB_STATUS_OK;
 }
@@ -1088,6 +1175,8 @@ int qob_lazyproduct_create(qob_ctx *ctx, int32_t nops, qob_op *const *ops, qob_c
   if (nops < 1 || !ops) QOB_FAIL(QOB_STATUS_INVALID_ARG, "LazyProduct needs at least one operator!");
   for (int i = 0; i < nops; ++i)
     if (!ops[i]) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null operator %d", i);
+  for (int i = 0; i < nops; ++i)
+    if (ops[i]->ctx != ctx) QOB_FAIL(QOB_STATUS_INVALID_ARG, "LazyProduct operator %d belongs to another context (device)", i + 1);
   for (int i = 1; i < nops; ++i)  // check_multiplicable (src/operators_lazyproduct.jl:4-10)
     if (ops[i - 1]->dr != ops[i]->dl) QOB_FAIL(QOB_STATUS_DIM_MISMATCH, "LazyProduct operators %d and %d are not multiplicable", i, i + 1);
   auto op = std::make_unique<LazyProductOp>(ctx);
@@ -1125,7 +1214,7 @@ int qob_op_apply(qob_op *op, int32_t side, qob_c64 alpha, const void *x, qob_c64
   if (!y || (!x && n_in > 0)) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null data pointer");
   QOB_TRY(check_alias(x, n_in, y, n_out));
   if (op->ctx->device < 0) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
-  QOB_CUDA(cudaSetDevice(op->ctx->device));
+  QOB_DEVICE(op->ctx->device);
   return op->apply(side, C(alpha), x, C(beta), y, batch, (cudaStream_t)stream);
 }
 
@@ -1153,12 +1242,15 @@ static int apply_host_pipelined(qob_op *op, cplx alpha, const qob_c64 *x, cplx b
     QOB_TRY(ctx->get_scratch(lane[l], op->slot_base + 6, (size_t)std::max<int64_t>(1, d_in * g) * 16, &dx[l]));
     QOB_TRY(ctx->get_scratch(lane[l], op->slot_base + 7, (size_t)std::max<int64_t>(1, d_out * g) * 16, &dy[l]));
   }
-  cudaEvent_t e_up[2], e_done[2], e_down[2];
-  for (int l = 0; l < 2; ++l) {
-    QOB_CUDA(cudaEventCreateWithFlags(&e_up[l], cudaEventDisableTiming));
-    QOB_CUDA(cudaEventCreateWithFlags(&e_done[l], cudaEventDisableTiming));
-    QOB_CUDA(cudaEventCreateWithFlags(&e_down[l], cudaEventDisableTiming));
-  }
+  struct Events {  // destroyed on every exit path
+    cudaEvent_t e[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~Events() {
+      for (cudaEvent_t v : e)
+        if (v) cudaEventDestroy(v);
+    }
+  } evs;
+  for (int i = 0; i < 6; ++i) QOB_CUDA(cudaEventCreateWithFlags(&evs.e[i], cudaEventDisableTiming));
+  cudaEvent_t *e_up = evs.e, *e_done = evs.e + 2, *e_down = evs.e + 4;
   int rc = QOB_STATUS_OK;
   const int64_t ngroups = (batch + g - 1) / g;
   for (int64_t j = 0; j < ngroups && rc == QOB_STATUS_OK; ++j) {
@@ -1193,11 +1285,6 @@ static int apply_host_pipelined(qob_op *op, cplx alpha, const qob_c64 *x, cplx b
   }
   cudaError_t e1 = cudaStreamSynchronize(up), e2 = cudaStreamSynchronize(lane[0]), e3 = cudaStreamSynchronize(lane[1]),
               e4 = cudaStreamSynchronize(down);
-  for (int l = 0; l < 2; ++l) {
-    cudaEventDestroy(e_up[l]);
-    cudaEventDestroy(e_done[l]);
-    cudaEventDestroy(e_down[l]);
-  }
   if (rc != QOB_STATUS_OK) return rc;
   for (cudaError_t e : {e1, e2, e3, e4})
     if (e != cudaSuccess) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "CUDA error in pipelined host apply: %s", cudaGetErrorString(e));
@@ -1214,7 +1301,7 @@ int qob_op_apply_host(qob_op *op, int32_t side, qob_c64 alpha, const qob_c64 *x,
   if (!x || !y) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null data pointer");
   if ((const void *)x == (const void *)y) QOB_FAIL(QOB_STATUS_ALIASING, "output matrix must not be aliased with input matrix");
   if (op->ctx->device < 0) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
-  QOB_CUDA(cudaSetDevice(op->ctx->device));
+  QOB_DEVICE(op->ctx->device);
   const int64_t d_in = side == QOB_SIDE_LEFT ? op->dr : op->dl, d_out = side == QOB_SIDE_LEFT ? op->dl : op->dr;
   // A batch of kets (LEFT side: the columns are contiguous) that is large enough is streamed through the device in column
   // groups: group j+1 goes up on one copy engine while group j is applied and group j-1 comes down on the other, so the
@@ -1344,7 +1431,7 @@ int qob_layout_plan_apply(qob_op *sum, int32_t plan_id, qob_c64 alpha, const voi
   cudaStream_t s = (cudaStream_t)stream;
   if (!x || !y) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null data pointer");
   QOB_TRY(check_alias(x, n, y, n));
-  QOB_CUDA(cudaSetDevice(S->ctx->device));
+  QOB_DEVICE(S->ctx->device);
   if (C(alpha) == ZERO) return launch_scale(y, n, C(beta), s);
   QOB_TRY(qtile_set_coefs(lp.prog, S->coefs, s));
   return qtile_launch(lp.prog, C(alpha), x, C(beta), y, s);
@@ -1382,7 +1469,7 @@ int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const 
     QOB_TRY(check_alias(x, n, y, n));
     if (zadd) QOB_TRY(check_alias(zadd, n, y, n));
   }
-  QOB_CUDA(cudaSetDevice(S->ctx->device));
+  QOB_DEVICE(S->ctx->device);
   if (C(alpha) == ZERO) {
     if (npeers > 0) QOB_FAIL(QOB_STATUS_INVALID_ARG, "alpha == 0 in the peer-addressed form");
     if (zadd) return launch_axpby(zadd, y, n, ONE, C(beta), s);

@@ -36,6 +36,10 @@ void qob_set_error(const char *fmt, ...);
     if (s__ != QOB_STATUS_OK) return s__; \
   } while (0)
 
+#define QOB_MAX_DEVICES 64
+// SM count of the CURRENT device (cached per device; a process may drive several devices, one qob_ctx each)
+int qob_device_sm_count();
+
 extern std::atomic<int64_t> g_launch_count;
 // set by the ABI entry points while they work for a planning-only context (device < 0): device uploads
 // become no-ops so that validation and planning can be exercised (and tested) on a box without a GPU.
@@ -69,6 +73,7 @@ struct qob_ctx {
   int device = 0;
   int sm_count = 148;
   size_t smem_optin = 0;
+  std::atomic<int> live_ops{0};   // operator handles created on this context and not yet destroyed
   std::mutex mu;
   // scratch slots keyed by (stream, slot): the analogue of the reference's LRU temp cache keyed by
   // (stage symbol, task id) — operators_lazytensor.jl:303-315

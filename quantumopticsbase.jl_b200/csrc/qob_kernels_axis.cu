@@ -310,10 +310,16 @@ static int launch_axis_pipe(const AxisParams &P, const double2 *xp, double2 *yp,
   int ldx = kpad;
   while (ldx % 8 != 4) ++ldx;  // conflict-free LDS.128 fragment loads
   const size_t smem = (size_t)(16 * MW + 2 * TN) * ldx * sizeof(double2);
-  static size_t configured = 0;
-  if (smem > configured) {
-    QOB_CUDA(cudaFuncSetAttribute(axis_dmma_pipe_kernel<MW, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  {
+    // the opt-in is per device: remember the largest size configured on each
+    static std::atomic<size_t> configured[QOB_MAX_DEVICES];
+    int dev = 0;
+    QOB_CUDA(cudaGetDevice(&dev));
+    const int slot = dev >= 0 && dev < QOB_MAX_DEVICES ? dev : 0;
+    if (dev != slot || smem > configured[slot].load(std::memory_order_relaxed)) {
+      QOB_CUDA(cudaFuncSetAttribute(axis_dmma_pipe_kernel<MW, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[slot].store(smem, std::memory_order_relaxed);
+    }
   }
   const int per_sm = (NB == 1 && MW <= 3 && 2 * (smem + 1024) <= 227 * 1024) ? 2 : 1;
   const long long ntiles = (P.N + TN - 1) / TN;
@@ -324,12 +330,7 @@ static int launch_axis_pipe(const AxisParams &P, const double2 *xp, double2 *yp,
 
 template <int MW>
 static int launch_axis_wk(const AxisParams &P, const double2 *xp, double2 *yp, cudaStream_t s) {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int sms = qob_device_sm_count();
   static const int nb_env = getenv("QOB_AXIS_NB") ? atoi(getenv("QOB_AXIS_NB")) : 1;
   if (nb_env == 2) return launch_axis_pipe<MW, 2>(P, xp, yp, sms, s);
   return launch_axis_pipe<MW, 1>(P, xp, yp, sms, s);

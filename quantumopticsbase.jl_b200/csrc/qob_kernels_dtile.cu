@@ -969,10 +969,16 @@ int dtile_set_coefs(DTileProgram &prog, const std::vector<cplx> &coefs, cudaStre
 int dtile_launch(const DTileProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s) {
   DTileProgramHost &H = *prog.h;
   if (t_planning_only) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    auto set = [](const void *f) {
+  // the shared-memory opt-in is per device: once per (process, device)
+  static std::once_flag once[QOB_MAX_DEVICES];
+  static cudaError_t attr_errs[QOB_MAX_DEVICES];
+  int cur_dev = 0;
+  QOB_CUDA(cudaGetDevice(&cur_dev));
+  if (cur_dev < 0 || cur_dev >= QOB_MAX_DEVICES) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "device ordinal %d out of range", cur_dev);
+  cudaError_t &attr_err = attr_errs[cur_dev];
+  std::call_once(once[cur_dev], [&attr_err] {
+    attr_err = cudaSuccess;
+    auto set = [&attr_err](const void *f) {
       if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     };
     set((const void *)dtile_kernel<true, true, true>);

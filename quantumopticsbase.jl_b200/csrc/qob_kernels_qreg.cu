@@ -41,26 +41,28 @@
 #define QR_DIAG_WINDOW 6
 
 // classes of lookup records; records of a pass are sorted by class
-enum { QR_PRE = 0, QR_DIAGR = 1, QR_INREG = 2, QR_GATHER = 3, QR_GATHER_SLOW = 4 };
+enum { QR_PRE_TILE = 0, QR_PRE = 1, QR_DIAGR = 2, QR_INREG = 3, QR_GATHER = 4, QR_GATHER_SLOW = 5 };
 
-struct QRComp {       // 80 bytes
+// A thread owns the 16 amplitudes whose tile-local index bits 8..11 ("R bits") vary: amplitude u of thread t sits at byte
+// t*16 + u*4096 of the staged tile, so every shared-memory access of the hot loops is [thread base + immediate].
+struct QRComp {       // 32 bytes
   uint32_t kind;      // class | SELR << 4 | M << 8   (SELR: which of the 4 R bits select the weight; M: flip mask inside R)
   uint32_t tabE;      // first entry of the weight table inside the pass table
-  uint32_t sel;       // bit-field runs (<= 3) of the selector bits OUTSIDE R in the flat index: 9 bits each: shift (6) | width (3)
-  uint32_t xorT;      // gather: XOR applied to the thread's byte offset inside the tile (mask bits on thread positions)
-  uint32_t goff[16];  // gather: byte offset of the R part of the partner of amplitude u (= uoffB[u ^ M])
+  uint32_t selT;      // selector bits among the 8 thread bits: bit-field runs of the thread id, 9 bits each: shift (6) | width (3)
+  uint32_t selG;      // selector bits among the tile-id / rank bits: bit-field runs of the 64-bit flat index
+  uint32_t xorB;      // gather: XOR applied to the thread's byte offset inside the tile (thread bits and R bits of the mask)
+  uint32_t nT;        // number of selector bits among the thread bits (the tile part of the table index is shifted by it)
+  uint32_t pad[2];
 };
 
 struct QRPass {
-  uint32_t uoffB[16];             // byte offset inside the staged tile of amplitude u of a thread
-  unsigned long long ugoff[16];   // element offset in global memory of amplitude u of a thread
-  unsigned char tpos[8];          // consumer-thread bit b -> tile-local bit position
+  unsigned long long rstride[4];  // element stride in global memory of R bit k
   unsigned char tgbit[8];         // consumer-thread bit b -> flat-index bit
   int nfixed_seg;                 // compact tile id -> element offset of the tile
   unsigned char xs_l[QR_MAXSEG], xs_n[QR_MAXSEG], xs_g[QR_MAXSEG];
   int rank;                       // tensor-map rank; coordinate d = ((tile >> tshift) & (2^tbits - 1)) << boxlog
   unsigned char dim_tshift[5], dim_tbits[5], dim_boxlog[5];
-  int n_pre, n_diagr, n_inreg, n_gather;  // records: [pre | diagR | in-register | gather]
+  int n_pretile, n_pre, n_diagr, n_inreg, n_gather;  // records: [pre (tile) | pre (thread) | diagR | in-register | gather]
   unsigned long long hi_or;       // index bits above the local address (rank of a sharded state), already shifted
   uint32_t tab_smem_off;          // byte offset of this pass's tables inside the shared-memory table area
   uint32_t tab_bytes;
@@ -80,8 +82,10 @@ struct QRLaunch {
   unsigned tpc_log2;     // log2(tiles per chunk and pass)
   unsigned nchunks, lag; // chunks; pass 2 runs `lag` chunks behind pass 1
   unsigned total_items;
+  int prefetch;          // work items the producer runs ahead with L2 prefetches of their tiles
   unsigned *queue;       // work counter
   unsigned *done;        // per chunk: finished pass-1 tiles
+  long long *stats;      // debug (QOB_QREG_STATS=1): per-CTA cycle counts of the pipeline phases, 16 per CTA
   double2 alpha, beta;
   QRPass pass[2];
 };
@@ -137,6 +141,26 @@ __device__ __forceinline__ void qr_tma_load(unsigned dst, const CUtensorMap *map
       break;
   }
 }
+// pull a tile into L2 without occupying shared memory (the DRAM latency is paid here, several tiles ahead)
+__device__ __forceinline__ void qr_tma_prefetch(const CUtensorMap *map, int rank, const int *c) {
+  const unsigned long long m = (unsigned long long)map;
+  switch (rank) {
+    case 1: asm volatile("cp.async.bulk.prefetch.tensor.1d.L2.global.tile [%0, {%1}];\n" ::"l"(m), "r"(c[0]) : "memory"); break;
+    case 2: asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(m), "r"(c[0]), "r"(c[1]) : "memory"); break;
+    case 3:
+      asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];\n" ::"l"(m), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory");
+      break;
+    case 4:
+      asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];\n" ::"l"(m), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3])
+                   : "memory");
+      break;
+    default:
+      asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];\n" ::"l"(m), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]),
+                   "r"(c[4])
+                   : "memory");
+      break;
+  }
+}
 
 __host__ __device__ constexpr int qr_popc(int v) { return (v & 1) + ((v >> 1) & 1) + ((v >> 2) & 1) + ((v >> 3) & 1); }
 __host__ __device__ constexpr int qr_pext(int u, int sel) {
@@ -166,7 +190,7 @@ __device__ __forceinline__ unsigned qr_deposit(unsigned v, int nseg, const unsig
   return a;
 }
 
-// table index (in entries) of the selector bits outside R: up to three bit-field runs of the 64-bit flat index
+// table index (in entries) of selector bits given as up to three bit-field runs of a 64-bit (32-bit) value
 __device__ __forceinline__ unsigned qr_run(unsigned sel, int r, unsigned lo, unsigned hi, unsigned pos) {
   const unsigned sh = (sel >> (9 * r)) & 63u, w = (sel >> (9 * r + 6)) & 7u;
   const unsigned v = sh < 32 ? __funnelshift_r(lo, hi, sh) : (hi >> (sh & 31));
@@ -179,6 +203,22 @@ __device__ __forceinline__ unsigned qr_field(unsigned sel, unsigned lo, unsigned
     idx |= qr_run(sel, 1, lo, hi, w0);
     if (sel >> 18) idx |= qr_run(sel, 2, lo, hi, w0 + w1);
   }
+  return idx;
+}
+__device__ __forceinline__ unsigned qr_field32(unsigned sel, unsigned v) {
+  unsigned idx = (v >> (sel & 63u)) & ((1u << ((sel >> 6) & 7u)) - 1u);
+  if (sel >> 9) {
+    const unsigned w0 = (sel >> 6) & 7u, w1 = (sel >> 15) & 7u;
+    idx |= ((v >> ((sel >> 9) & 63u)) & ((1u << w1) - 1u)) << w0;
+    if (sel >> 18) idx |= ((v >> ((sel >> 18) & 63u)) & ((1u << ((sel >> 24) & 7u)) - 1u)) << (w0 + w1);
+  }
+  return idx;
+}
+// index of the selector bits outside R: thread part | tile part << nT; most records have neither
+__device__ __forceinline__ unsigned qr_index(const QRComp &cd, unsigned tid, unsigned g_lo, unsigned g_hi) {
+  unsigned idx = 0;
+  if (cd.selT) idx = qr_field32(cd.selT, tid);
+  if (cd.selG) idx |= qr_field(cd.selG, g_lo, g_hi) << cd.nT;
   return idx;
 }
 
@@ -219,10 +259,10 @@ __device__ __forceinline__ void qr_inreg(double2 (&acc)[16], const double2 (&xr)
 #pragma unroll
   for (int u = 0; u < 16; ++u) w[qr_pext(u, SELR)].fma_into(acc[u], xr[u ^ M]);
 }
-// bond that leaves the thread: one LDS.128 per amplitude, weights hoisted
-template <bool REALW, int SELR>
-__device__ __forceinline__ void qr_gather(double2 (&acc)[16], const unsigned char *xt, const uint32_t (&goff)[16],
-                                          const unsigned char *wt) {
+// bond that leaves the thread: one LDS.128 per amplitude, weights hoisted.  The partner of amplitude u sits at
+// [xt + (u ^ M)*4096]: an immediate offset when the mask has no R bit (MR == false), one XOR per amplitude otherwise.
+template <bool REALW, int SELR, bool MR>
+__device__ __forceinline__ void qr_gather(double2 (&acc)[16], const unsigned char *xt, const unsigned char *wt, unsigned mxor) {
   constexpr int NW = 1 << qr_popc(SELR);
   QRW<REALW> w[NW];
 #pragma unroll
@@ -231,15 +271,16 @@ __device__ __forceinline__ void qr_gather(double2 (&acc)[16], const unsigned cha
   for (int h = 0; h < 2; ++h) {
     double2 v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const double2 *>(xt + goff[8 * h + u]);
+    for (int u = 0; u < 8; ++u)
+      v[u] = *reinterpret_cast<const double2 *>(xt + (MR ? (((8 * h + u) * 4096u) ^ mxor) : (8 * h + u) * 4096u));
 #pragma unroll
     for (int u = 0; u < 8; ++u) w[qr_pext(8 * h + u, SELR)].fma_into(acc[8 * h + u], v[u]);
   }
 }
 // any selector pattern: weight looked up per amplitude
 template <bool REALW>
-__device__ __forceinline__ void qr_gather_slow(double2 (&acc)[16], const unsigned char *xt, const uint32_t (&goff)[16],
-                                               const unsigned char *wt, unsigned selr) {
+__device__ __forceinline__ void qr_gather_slow(double2 (&acc)[16], const unsigned char *xt, const unsigned char *wt, unsigned selr,
+                                               unsigned mxor) {
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
     unsigned r = 0, k = 0;
@@ -251,16 +292,17 @@ __device__ __forceinline__ void qr_gather_slow(double2 (&acc)[16], const unsigne
       }
     QRW<REALW> w;
     w.load(wt + r * (REALW ? 8 : 16));
-    const double2 v = *reinterpret_cast<const double2 *>(xt + goff[u]);
+    const double2 v = *reinterpret_cast<const double2 *>(xt + ((u * 4096u) ^ mxor));
     w.fma_into(acc[u], v);
   }
 }
 
-struct QRItem {
-  int pass;        // -1: no more work
-  unsigned tile;   // compact tile id
+struct QRItem {     // 32 bytes, written by the producer for the consumers
+  int pass;         // -1: no more work
+  unsigned tile;    // compact tile id
   unsigned chunk;
   unsigned pad;
+  double dre, dim;  // diagonal weight that is the same for every amplitude of the tile
 };
 
 // work item -> (pass, chunk, tile within chunk); false when the queue is exhausted
@@ -326,40 +368,104 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
   __syncthreads();
 
   if (tid >= QR_CTHREADS) {
-    // ------------------------------------------------------------------ producer (one thread)
-    if (tid == QR_CTHREADS) {
-      unsigned long long pol_keep, pol_stream;
-      asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-      unsigned stage = 0, xphase = 0, yphase = 0;  // bit s of xphase: parity of the next wait on x-empty[s]
-      while (true) {
-        const unsigned item = atomicAdd(L.queue, 1u);
-        int p = 0;
-        unsigned c = 0, j = 0;
-        const bool more = qr_decode(L, item, p, c, j);
+    // ------------------------------------------------------------------ producer warp
+    // Work items are dealt round-robin (item = blockIdx.x + k*gridDim.x, in queue order), so the warp knows its future
+    // tiles: lane 0 pulls the tile `prefetch` items ahead into L2 (the DRAM latency is paid there, without holding shared
+    // memory) and issues the TMA loads of the current one; all lanes evaluate the diagonal tables whose selector bits are
+    // tile-id bits (one table per lane).
+    const unsigned lane = tid & 31u;
+    unsigned long long pol_keep, pol_stream;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    unsigned stage = 0, xphase = 0, yphase = 0;  // bit s of xphase: parity of the next wait on x-empty[s]
+    auto tile_of = [&](unsigned item, int &p, unsigned &t, unsigned &c) -> bool {
+      unsigned j = 0;
+      if (!qr_decode(L, item, p, c, j)) return false;
+      const QRPass &P = L.pass[p];
+      t = L.npass == 1 ? j : (qr_deposit(c, P.ncs, P.cs_l, P.cs_n, P.cs_d) | qr_deposit(j, P.njs, P.js_l, P.js_n, P.js_d));
+      return true;
+    };
+    auto prefetch_item = [&](unsigned item) {
+      int p = 0;
+      unsigned t = 0, c = 0;
+      if (!tile_of(item, p, t, c)) return;
+      const QRPass &P = L.pass[p];
+      if (P.wait) return;  // tiles of a waiting pass are already in L2 (that is the point of the chaining)
+      int co[5];
+#pragma unroll
+      for (int d = 0; d < 5; ++d) co[d] = (int)(((t >> P.dim_tshift[d]) & ((1u << P.dim_tbits[d]) - 1u)) << P.dim_boxlog[d]);
+      qr_tma_prefetch(p ? &mx1 : &mx0, P.rank, co);
+      if (P.mode != 0) qr_tma_prefetch(p ? &my1 : &my0, P.rank, co);
+    };
+    const unsigned ahead = L.prefetch > 0 ? (unsigned)L.prefetch : 0u;
+    if (lane == 0)
+      for (unsigned k = 0; k < ahead; ++k) prefetch_item(blockIdx.x + k * gridDim.x);
+    long long st_ex = 0, st_dep = 0, st_ey = 0, st_tot = 0, st_n = 0;
+    const long long st_t0 = clock64();
+    for (unsigned item = blockIdx.x;; item += gridDim.x) {
+      int p = 0;
+      unsigned t = 0, c = 0;
+      const bool more = tile_of(item, p, t, c);   // every lane decodes: no broadcast needed
+      if (lane == 0) {
+        if (ahead > 0) prefetch_item(item + ahead * gridDim.x);
+        const long long q0 = clock64();
         qr_mbar_wait(qr_smem(bars + 2 + stage), ((xphase >> stage) & 1u) ^ 1u);
+        st_ex += clock64() - q0;
         xphase ^= 1u << stage;
-        QRItem it;
-        it.pass = more ? p : -1;
-        it.chunk = c;
-        it.pad = 0;
-        if (!more) {
-          it.tile = 0;
+      }
+      if (!more) {
+        if (lane == 0) {
+          QRItem it;
+          it.pass = -1;
+          it.tile = it.chunk = it.pad = 0;
+          it.dre = it.dim = 0.0;
           slots[stage] = it;
           qr_mbar_arrive(qr_smem(bars + stage));
-          break;
+          if (L.stats) {
+            long long *o = L.stats + 16 * blockIdx.x;
+            o[0] = st_ex, o[1] = st_dep, o[2] = st_ey, o[3] = clock64() - st_t0, o[4] = st_n;
+          }
         }
-        const QRPass &P = L.pass[p];
-        const unsigned t = L.npass == 1 ? j : (qr_deposit(c, P.ncs, P.cs_l, P.cs_n, P.cs_d) | qr_deposit(j, P.njs, P.js_l, P.js_n, P.js_d));
+        break;
+      }
+      ++st_n;
+      const QRPass &P = L.pass[p];
+      // tile-constant diagonal weight: lane k evaluates table k
+      double dre = 0.0, dim = 0.0;
+      if (P.n_pretile > 0) {
+        const unsigned long long gidx = qr_expand(t, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g) | P.hi_or;
+        const unsigned char *tb = tabs + P.tab_smem_off;
+        for (int k = (int)lane; k < P.n_pretile; k += 32) {
+          const QRComp &cd = P.comps[k];
+          QRW<REALW> w;
+          w.load(tb + (size_t)(cd.tabE + qr_field(cd.selG, (unsigned)gidx, (unsigned)(gidx >> 32))) * WB);
+          dre += w.re;
+          dim += w.im;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          dre += __shfl_xor_sync(0xffffffffu, dre, o);
+          dim += __shfl_xor_sync(0xffffffffu, dim, o);
+        }
+      }
+      if (lane == 0) {
+        QRItem it;
+        it.pass = p;
         it.tile = t;
+        it.chunk = c;
+        it.pad = 0;
+        it.dre = dre;
+        it.dim = dim;
         slots[stage] = it;
         if (P.wait) {
-          const unsigned need = 1u << L.tpc_log2;
+          const unsigned need = (QR_CTHREADS / 32u) << L.tpc_log2;   // every consumer warp of every pass-1 tile of the chunk
           unsigned have;
+          const long long q0 = clock64();
           do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(L.done + c) : "memory");
             if (have < need) __nanosleep(64);
           } while (have < need);
+          st_dep += clock64() - q0;
           asm volatile("fence.proxy.async;\n" ::: "memory");  // the tiles written by other CTAs are read by the async proxy
         }
         int co[5];
@@ -369,13 +475,16 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
         qr_mbar_expect(qr_smem(bars + stage), QR_TILE_BYTES);
         qr_tma_load(qr_smem(xs0 + stage * QR_TILE_BYTES), p ? &mx1 : &mx0, qr_smem(bars + stage), P.rank, co, pol);
         if (P.mode != 0) {
+          const long long q0 = clock64();
           qr_mbar_wait(qr_smem(bars + 5), (yphase & 1u) ^ 1u);
+          st_ey += clock64() - q0;
           yphase ^= 1u;
           qr_mbar_expect(qr_smem(bars + 4), QR_TILE_BYTES);
           qr_tma_load(qr_smem(ysb), p ? &my1 : &my0, qr_smem(bars + 4), P.rank, co, pol);
         }
-        stage ^= 1u;
       }
+      __syncwarp();
+      stage ^= 1u;
     }
     return;
   }
@@ -383,42 +492,48 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
   // -------------------------------------------------------------------- consumers
   unsigned long long pol_stream;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  // element offset in global memory of this thread's amplitude u = 0, for either pass
+  unsigned long long go0 = 0, go1 = 0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b)
+    if ((tid >> b) & 1u) {
+      go0 |= 1ull << L.pass[0].tgbit[b];
+      go1 |= 1ull << L.pass[1].tgbit[b];
+    }
+  const unsigned so = tid * 16u;
   unsigned stage = 0, xphase = 0, yphase = 0;
+  long long sc_wx = 0, sc_cmp = 0, sc_wy = 0, sc_epi = 0;
 #pragma unroll 1
   while (true) {
+    long long q0 = clock64();
     qr_mbar_wait(qr_smem(bars + stage), (xphase >> stage) & 1u);
+    long long q1 = clock64();
+    sc_wx += q1 - q0;
     xphase ^= 1u << stage;
     const QRItem it = slots[stage];
     if (it.pass < 0) break;
     const QRPass &P = L.pass[it.pass];
     const unsigned char *xs = xs0 + stage * QR_TILE_BYTES;
     const unsigned char *tb = tabs + P.tab_smem_off;
-    // thread part of the tile-local byte offset and of the global element offset
-    unsigned so = 0;
-    unsigned long long go = 0;
-#pragma unroll
-    for (int b = 0; b < 8; ++b)
-      if ((tid >> b) & 1u) {
-        so |= 16u << P.tpos[b];
-        go |= 1ull << P.tgbit[b];
-      }
+    const unsigned long long go = it.pass ? go1 : go0;
     const unsigned long long tbase = qr_expand(it.tile, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g);
-    const unsigned long long gidx = tbase | go | P.hi_or;
+    const unsigned long long gidx = tbase | P.hi_or;   // the thread bits enter the lookups through `tid` (selT)
     const unsigned g_lo = (unsigned)gidx, g_hi = (unsigned)(gidx >> 32);
 
     double2 acc[16];
     {
       double2 xr[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) xr[u] = *reinterpret_cast<const double2 *>(xs + so + P.uoffB[u]);
-      int c = 0;
-      if (P.n_pre + P.n_diagr > 0) {
-        // diagonal weight: tables whose selector bits are fixed for the thread, plus tables indexed by the R bits
-        double dre = 0.0, dim = 0.0;
-        for (; c < P.n_pre; ++c) {
+      for (int u = 0; u < 16; ++u) xr[u] = *reinterpret_cast<const double2 *>(xs + so + u * 4096);
+      int c = P.n_pretile;
+      const int c_diag_end = P.n_pretile + P.n_pre + P.n_diagr;
+      if (c_diag_end > 0) {
+        // diagonal weight: tile constant (from the producer) + tables on thread bits + tables indexed by the R bits
+        double dre = it.dre, dim = it.dim;
+        for (; c < P.n_pretile + P.n_pre; ++c) {
           const QRComp &cd = P.comps[c];
           QRW<REALW> w;
-          w.load(tb + (size_t)(cd.tabE + qr_field(cd.sel, g_lo, g_hi)) * WB);
+          w.load(tb + (size_t)(cd.tabE + qr_index(cd, tid, g_lo, g_hi)) * WB);
           dre += w.re;
           dim += w.im;
         }
@@ -428,9 +543,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
           d[u].re = dre;
           d[u].im = dim;
         }
-        for (; c < P.n_pre + P.n_diagr; ++c) {
+        for (; c < c_diag_end; ++c) {
           const QRComp &cd = P.comps[c];
-          const unsigned char *wt = tb + (size_t)(cd.tabE + qr_field(cd.sel, g_lo, g_hi) * 16u) * WB;
+          const unsigned char *wt = tb + (size_t)(cd.tabE + qr_index(cd, tid, g_lo, g_hi) * 16u) * WB;
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             QRW<REALW> w;
@@ -448,11 +563,11 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
 #pragma unroll
         for (int u = 0; u < 16; ++u) acc[u] = make_double2(0.0, 0.0);
       }
-      const int c_in_end = P.n_pre + P.n_diagr + P.n_inreg;
-      for (; c < c_in_end; ++c) {
+      const int c_in_end = c_diag_end + P.n_inreg;
+      for (c = c_diag_end; c < c_in_end; ++c) {
         const QRComp &cd = P.comps[c];
         const unsigned sr = __popc((cd.kind >> 4) & 15u);
-        const unsigned char *wt = tb + (size_t)(cd.tabE + (qr_field(cd.sel, g_lo, g_hi) << sr)) * WB;
+        const unsigned char *wt = tb + (size_t)(cd.tabE + (qr_index(cd, tid, g_lo, g_hi) << sr)) * WB;
         switch (cd.kind >> 4) {  // SELR | M << 4, SELR == M
 #define QR_IN(MM) \
   case (MM | (MM << 4)): qr_inreg<REALW, MM, MM>(acc, xr, wt); break;
@@ -463,38 +578,53 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
       }
     }
     {
-      const int c0 = P.n_pre + P.n_diagr + P.n_inreg, c1 = c0 + P.n_gather;
+      const int c0 = P.n_pretile + P.n_pre + P.n_diagr + P.n_inreg, c1 = c0 + P.n_gather;
       for (int c = c0; c < c1; ++c) {
         const QRComp &cd = P.comps[c];
         const unsigned selr = (cd.kind >> 4) & 15u;
         const unsigned sr = __popc(selr);
-        const unsigned char *wt = tb + (size_t)(cd.tabE + (qr_field(cd.sel, g_lo, g_hi) << sr)) * WB;
-        const unsigned char *xt = xs + (so ^ cd.xorT);
+        const unsigned char *wt = tb + (size_t)(cd.tabE + (qr_index(cd, tid, g_lo, g_hi) << sr)) * WB;
+        const unsigned char *xt = xs + (so ^ cd.xorB);   // xorB: thread bits of the mask only
+        const unsigned mxor = ((cd.kind >> 8) & 15u) << 12;  // R bits of the mask
         if ((cd.kind & 15u) == QR_GATHER) {
-          switch (selr) {
+          if (mxor == 0) {
+            switch (selr) {
 #define QR_GA(SS) \
-  case SS: qr_gather<REALW, SS>(acc, xt, cd.goff, wt); break;
-            QR_GA(0) QR_GA(1) QR_GA(2) QR_GA(4) QR_GA(8) QR_GA(3) QR_GA(5) QR_GA(6) QR_GA(9) QR_GA(10) QR_GA(12)
+  case SS: qr_gather<REALW, SS, false>(acc, xt, wt, 0u); break;
+              QR_GA(0) QR_GA(1) QR_GA(2) QR_GA(4) QR_GA(8) QR_GA(3) QR_GA(5) QR_GA(6) QR_GA(9) QR_GA(10) QR_GA(12)
 #undef QR_GA
-            default: break;
+              default: break;
+            }
+          } else {
+            switch (selr) {
+#define QR_GA(SS) \
+  case SS: qr_gather<REALW, SS, true>(acc, xt, wt, mxor); break;
+              QR_GA(0) QR_GA(1) QR_GA(2) QR_GA(4) QR_GA(8) QR_GA(3) QR_GA(5) QR_GA(6) QR_GA(9) QR_GA(10) QR_GA(12)
+#undef QR_GA
+              default: break;
+            }
           }
         } else {
-          qr_gather_slow<REALW>(acc, xt, cd.goff, wt, selr);
+          qr_gather_slow<REALW>(acc, xt, wt, selr, mxor);
         }
       }
     }
     // all reads of this x stage are done
     __syncwarp();
     if ((tid & 31u) == 0) qr_mbar_arrive(qr_smem(bars + 2 + stage));
+    q0 = clock64();
+    sc_cmp += q0 - q1;
 
     // ---- epilogue
-    double2 *yt = y + tbase + go;
     if (P.mode != 0) {
       qr_mbar_wait(qr_smem(bars + 4), yphase & 1u);
+      q1 = clock64();
+      sc_wy += q1 - q0;
+      q0 = q1;
       yphase ^= 1u;
       double2 yo[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) yo[u] = *reinterpret_cast<const double2 *>(ysb + so + P.uoffB[u]);
+      for (int u = 0; u < 16; ++u) yo[u] = *reinterpret_cast<const double2 *>(ysb + so + u * 4096);
       __syncwarp();
       if ((tid & 31u) == 0) qr_mbar_arrive(qr_smem(bars + 5));
       if (P.mode == 1) {
@@ -512,23 +642,36 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
       for (int u = 0; u < 16; ++u)
         acc[u] = make_double2(L.alpha.x * acc[u].x - L.alpha.y * acc[u].y, L.alpha.x * acc[u].y + L.alpha.y * acc[u].x);
     }
-    if (P.stream_out) {
+    {
+      double2 *yp[16];
+      yp[0] = y + tbase + go;
 #pragma unroll
-      for (int u = 0; u < 16; ++u)
-        asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(yt + P.ugoff[u]), "d"(acc[u].x), "d"(acc[u].y), "l"(pol_stream)
-                     : "memory");
-    } else {
+      for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int u = 0; u < 16; ++u) yt[P.ugoff[u]] = acc[u];
+        for (int u = 0; u < (1 << k); ++u) yp[(1 << k) + u] = yp[u] + P.rstride[k];
+      if (P.stream_out) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(yp[u]), "d"(acc[u].x), "d"(acc[u].y), "l"(pol_stream) : "memory");
+      } else {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) *yp[u] = acc[u];
+      }
     }
-    if (P.signal) {
-      asm volatile("bar.sync 1, %0;\n" ::"n"(QR_CTHREADS) : "memory");
-      if (tid == 0) {
+    if (P.signal) {  // one count per consumer warp: no CTA-wide barrier
+      __syncwarp();
+      if ((tid & 31u) == 0) {
         __threadfence();
         atomicAdd(L.done + it.chunk, 1u);
       }
     }
+    sc_epi += clock64() - q0;
     stage ^= 1u;
+  }
+  if (L.stats && (tid & 31u) == 0) {
+    long long *o = L.stats + 16 * blockIdx.x + 8;
+    if (tid == 0) o[0] = sc_wx, o[1] = sc_cmp, o[2] = sc_wy, o[3] = sc_epi;
+    if (tid == 224) o[4] = sc_wx, o[5] = sc_cmp, o[6] = sc_wy, o[7] = sc_epi;
   }
 }
 
@@ -659,28 +802,12 @@ static void qr_fill_tables(QRegProgramHost &h, const std::vector<cplx> &coefs) {
   h.real_tables = real && !getenv("QOB_QTILE_NO_REALW");
 }
 
-// tile-local bit positions -> the thread / amplitude split and every offset table of a pass
+// tile-local bit positions 0..7 belong to the thread id, 8..11 are the R bits (the thread's 16 amplitudes)
 static void qr_layout(QRPassHost &ph, int nbits, uint64_t hi_value) {
   QRPass &P = ph.params;
   const std::vector<int> &fb = ph.free_bits;
-  for (int u = 0; u < 16; ++u) {
-    uint32_t o = 0;
-    unsigned long long g = 0;
-    for (int k = 0; k < 4; ++k)
-      if ((u >> k) & 1) {
-        o |= 16u << ph.rpos[k];
-        g |= 1ull << fb[ph.rpos[k]];
-      }
-    P.uoffB[u] = o;
-    P.ugoff[u] = g;
-  }
-  int b = 0;
-  for (int pos = 0; pos < QR_T; ++pos) {
-    if (std::find(ph.rpos.begin(), ph.rpos.end(), pos) != ph.rpos.end()) continue;
-    P.tpos[b] = (unsigned char)pos;
-    P.tgbit[b] = (unsigned char)fb[pos];
-    ++b;
-  }
+  for (int k = 0; k < 4; ++k) P.rstride[k] = 1ull << fb[8 + k];
+  for (int b = 0; b < 8; ++b) P.tgbit[b] = (unsigned char)fb[b];
   std::vector<int> fixed;
   for (int i = 0; i < nbits; ++i)
     if (std::find(fb.begin(), fb.end(), i) == fb.end()) fixed.push_back(i);
@@ -769,8 +896,10 @@ static int qr_encode_map(const QRPassHost &ph, const void *base, CUtensorMap *ou
   return QOB_STATUS_OK;
 }
 
-// merge diagonal components whose selector bits avoid R into tables over windows of <= QR_DIAG_WINDOW bits
-static void qr_merge_pre(const QRegProgramHost &h, std::vector<int> ids, std::vector<QRTableHost> &out) {
+// merge diagonal components into tables over <= QR_DIAG_WINDOW selector bits; `ok(bits)` says whether a bit set can be
+// addressed by one record (bit-field runs)
+template <class OK>
+static void qr_merge_diag(const QRegProgramHost &h, std::vector<int> ids, std::vector<QRTableHost> &out, OK ok) {
   std::sort(ids.begin(), ids.end(), [&](int a, int b) {
     const auto &sa = h.comps[a].sel, &sb = h.comps[b].sel;
     int la = sa.empty() ? -1 : sa.front(), lb = sb.empty() ? -1 : sb.front();
@@ -790,8 +919,7 @@ static void qr_merge_pre(const QRegProgramHost &h, std::vector<int> ids, std::ve
       for (int b : h.comps[ids[j]].sel)
         if (std::find(u.begin(), u.end(), b) == u.end()) u.push_back(b);
       std::sort(u.begin(), u.end());
-      uint32_t dummy;
-      if ((int)u.size() <= QR_DIAG_WINDOW && qr_pack_runs(u, dummy)) {
+      if ((int)u.size() <= QR_DIAG_WINDOW && ok(u)) {
         bits = u;
         mem.push_back(j);
         used[j] = true;
@@ -801,7 +929,7 @@ static void qr_merge_pre(const QRegProgramHost &h, std::vector<int> ids, std::ve
     for (size_t m : mem) {
       QRTableHost::Member mm;
       mm.comp = ids[m];
-      for (int b : h.comps[ids[m]].sel) mm.pos.push_back((int)(std::find(bits.begin(), bits.end(), b) - bits.begin()));
+      mm.pos.clear();
       t.members.push_back(mm);
     }
     out.push_back(std::move(t));
@@ -900,8 +1028,8 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
     for (int b = 0; b < nbits; ++b)
       if (free_sets[p] >> b & 1) fbits[p].push_back(b);
 
-  // ---- the R bits of every pass: the 4 tile-local positions (>= 3, so that 8 consecutive lanes read one 128-byte line)
-  // that make the most masks of the pass register-resident (mask inside R, <= 2 bits, selectors == mask bits)
+  // ---- the R bits of a pass are its 4 highest free bits (tile-local positions 8..11): a mask inside them, on <= 2 bits and
+  // with no other selector bit inside R, is applied from registers
   auto in_reg_ok = [&](const QRCompHost &c, uint64_t rbits) {
     if (!c.mask || (c.mask & ~rbits) || __builtin_popcountll(c.mask) > 2) return false;
     uint64_t sb = 0;
@@ -911,33 +1039,8 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
   std::vector<std::vector<int>> rpos(np);
   std::vector<uint64_t> rbits(np, 0);
   for (int p = 0; p < np; ++p) {
-    int best_score = -1;
-    std::vector<int> best;
-    for (int a = 3; a < T; ++a)
-      for (int b = a + 1; b < T; ++b)
-        for (int c = b + 1; c < T; ++c)
-          for (int d = c + 1; d < T; ++d) {
-            const uint64_t rb = (1ull << fbits[p][a]) | (1ull << fbits[p][b]) | (1ull << fbits[p][c]) | (1ull << fbits[p][d]);
-            int score = 0;
-            std::vector<uint64_t> seen;
-            for (auto &cc : h->comps) {
-              if (!cc.mask || (cc.mask & ~free_sets[p])) continue;
-              if (in_reg_ok(cc, rb) && std::find(seen.begin(), seen.end(), cc.mask) == seen.end()) {
-                seen.push_back(cc.mask);
-                // a mask that only this pass can take counts double
-                int ncand = 0;
-                for (int q = 0; q < np; ++q) ncand += ((cc.mask & ~free_sets[q]) == 0);
-                score += ncand == 1 ? 4 : 3;
-              }
-            }
-            score = score * 16 + (a + b + c + d) / 4;  // ties: the highest positions
-            if (score > best_score) {
-              best_score = score;
-              best = {a, b, c, d};
-            }
-          }
-    rpos[p] = best;
-    for (int k : best) rbits[p] |= 1ull << fbits[p][k];
+    rpos[p] = {8, 9, 10, 11};
+    for (int k : rpos[p]) rbits[p] |= 1ull << fbits[p][k];
   }
 
   // ---- assign components to passes.  Diagonal weights go to pass 0.  A mask goes where it is register-resident if that
@@ -989,124 +1092,149 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
     if (!qr_tensor_geometry(*ph, nbits)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: tile shape needs a tensor map of rank > 5");
     std::vector<int> rg;  // flat-index bits of R, ascending
     for (int k : ph->rpos) rg.push_back(ph->free_bits[k]);
-    std::vector<int> pre_ids, diagr_ids, inreg_ids, gather_ids;
+    // a selector bit is an R bit, a thread bit (tile-local position < 8, i.e. a bit of the thread id) or a tile / rank bit
+    auto tpos_of = [&](int bit) {  // position in the thread id, -1 if none
+      for (int q = 0; q < 8; ++q)
+        if (ph->free_bits[q] == bit) return q;
+      return -1;
+    };
+    auto is_r = [&](int bit) { return std::find(rg.begin(), rg.end(), bit) != rg.end(); };
+    // split selector bits outside R into thread positions and tile bits and pack both as bit-field runs
+    auto pack_outside = [&](const std::vector<int> &bits, std::vector<int> &tbits, std::vector<int> &gbits, uint32_t &selT, uint32_t &selG) {
+      tbits.clear();
+      gbits.clear();
+      std::vector<int> tp;
+      for (int b : bits) {
+        if (is_r(b)) continue;
+        const int q = tpos_of(b);
+        if (q >= 0) {
+          tbits.push_back(b);
+          tp.push_back(q);
+        } else {
+          gbits.push_back(b);
+        }
+      }
+      return qr_pack_runs(tp, selT) && qr_pack_runs(gbits, selG);
+    };
+    std::vector<int> pretile_ids, pre_ids, diagr_ids, inreg_ids, gather_ids;
     for (size_t id = 0; id < h->comps.size(); ++id) {
       const QRCompHost &c = h->comps[id];
       if (c.pass != p) continue;
       uint64_t sb = 0;
-      for (int b : c.sel) sb |= 1ull << b;
-      if (!c.mask) ((sb & rbits[p]) ? diagr_ids : pre_ids).push_back((int)id);
-      else if (in_reg_ok(c, rbits[p])) inreg_ids.push_back((int)id);
-      else gather_ids.push_back((int)id);
+      bool any_thread = false;
+      for (int b : c.sel) {
+        sb |= 1ull << b;
+        any_thread |= tpos_of(b) >= 0;
+      }
+      if (!c.mask) {
+        if (sb & rbits[p]) diagr_ids.push_back((int)id);
+        else (any_thread ? pre_ids : pretile_ids).push_back((int)id);
+      } else if (in_reg_ok(c, rbits[p])) {
+        inreg_ids.push_back((int)id);
+      } else {
+        gather_ids.push_back((int)id);
+      }
     }
-    ph->n_work = (int)(pre_ids.size() + diagr_ids.size() + inreg_ids.size() + gather_ids.size());
+    ph->n_work = (int)(pretile_ids.size() + pre_ids.size() + diagr_ids.size() + inreg_ids.size() + gather_ids.size());
     std::vector<QRComp> recs;
     uint32_t tab_off = 0;
-    auto selr_of = [&](const std::vector<int> &bits) {
-      unsigned s = 0;
-      for (int k = 0; k < 4; ++k)
-        if (std::find(bits.begin(), bits.end(), rg[k]) != bits.end()) s |= 1u << k;
-      return s;
+    // finish a table whose index bits are [inside R (given) | thread bits | tile bits] and emit its record
+    auto emit = [&](QRTableHost &t, const std::vector<int> &inside, const std::vector<int> &all_bits, uint32_t kind, uint32_t xorB) -> bool {
+      QRComp r;
+      memset(&r, 0, sizeof r);
+      std::vector<int> tb_, gb_;
+      if (!pack_outside(all_bits, tb_, gb_, r.selT, r.selG)) return false;
+      t.bits = inside;
+      for (int b : tb_) t.bits.push_back(b);
+      for (int b : gb_) t.bits.push_back(b);
+      for (auto &m : t.members) {
+        m.pos.clear();
+        for (int b : h->comps[m.comp].sel) m.pos.push_back((int)(std::find(t.bits.begin(), t.bits.end(), b) - t.bits.begin()));
+      }
+      r.kind = kind;
+      r.nT = (uint32_t)tb_.size();
+      r.xorB = xorB;
+      r.tabE = tab_off;
+      t.tab_off = tab_off;
+      tab_off += 1u << t.bits.size();
+      recs.push_back(r);
+      ph->tables.push_back(t);
+      return true;
     };
-    // (a) diagonal tables without R bits
+    auto runs_ok = [&](const std::vector<int> &bits) {
+      std::vector<int> tb_, gb_;
+      uint32_t a_, b_;
+      return pack_outside(bits, tb_, gb_, a_, b_);
+    };
+    // (a) diagonal tables on tile / rank bits only: evaluated once per tile by the producer warp
     {
       std::vector<QRTableHost> tabs;
-      qr_merge_pre(*h, pre_ids, tabs);
-      for (auto &t : tabs) {
-        QRComp r;
-        memset(&r, 0, sizeof r);
-        r.kind = QR_PRE;
-        if (!qr_pack_runs(t.bits, r.sel)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
-        r.tabE = tab_off;
-        t.tab_off = tab_off;
-        tab_off += 1u << t.bits.size();
-        recs.push_back(r);
-        ph->tables.push_back(t);
-      }
+      qr_merge_diag(*h, pretile_ids, tabs, runs_ok);
+      for (auto &t : tabs)
+        if (!emit(t, {}, t.bits, QR_PRE_TILE, 0)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
+      P.n_pretile = (int)tabs.size();
+    }
+    // (b) diagonal tables that involve thread bits (but no R bit): once per thread and tile
+    {
+      std::vector<QRTableHost> tabs;
+      qr_merge_diag(*h, pre_ids, tabs, runs_ok);
+      for (auto &t : tabs)
+        if (!emit(t, {}, t.bits, QR_PRE, 0)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
       P.n_pre = (int)tabs.size();
     }
-    // (b) diagonal tables indexed by all 4 R bits (low index bits) and <= 4 selector bits outside R
+    // (c) diagonal tables indexed by all 4 R bits (low index bits) and <= 4 selector bits outside R
     {
       std::vector<bool> used(diagr_ids.size(), false);
       int n = 0;
       for (size_t i = 0; i < diagr_ids.size(); ++i) {
         if (used[i]) continue;
         std::vector<int> outside;
-        std::vector<size_t> mem;
+        QRTableHost t;
         for (size_t j = i; j < diagr_ids.size(); ++j) {
           if (used[j]) continue;
           std::vector<int> u = outside;
           for (int b : h->comps[diagr_ids[j]].sel)
-            if (std::find(rg.begin(), rg.end(), b) == rg.end() && std::find(u.begin(), u.end(), b) == u.end()) u.push_back(b);
+            if (!is_r(b) && std::find(u.begin(), u.end(), b) == u.end()) u.push_back(b);
           std::sort(u.begin(), u.end());
-          uint32_t dummy;
-          if (u.size() <= 4 && qr_pack_runs(u, dummy)) {
+          if (u.size() <= 4 && runs_ok(u)) {
             outside = u;
-            mem.push_back(j);
+            QRTableHost::Member mm;
+            mm.comp = diagr_ids[j];
+            t.members.push_back(mm);
             used[j] = true;
           }
         }
-        if (mem.empty()) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
-        QRTableHost t;
-        t.bits = rg;
-        for (int b : outside) t.bits.push_back(b);
-        for (size_t m : mem) {
-          QRTableHost::Member mm;
-          mm.comp = diagr_ids[m];
-          for (int b : h->comps[diagr_ids[m]].sel) mm.pos.push_back((int)(std::find(t.bits.begin(), t.bits.end(), b) - t.bits.begin()));
-          t.members.push_back(mm);
-        }
-        QRComp r;
-        memset(&r, 0, sizeof r);
-        r.kind = QR_DIAGR | (15u << 4);
-        if (!qr_pack_runs(outside, r.sel)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
-        r.tabE = tab_off;
-        t.tab_off = tab_off;
-        tab_off += 1u << t.bits.size();
-        recs.push_back(r);
-        ph->tables.push_back(t);
+        if (t.members.empty()) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
+        if (!emit(t, rg, outside, QR_DIAGR | (15u << 4), 0)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
         ++n;
       }
       P.n_diagr = n;
     }
-    // (c, d) off-diagonal records: table index = [selector bits inside R, ascending | selector bits outside R, ascending]
-    auto flip_record = [&](int id, int cls) -> int {
+    // (d, e) off-diagonal records: table index = [selector bits inside R | on thread bits | on tile bits], each ascending
+    auto flip_record = [&](int id, int cls) -> bool {
       const QRCompHost &c = h->comps[id];
-      std::vector<int> inside, outside;
-      for (int b : c.sel) ((std::find(rg.begin(), rg.end(), b) != rg.end()) ? inside : outside).push_back(b);
+      std::vector<int> inside;
+      for (int b : c.sel)
+        if (is_r(b)) inside.push_back(b);
+      unsigned selr = 0, mR = 0, xorB = 0;
+      for (int k = 0; k < 4; ++k) {
+        if (std::find(c.sel.begin(), c.sel.end(), rg[k]) != c.sel.end()) selr |= 1u << k;
+        if (c.mask >> rg[k] & 1) mR |= 1u << k;
+      }
+      for (int pos = 0; pos < 8; ++pos)   // thread bits of the mask; its R bits travel in `kind` (mR)
+        if (c.mask >> ph->free_bits[pos] & 1) xorB |= 16u << pos;
+      if (cls == QR_GATHER && __builtin_popcount(selr) > 2) cls = QR_GATHER_SLOW;
       QRTableHost t;
-      t.bits = inside;
-      for (int b : outside) t.bits.push_back(b);
       QRTableHost::Member mm;
       mm.comp = id;
-      for (int b : c.sel) mm.pos.push_back((int)(std::find(t.bits.begin(), t.bits.end(), b) - t.bits.begin()));
       t.members.push_back(mm);
-      QRComp r;
-      memset(&r, 0, sizeof r);
-      const unsigned selr = selr_of(c.sel);
-      unsigned mR = 0, lmaskT = 0;
-      for (int k = 0; k < 4; ++k)
-        if (c.mask >> rg[k] & 1) mR |= 1u << k;
-      for (int pos = 0; pos < QR_T; ++pos)
-        if ((c.mask >> ph->free_bits[pos] & 1) && std::find(ph->rpos.begin(), ph->rpos.end(), pos) == ph->rpos.end())
-          lmaskT |= 1u << pos;
-      if (cls == QR_GATHER && __builtin_popcount(selr) > 2) cls = QR_GATHER_SLOW;
-      r.kind = (uint32_t)cls | (selr << 4) | (mR << 8);
-      if (!qr_pack_runs(outside, r.sel)) return QOB_STATUS_UNSUPPORTED;
-      r.xorT = lmaskT * 16u;
-      for (int u = 0; u < 16; ++u) r.goff[u] = P.uoffB[u ^ mR];
-      r.tabE = tab_off;
-      t.tab_off = tab_off;
-      tab_off += 1u << t.bits.size();
-      recs.push_back(r);
-      ph->tables.push_back(t);
-      return QOB_STATUS_OK;
+      return emit(t, inside, c.sel, (uint32_t)cls | (selr << 4) | (mR << 8), xorB);
     };
     for (int id : inreg_ids)
-      if (flip_record(id, QR_INREG) != QOB_STATUS_OK) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
+      if (!flip_record(id, QR_INREG)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
     P.n_inreg = (int)inreg_ids.size();
     for (int id : gather_ids)
-      if (flip_record(id, QR_GATHER) != QOB_STATUS_OK) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
+      if (!flip_record(id, QR_GATHER)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
     P.n_gather = (int)gather_ids.size();
     if (recs.size() > QR_MAXC) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: %d lookup records in one pass (max %d)", (int)recs.size(), QR_MAXC);
     for (size_t i = 0; i < recs.size(); ++i) P.comps[i] = recs[i];
@@ -1201,9 +1329,9 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
         snprintf(buf, sizeof buf, "%s%d-%d", s ? "," : "", sg[s], sg[s] + sn[s] - 1);
         prog.describe += buf;
       }
-      snprintf(buf, sizeof buf, " R:%d,%d,%d,%d diag:%d+%d in-register:%d gathers:%d rank:%d]", ph.free_bits[ph.rpos[0]],
-               ph.free_bits[ph.rpos[1]], ph.free_bits[ph.rpos[2]], ph.free_bits[ph.rpos[3]], ph.params.n_pre, ph.params.n_diagr,
-               ph.params.n_inreg, ph.params.n_gather, ph.rank);
+      snprintf(buf, sizeof buf, " R:%d,%d,%d,%d diag:%d+%d+%d in-register:%d gathers:%d rank:%d]", ph.free_bits[ph.rpos[0]],
+               ph.free_bits[ph.rpos[1]], ph.free_bits[ph.rpos[2]], ph.free_bits[ph.rpos[3]], ph.params.n_pretile, ph.params.n_pre,
+               ph.params.n_diagr, ph.params.n_inreg, ph.params.n_gather, ph.rank);
       prog.describe += buf;
     }
     prog.describe += "}";
@@ -1243,14 +1371,12 @@ int qreg_set_coefs(QRegProgram &prog, const std::vector<cplx> &coefs, cudaStream
   return QOB_STATUS_OK;
 }
 
-static int g_qreg_sm_count = 0;
 
 int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s) {
   QRegProgramHost &h = *prog.h;
   int dev = 0, sms = 148;
   QOB_CUDA(cudaGetDevice(&dev));
   QOB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  (void)g_qreg_sm_count;
   unsigned *sync = nullptr;
   {
     std::lock_guard<std::mutex> lk(h.mu);
@@ -1282,6 +1408,11 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
     Lp.nchunks = g.nchunks;
     Lp.lag = g.lag;
     Lp.total_items = ntiles * (unsigned)g.count;
+    Lp.prefetch = qr_env_int("QOB_QREG_PREFETCH", 0);
+    static long long *stats_buf = nullptr;
+    const bool want_stats = qr_env_int("QOB_QREG_STATS", 0) != 0;
+    if (want_stats && !stats_buf) QOB_CUDA(cudaMalloc(&stats_buf, 16 * 256 * sizeof(long long)));
+    Lp.stats = want_stats ? stats_buf : nullptr;
     alignas(64) CUtensorMap maps[4];
     uint32_t tab_off = 0;
     for (int q = 0; q < g.count; ++q) {
@@ -1326,6 +1457,16 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
     if (h.real_tables) QOB_TRY(launch(qreg_kernel<true>));
     else QOB_TRY(launch(qreg_kernel<false>));
     qprof_end(s, prof_token);
+    if (want_stats) {
+      std::vector<long long> hs(16 * 256);
+      cudaStreamSynchronize(s);
+      cudaMemcpy(hs.data(), stats_buf, hs.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      for (int b : {0, 1, 73, 147}) {
+        const long long *o = hs.data() + 16 * b;
+        fprintf(stderr, "[qreg stats] launch %d cta %3d: tiles %lld total %lld | producer wait x-empty %lld dep %lld y-empty %lld | consumer w0 wait-x %lld compute %lld wait-y %lld epilogue %lld | w7 %lld %lld %lld %lld\n",
+                gi - 1, b, o[4], o[3], o[0], o[1], o[2], o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]);
+      }
+    }
   }
   return QOB_STATUS_OK;
 }

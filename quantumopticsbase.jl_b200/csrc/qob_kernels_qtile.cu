@@ -951,10 +951,16 @@ template <int T, int THREADS, int MINB, bool IDX64, bool REALW, bool PEER>
 static int launch_pass(const QTileProgramHost &h, const QPassHost &p, const QPassParams &P, const void *x, void *y,
                        int max_ctas, cudaStream_t s) {
   size_t smem = h.smem_bytes(p);
-  static size_t configured = 0;
-  if (smem > configured) {
-    QOB_CUDA(cudaFuncSetAttribute(qtile_kernel<T, THREADS, MINB, IDX64, REALW, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  {
+    // the opt-in is per device (and per template instantiation): remember the largest size configured on each device
+    static std::atomic<size_t> configured[QOB_MAX_DEVICES];
+    int dev = 0;
+    QOB_CUDA(cudaGetDevice(&dev));
+    const int slot = dev >= 0 && dev < QOB_MAX_DEVICES ? dev : 0;
+    if (dev != slot || smem > configured[slot].load(std::memory_order_relaxed)) {
+      QOB_CUDA(cudaFuncSetAttribute(qtile_kernel<T, THREADS, MINB, IDX64, REALW, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured[slot].store(smem, std::memory_order_relaxed);
+    }
   }
   if ((1ull << (h.nbits - T)) > 0x7FFFFFFFull) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qtile: too many tiles");
   const uint64_t ntiles = P.ntiles;
@@ -1032,13 +1038,7 @@ extern "C" int qob_set_sm_budget(int32_t sms) {
 int qtile_launch(const QTileProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s,
                  const QLaunchOpts *opts) {
   const QTileProgramHost &h = *prog.h;
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (sm_count <= 0) sm_count = 148;
-  }
+  const int sm_count = qob_device_sm_count();
   QLaunchOpts none;
   const QLaunchOpts &o = opts ? *opts : none;
   if (o.npeers > QT_MAXPEER) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "more than %d peers", QT_MAXPEER);
