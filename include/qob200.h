@@ -111,6 +111,10 @@ int qob_lazysum_set_coefs(qob_op *sum, int32_t nterms, const qob_c64 *coefs);
  * device buffers (the reference pre-allocates ket_l/bra_r, :12-21). */
 int qob_lazyproduct_create(qob_ctx *ctx, int32_t nops, qob_op *const *ops, qob_c64 factor, qob_op **out);
 
+/* LazyDirectSum(op1, op2, ...) — src/spinors.jl:158-169; mul! for Ket / Bra :221-247 (block i acts on slice i of the
+ * SumBasis state; blocks must be square, batch must be 1 — the reference defines no other method). */
+int qob_lazydirectsum_create(qob_ctx *ctx, int32_t nops, qob_op *const *ops, qob_op **out);
+
 int qob_op_destroy(qob_op *op);
 int qob_op_dims(const qob_op *op, int64_t *dim_l, int64_t *dim_r);
 
@@ -161,6 +165,25 @@ int qob_fill_state(void *x, int64_t offset, int64_t n, uint64_t seed, double sca
 /* sum |x|^2 and <x|y> reductions for size-independent parity properties (device result -> host). */
 int qob_norm2(const void *x, int64_t n, double *out, void *stream);
 int qob_dot(const void *x, const void *y, int64_t n, qob_c64 *out, void *stream);
+
+/* expect(op, psi) = dot(psi, op*psi) and variance(op, psi) = psi'(op(op psi)) - (psi'(op psi))^2 for a Ket
+ * (src/operators.jl:119,139-142).  x: device pointer to dim_r ComplexF64; the scalar result is written to HOST memory
+ * (the call synchronises `stream`).  The intermediate op*psi lives in the handle's scratch (per stream). */
+int qob_expect(qob_op *op, const void *x, qob_c64 *out, void *stream);
+int qob_variance(qob_op *op, const void *x, qob_c64 *out, void *stream);
+
+/* ptrace(a::DataOperator, indices) / ptrace(psi::Ket, indices) / ptrace(psi::Bra, indices)
+ * (src/operators_dense.jl:191-215, generated loop nests :311-383).  `traced`: ntraced distinct 1-based subsystem indices.
+ * qob_ptrace_op:    a = dense prod(dims_l) x prod(dims_r) device matrix -> result (kept dims_l) x (kept dims_r), column-major;
+ *                   traced subsystems need dims_l == dims_r.
+ * qob_ptrace_state: psi = device vector over dims -> result M x M with M = prod(kept dims): psi psi^+ summed over the traced
+ *                   subsystems (is_bra != 0: conj(psi[Il]) * psi[Ir], the reference's Bra method).
+ * Errors follow check_ptrace_arguments (src/operators.jl:153-176): QOB_STATUS_INVALID_ARG when all subsystems are traced, an
+ * index is out of range or repeated, or a traced subsystem is not square. */
+int qob_ptrace_op(qob_ctx *ctx, int32_t nsub, const int64_t *dims_l, const int64_t *dims_r, int32_t ntraced,
+                  const int32_t *traced, const void *a, void *result, void *stream);
+int qob_ptrace_state(qob_ctx *ctx, int32_t nsub, const int64_t *dims, int32_t ntraced, const int32_t *traced,
+                     int32_t is_bra, const void *psi, void *result, void *stream);
 
 /* ---- sharded (multi-GPU) LazySum apply: one process per GPU -----------------------------------
  * The state is sharded on its highest-stride axes: rank r of P=2^p owns the contiguous slab

@@ -8,7 +8,7 @@ loads this package under that name).  Contents: `csrc/` (CUDA kernels + C ABI ->
 from ._lib import (ArgumentError, CudaError, DimensionMismatch, IncompatibleBases, MethodError, LIB_PATH, EXPORTED,
                    context, lib)
 from .operators import (Adjoint, Basis, Bra, CompositeBasis, DenseOperator, Eye, FockBasis, GenericBasis, Ket,
-                        LazyProduct, LazySum, LazyTensor, LindbladRHS, NLevelBasis, Operator, SparseOperator, SpinBasis, TimeDependentSum,
+                        LazyDirectSum, LazyProduct, LazySum, LazyTensor, LindbladRHS, SumBasis, directsum, ptrace, reduced, NLevelBasis, Operator, SparseOperator, SpinBasis, TimeDependentSum,
                         apply_host, create, dagger, dense, describe, destroy, dot, expect, fill_state, handle,
                         identityoperator, launch_count, mul_, norm2, number, profile_enable, profile_read, randstate, sigmam, sigmap, sigmax,
                         sigmay, sigmaz, sparse, tensor, transition, variance)

@@ -115,6 +115,11 @@ _sigs = {
     "qob_layout_plan_info": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(C.c_uint64)]),
     "qob_layout_plan_set_chunk_bits": (C.c_int, [_vp, _i32, C.c_uint64]),
     "qob_set_sm_budget": (C.c_int, [_i32]),
+    "qob_lazydirectsum_create": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_vp)]),
+    "qob_expect": (C.c_int, [_vp, _vp, C.POINTER(c64), _vp]),
+    "qob_variance": (C.c_int, [_vp, _vp, C.POINTER(c64), _vp]),
+    "qob_ptrace_op": (C.c_int, [_vp, _i32, C.POINTER(_i64), C.POINTER(_i64), _i32, C.POINTER(_i32), _vp, _vp, _vp]),
+    "qob_ptrace_state": (C.c_int, [_vp, _i32, C.POINTER(_i64), _i32, C.POINTER(_i32), _i32, _vp, _vp, _vp]),
 }
 for _name, (_res, _args) in _sigs.items():
     _f = getattr(lib, _name)

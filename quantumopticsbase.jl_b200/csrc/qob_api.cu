@@ -199,7 +199,7 @@ void qob_ctx::clear_scratch() {
 static std::atomic<int> g_slot_counter{1000};
 
 // ============================================================================ operator handles
-enum OpKind { OP_LAZYTENSOR, OP_SPARSE, OP_DENSE, OP_LAZYSUM, OP_LAZYPRODUCT, OP_LINDBLAD };
+enum OpKind { OP_LAZYTENSOR, OP_SPARSE, OP_DENSE, OP_LAZYSUM, OP_LAZYPRODUCT, OP_LINDBLAD, OP_DIRECTSUM };
 
 struct qob_op {
   qob_ctx *ctx;
@@ -751,6 +751,35 @@ struct LazyProductOp : qob_op {
   }
   std::string describe(int side, int64_t batch) override {
     std::string t = "lazyproduct[";
+    for (qob_op *o : ops) t += o->describe(side, batch) + "; ";
+    return t + "]";
+  }
+};
+
+// LazyDirectSum (src/spinors.jl:158-163, mul! :221-247): block-diagonal operator on a SumBasis.  Block i maps the slice
+// [index[i], index[i+1]) of the state to the same slice of the result; like the reference the slices are cut by the RIGHT
+// basis lengths for both vectors, so every block has to be square (the reference's `Ket(bases_l[i], result.data[...])`
+// throws DimensionMismatch otherwise).  Only Ket / Bra methods exist in the reference: batch must be 1.
+struct LazyDirectSumOp : qob_op {
+  std::vector<qob_op *> ops;
+  LazyDirectSumOp(qob_ctx *c) : qob_op(c, OP_DIRECTSUM) {}
+  ~LazyDirectSumOp() override {
+    for (qob_op *t : ops) op_release(t);
+  }
+  int apply(int side, cplx alpha, const void *x, cplx beta, void *y, int64_t batch, cudaStream_t s) override {
+    if (batch != 1) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "LazyDirectSum: mul! is only defined for Ket and Bra states (src/spinors.jl:221-247)");
+    int64_t off = 0;
+    for (qob_op *o : ops) {
+      if (o->dl != o->dr)
+        QOB_FAIL(QOB_STATUS_DIM_MISMATCH, "LazyDirectSum block of size %lldx%lld: the reference slices state and result by the same lengths",
+                 (long long)o->dl, (long long)o->dr);
+      QOB_TRY(o->apply(side, alpha, (const char *)x + off * 16, beta, (char *)y + off * 16, 1, s));
+      off += o->dr;
+    }
+    return QOB_STATUS_OK;
+  }
+  std::string describe(int side, int64_t batch) override {
+    std::string t = "lazydirectsum[";
     for (qob_op *o : ops) t += o->describe(side, batch) + "; ";
     return t + "]";
   }
@@ -1349,6 +1378,90 @@ int qob_dot(const void *x, const void *y, int64_t n, qob_c64 *out, void *stream)
   out->re = r.real();
   out->im = r.imag();
   return QOB_STATUS_OK;
+}
+
+// ---- LazyDirectSum, expect / variance, partial traces -----------------------------------------
+int qob_lazydirectsum_create(qob_ctx *ctx, int32_t nops, qob_op *const *ops, qob_op **out) {
+  if (!ctx || !out) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null argument");
+  if (nops < 1 || !ops) QOB_FAIL(QOB_STATUS_INVALID_ARG, "LazyDirectSum needs at least one operator");
+  auto op = std::make_unique<LazyDirectSumOp>(ctx);
+  for (int i = 0; i < nops; ++i) {
+    if (!ops[i]) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null operator %d", i);
+    if (ops[i]->ctx != ctx) QOB_FAIL(QOB_STATUS_INVALID_ARG, "LazyDirectSum operator %d belongs to another context (device)", i + 1);
+  }
+  for (int i = 0; i < nops; ++i) {
+    op_retain(ops[i]);
+    op->ops.push_back(ops[i]);
+    op->dl += ops[i]->dl;
+    op->dr += ops[i]->dr;
+  }
+  *out = op.release();
+  return QOB_STATUS_OK;
+}
+
+// <x| op |x> = dot(x, op*x)  (src/operators.jl:119): mul! into the handle's scratch, then one deterministic device reduction;
+// only the scalar crosses to the host.
+int qob_expect(qob_op *op, const void *x, qob_c64 *out, void *stream) {
+  if (!op || !out) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null argument");
+  if (op->dl != op->dr) QOB_FAIL(QOB_STATUS_DIM_MISMATCH, "expect needs an operator with equal left and right bases");
+  if (!x && op->dr > 0) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null data pointer");
+  if (op->ctx->device < 0) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
+  QOB_DEVICE(op->ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  void *tmp = nullptr;
+  QOB_TRY(op->ctx->get_scratch(s, op->slot_base + 4, (size_t)std::max<int64_t>(1, op->dl) * 16, &tmp));
+  QOB_TRY(op->apply(QOB_SIDE_LEFT, ONE, x, ZERO, tmp, 1, s));
+  cplx r;
+  QOB_TRY(launch_dot(x, tmp, op->dl, &r, s));
+  out->re = r.real();
+  out->im = r.imag();
+  return QOB_STATUS_OK;
+}
+
+// variance(op, psi) = psi' (op (op psi)) - (psi' (op psi))^2  (src/operators.jl:139-142), two applications like the reference
+int qob_variance(qob_op *op, const void *x, qob_c64 *out, void *stream) {
+  if (!op || !out) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null argument");
+  if (op->dl != op->dr) QOB_FAIL(QOB_STATUS_DIM_MISMATCH, "variance needs an operator with equal left and right bases");
+  if (!x && op->dr > 0) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null data pointer");
+  if (op->ctx->device < 0) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
+  QOB_DEVICE(op->ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  void *t1 = nullptr, *t2 = nullptr;
+  QOB_TRY(op->ctx->get_scratch(s, op->slot_base + 4, (size_t)std::max<int64_t>(1, op->dl) * 16, &t1));
+  QOB_TRY(op->ctx->get_scratch(s, op->slot_base + 5, (size_t)std::max<int64_t>(1, op->dl) * 16, &t2));
+  QOB_TRY(op->apply(QOB_SIDE_LEFT, ONE, x, ZERO, t1, 1, s));
+  QOB_TRY(op->apply(QOB_SIDE_LEFT, ONE, t1, ZERO, t2, 1, s));
+  cplx e1, e2;
+  QOB_TRY(launch_dot(x, t1, op->dl, &e1, s));
+  QOB_TRY(launch_dot(x, t2, op->dl, &e2, s));
+  const cplx v = e2 - e1 * e1;
+  out->re = v.real();
+  out->im = v.imag();
+  return QOB_STATUS_OK;
+}
+
+static const int PTRACE_SLOT = 900;  // context-level scratch slots (operator handles start at 1000)
+int qob_ptrace_op(qob_ctx *ctx, int32_t nsub, const int64_t *dims_l, const int64_t *dims_r, int32_t ntraced, const int32_t *traced,
+                  const void *a, void *result, void *stream) {
+  if (!ctx) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null context");
+  PlanningScope ps(ctx->device < 0);
+  if (ctx->device >= 0) {
+    if (!a || !result) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null data pointer");
+    QOB_DEVICE(ctx->device);
+    return launch_ptrace_op(ctx, PTRACE_SLOT, nsub, dims_l, dims_r, ntraced, traced, a, result, (cudaStream_t)stream);
+  }
+  return launch_ptrace_op(ctx, PTRACE_SLOT, nsub, dims_l, dims_r, ntraced, traced, a, result, (cudaStream_t)stream);
+}
+int qob_ptrace_state(qob_ctx *ctx, int32_t nsub, const int64_t *dims, int32_t ntraced, const int32_t *traced, int32_t is_bra,
+                     const void *psi, void *result, void *stream) {
+  if (!ctx) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null context");
+  PlanningScope ps(ctx->device < 0);
+  if (ctx->device >= 0) {
+    if (!psi || !result) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null data pointer");
+    QOB_DEVICE(ctx->device);
+    return launch_ptrace_state(ctx, PTRACE_SLOT + 1, nsub, dims, ntraced, traced, is_bra != 0, psi, result, (cudaStream_t)stream);
+  }
+  return launch_ptrace_state(ctx, PTRACE_SLOT + 1, nsub, dims, ntraced, traced, is_bra != 0, psi, result, (cudaStream_t)stream);
 }
 
 // ---- sharded apply: per-rank compute in an arbitrary index layout ----------------

@@ -252,6 +252,12 @@ int dtile_build(DTileProgram &p, const std::vector<int64_t> &dims, const std::ve
 int dtile_set_coefs(DTileProgram &p, const std::vector<cplx> &coefs, cudaStream_t s);
 int dtile_launch(const DTileProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s);
 
+// Partial traces (qob_kernels_ptrace.cu); `slot` names the context scratch slot used for offset tables / partial sums
+int launch_ptrace_op(qob_ctx *ctx, int slot, int nsub, const int64_t *dims_l, const int64_t *dims_r, int ntraced, const int32_t *traced,
+                     const void *a, void *result, cudaStream_t s);
+int launch_ptrace_state(qob_ctx *ctx, int slot, int nsub, const int64_t *dims, int ntraced, const int32_t *traced, bool bra, const void *psi,
+                        void *result, cudaStream_t s);
+
 // misc device helpers
 int launch_fill_state(void *x, int64_t offset, int64_t n, uint64_t seed, double scale, cudaStream_t s);
 int launch_norm2(const void *x, int64_t n, double *host_out, cudaStream_t s);

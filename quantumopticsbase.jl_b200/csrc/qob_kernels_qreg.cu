@@ -36,6 +36,7 @@
 #define QR_TILE_BYTES (QR_TILE * 16)
 #define QR_CTHREADS 256                 // consumer threads (8 warps), 16 amplitudes each
 #define QR_THREADS (QR_CTHREADS + 32)   // + one producer warp
+#define QR_USTRIDE 4096                 // byte distance in the staged tile between consecutive amplitudes u of a thread
 #define QR_MAXC 40                      // lookup records per pass (kernel parameter space)
 #define QR_MAXSEG 8
 #define QR_DIAG_WINDOW 6
@@ -43,26 +44,32 @@
 // classes of lookup records; records of a pass are sorted by class
 enum { QR_PRE_TILE = 0, QR_PRE = 1, QR_DIAGR = 2, QR_INREG = 3, QR_GATHER = 4, QR_GATHER_SLOW = 5 };
 
-// A thread owns the 16 amplitudes whose tile-local index bits 8..11 ("R bits") vary: amplitude u of thread t sits at byte
-// t*16 + u*4096 of the staged tile, so every shared-memory access of the hot loops is [thread base + immediate].
+// Tile-local index bits: 0..7 = consumer thread, 8..11 = the thread's 16 amplitudes ("R bits").  Amplitude u of thread t sits at
+// byte t*16 + u*4096 of the staged tile, so every shared-memory access of the hot loops is [thread base + immediate].
 struct QRComp {       // 32 bytes
   uint32_t kind;      // class | SELR << 4 | M << 8   (SELR: which of the 4 R bits select the weight; M: flip mask inside R)
   uint32_t tabE;      // first entry of the weight table inside the pass table
   uint32_t selT;      // selector bits among the 8 thread bits: bit-field runs of the thread id, 9 bits each: shift (6) | width (3)
   uint32_t selG;      // selector bits among the tile-id / rank bits: bit-field runs of the 64-bit flat index
-  uint32_t xorB;      // gather: XOR applied to the thread's byte offset inside the tile (thread bits and R bits of the mask)
+  uint32_t xorB;      // gather: XOR applied to the thread's byte offset inside the tile (thread bits of the mask)
   uint32_t nT;        // number of selector bits among the thread bits (the tile part of the table index is shifted by it)
-  uint32_t pad[2];
+  // fast path, valid when bit 31 of `fast` is clear: the selector bits outside R are ONE run of thread bits (or none):
+  //   entry = tabE + (((tid >> (fast & 31)) & ((fast >> 8) & 255)) << ((fast >> 16) & 31))
+  uint32_t fast;
+  uint32_t code;      // dense body number for the dispatch switch
 };
 
 struct QRPass {
   unsigned long long rstride[4];  // element stride in global memory of R bit k
   unsigned char tgbit[8];         // consumer-thread bit b -> flat-index bit
+  int nfree_seg;                  // tile-local index -> element offset inside the tile (L2 prefetch of the next tile)
+  unsigned char fs_l[QR_MAXSEG], fs_n[QR_MAXSEG], fs_g[QR_MAXSEG];
   int nfixed_seg;                 // compact tile id -> element offset of the tile
   unsigned char xs_l[QR_MAXSEG], xs_n[QR_MAXSEG], xs_g[QR_MAXSEG];
   int rank;                       // tensor-map rank; coordinate d = ((tile >> tshift) & (2^tbits - 1)) << boxlog
   unsigned char dim_tshift[5], dim_tbits[5], dim_boxlog[5];
   int n_pretile, n_pre, n_diagr, n_inreg, n_gather;  // records: [pre (tile) | pre (thread) | diagR | in-register | gather]
+  int n_plain;                    // the first n_plain gather records have one weight per thread and no R bit in their mask
   unsigned long long hi_or;       // index bits above the local address (rank of a sharded state), already shifted
   uint32_t tab_smem_off;          // byte offset of this pass's tables inside the shared-memory table area
   uint32_t tab_bytes;
@@ -104,9 +111,10 @@ __device__ __forceinline__ void qr_mbar_expect(unsigned bar, unsigned bytes) {
 __device__ __forceinline__ void qr_mbar_wait(unsigned bar, unsigned parity) {
   unsigned done = 0;
   while (!done) {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+    // the hint lets the hardware park the warp until the phase completes instead of spinning through the issue slots
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(done)
-                 : "r"(bar), "r"(parity)
+                 : "r"(bar), "r"(parity), "r"(0x989680u)
                  : "memory");
   }
 }
@@ -214,12 +222,19 @@ __device__ __forceinline__ unsigned qr_field32(unsigned sel, unsigned v) {
   }
   return idx;
 }
-// index of the selector bits outside R: thread part | tile part << nT; most records have neither
-__device__ __forceinline__ unsigned qr_index(const QRComp &cd, unsigned tid, unsigned g_lo, unsigned g_hi) {
+// general index of the selector bits outside R: thread part | tile part << nT (kept out of line: rare)
+__device__ __noinline__ unsigned qr_index_slow(unsigned selT, unsigned selG, unsigned nT, unsigned tid, unsigned g_lo, unsigned g_hi) {
   unsigned idx = 0;
-  if (cd.selT) idx = qr_field32(cd.selT, tid);
-  if (cd.selG) idx |= qr_field(cd.selG, g_lo, g_hi) << cd.nT;
+  if (selT) idx = qr_field32(selT, tid);
+  if (selG) idx |= qr_field(selG, g_lo, g_hi) << nT;
   return idx;
+}
+// first table entry this thread uses: `shift` = number of selector bits inside R (the low index bits of the table).
+// hot = {kind | code << 16, tabE, fast, xorB} from shared memory; the cold fields are only touched on the slow path.
+__device__ __forceinline__ unsigned qr_entry(const uint4 hot, const QRComp &cold, unsigned shift, unsigned tid, unsigned g_lo, unsigned g_hi) {
+  const unsigned f = hot.z;
+  if (!(f >> 31)) return hot.y + (((tid >> (f & 31u)) & ((f >> 8) & 255u)) << ((f >> 16) & 31u));
+  return hot.y + (qr_index_slow(cold.selT, cold.selG, cold.nT, tid, g_lo, g_hi) << shift);
 }
 
 // weights: REALW tables hold 8-byte reals (2 DFMA per product), otherwise (re, im) pairs (4 DFMA)
@@ -272,7 +287,7 @@ __device__ __forceinline__ void qr_gather(double2 (&acc)[16], const unsigned cha
     double2 v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
-      v[u] = *reinterpret_cast<const double2 *>(xt + (MR ? (((8 * h + u) * 4096u) ^ mxor) : (8 * h + u) * 4096u));
+      v[u] = *reinterpret_cast<const double2 *>(xt + (MR ? (((8 * h + u) * (unsigned)QR_USTRIDE) ^ mxor) : (8 * h + u) * (unsigned)QR_USTRIDE));
 #pragma unroll
     for (int u = 0; u < 8; ++u) w[qr_pext(8 * h + u, SELR)].fma_into(acc[8 * h + u], v[u]);
   }
@@ -292,7 +307,7 @@ __device__ __forceinline__ void qr_gather_slow(double2 (&acc)[16], const unsigne
       }
     QRW<REALW> w;
     w.load(wt + r * (REALW ? 8 : 16));
-    const double2 v = *reinterpret_cast<const double2 *>(xt + ((u * 4096u) ^ mxor));
+    const double2 v = *reinterpret_cast<const double2 *>(xt + ((u * (unsigned)QR_USTRIDE) ^ mxor));
     w.fma_into(acc[u], v);
   }
 }
@@ -348,6 +363,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(tabs + ((tab_total + 15u) & ~15u));
   // bars[0,1]: x full; [2,3]: x empty; [4]: y full; [5]: y empty
   QRItem *slots = reinterpret_cast<QRItem *>(bars + 8);
+  // hot half of every lookup record {kind | code << 16, tabE, fast, xorB}: read with one broadcast LDS.128 instead of
+  // indexed constant-bank loads (7 KB of parameters do not stay in the immediate-constant cache)
+  uint4 *recs = reinterpret_cast<uint4 *>(slots + 2);
   const unsigned tid = threadIdx.x;
   constexpr int WB = REALW ? 8 : 16;
 
@@ -364,50 +382,33 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
     const int4 *g4 = reinterpret_cast<const int4 *>(L.pass[p].tab);
     int4 *t4 = reinterpret_cast<int4 *>(tabs + L.pass[p].tab_smem_off);
     for (unsigned i = tid; i < L.pass[p].tab_bytes / 16u; i += QR_THREADS) t4[i] = g4[i];
+    for (unsigned i = tid; i < QR_MAXC; i += QR_THREADS) {
+      const QRComp &cd = L.pass[p].comps[i];
+      recs[p * QR_MAXC + i] = make_uint4(cd.kind | (cd.code << 16), cd.tabE, cd.fast, cd.xorB);
+    }
   }
   __syncthreads();
 
   if (tid >= QR_CTHREADS) {
     // ------------------------------------------------------------------ producer warp
-    // Work items are dealt round-robin (item = blockIdx.x + k*gridDim.x, in queue order), so the warp knows its future
-    // tiles: lane 0 pulls the tile `prefetch` items ahead into L2 (the DRAM latency is paid there, without holding shared
-    // memory) and issues the TMA loads of the current one; all lanes evaluate the diagonal tables whose selector bits are
+    // Lane 0 claims work items from the ordered queue (the next one while the current loads are in flight, so the latency
+    // of the atomic is hidden) and issues the TMA loads; all lanes evaluate the diagonal tables whose selector bits are
     // tile-id bits (one table per lane).
     const unsigned lane = tid & 31u;
     unsigned long long pol_keep, pol_stream;
     asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
     unsigned stage = 0, xphase = 0, yphase = 0;  // bit s of xphase: parity of the next wait on x-empty[s]
-    auto tile_of = [&](unsigned item, int &p, unsigned &t, unsigned &c) -> bool {
-      unsigned j = 0;
-      if (!qr_decode(L, item, p, c, j)) return false;
-      const QRPass &P = L.pass[p];
-      t = L.npass == 1 ? j : (qr_deposit(c, P.ncs, P.cs_l, P.cs_n, P.cs_d) | qr_deposit(j, P.njs, P.js_l, P.js_n, P.js_d));
-      return true;
-    };
-    auto prefetch_item = [&](unsigned item) {
-      int p = 0;
-      unsigned t = 0, c = 0;
-      if (!tile_of(item, p, t, c)) return;
-      const QRPass &P = L.pass[p];
-      if (P.wait) return;  // tiles of a waiting pass are already in L2 (that is the point of the chaining)
-      int co[5];
-#pragma unroll
-      for (int d = 0; d < 5; ++d) co[d] = (int)(((t >> P.dim_tshift[d]) & ((1u << P.dim_tbits[d]) - 1u)) << P.dim_boxlog[d]);
-      qr_tma_prefetch(p ? &mx1 : &mx0, P.rank, co);
-      if (P.mode != 0) qr_tma_prefetch(p ? &my1 : &my0, P.rank, co);
-    };
-    const unsigned ahead = L.prefetch > 0 ? (unsigned)L.prefetch : 0u;
-    if (lane == 0)
-      for (unsigned k = 0; k < ahead; ++k) prefetch_item(blockIdx.x + k * gridDim.x);
-    long long st_ex = 0, st_dep = 0, st_ey = 0, st_tot = 0, st_n = 0;
+    long long st_ex = 0, st_dep = 0, st_ey = 0, st_n = 0;
     const long long st_t0 = clock64();
-    for (unsigned item = blockIdx.x;; item += gridDim.x) {
+    unsigned item = 0;
+    if (lane == 0) item = atomicAdd(L.queue, 1u);
+    while (true) {
+      item = __shfl_sync(0xffffffffu, item, 0);
       int p = 0;
-      unsigned t = 0, c = 0;
-      const bool more = tile_of(item, p, t, c);   // every lane decodes: no broadcast needed
+      unsigned t = 0, c = 0, j = 0;
+      const bool more = qr_decode(L, item, p, c, j);   // every lane decodes
       if (lane == 0) {
-        if (ahead > 0) prefetch_item(item + ahead * gridDim.x);
         const long long q0 = clock64();
         qr_mbar_wait(qr_smem(bars + 2 + stage), ((xphase >> stage) & 1u) ^ 1u);
         st_ex += clock64() - q0;
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
       }
       ++st_n;
       const QRPass &P = L.pass[p];
+      t = L.npass == 1 ? j : (qr_deposit(c, P.ncs, P.cs_l, P.cs_n, P.cs_d) | qr_deposit(j, P.njs, P.js_l, P.js_n, P.js_d));
       // tile-constant diagonal weight: lane k evaluates table k
       double dre = 0.0, dim = 0.0;
       if (P.n_pretile > 0) {
@@ -474,6 +476,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
         const unsigned long long pol = P.stream_out ? pol_stream : pol_keep;
         qr_mbar_expect(qr_smem(bars + stage), QR_TILE_BYTES);
         qr_tma_load(qr_smem(xs0 + stage * QR_TILE_BYTES), p ? &mx1 : &mx0, qr_smem(bars + stage), P.rank, co, pol);
+        item = atomicAdd(L.queue, 1u);   // the next item: its latency overlaps the wait below and the consumers' work
         if (P.mode != 0) {
           const long long q0 = clock64();
           qr_mbar_wait(qr_smem(bars + 5), (yphase & 1u) ^ 1u);
@@ -515,97 +518,118 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
     const QRPass &P = L.pass[it.pass];
     const unsigned char *xs = xs0 + stage * QR_TILE_BYTES;
     const unsigned char *tb = tabs + P.tab_smem_off;
-    const unsigned long long go = it.pass ? go1 : go0;
+    const uint4 *hr = recs + it.pass * QR_MAXC;
     const unsigned long long tbase = qr_expand(it.tile, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g);
     const unsigned long long gidx = tbase | P.hi_or;   // the thread bits enter the lookups through `tid` (selT)
     const unsigned g_lo = (unsigned)gidx, g_hi = (unsigned)(gidx >> 32);
 
     double2 acc[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc[u] = make_double2(0.0, 0.0);
     {
-      double2 xr[16];
+      {
+        // ---- own amplitudes in registers: diagonal weights and the bonds inside the R bits
+        double2 xr[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) xr[u] = *reinterpret_cast<const double2 *>(xs + so + u * 4096);
-      int c = P.n_pretile;
-      const int c_diag_end = P.n_pretile + P.n_pre + P.n_diagr;
-      if (c_diag_end > 0) {
-        // diagonal weight: tile constant (from the producer) + tables on thread bits + tables indexed by the R bits
-        double dre = it.dre, dim = it.dim;
-        for (; c < P.n_pretile + P.n_pre; ++c) {
-          const QRComp &cd = P.comps[c];
-          QRW<REALW> w;
-          w.load(tb + (size_t)(cd.tabE + qr_index(cd, tid, g_lo, g_hi)) * WB);
-          dre += w.re;
-          dim += w.im;
-        }
-        QRW<REALW> d[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          d[u].re = dre;
-          d[u].im = dim;
-        }
-        for (; c < c_diag_end; ++c) {
-          const QRComp &cd = P.comps[c];
-          const unsigned char *wt = tb + (size_t)(cd.tabE + qr_index(cd, tid, g_lo, g_hi) * 16u) * WB;
+        for (int u = 0; u < 16; ++u) xr[u] = *reinterpret_cast<const double2 *>(xs + so + u * QR_USTRIDE);
+        int c = P.n_pretile;
+        const int c_diag_end = P.n_pretile + P.n_pre + P.n_diagr;
+        if (c_diag_end > 0) {
+          // diagonal weight: tile constant (from the producer) + tables on thread bits + tables indexed by the R bits
+          double dre = it.dre, dim = it.dim;
+          for (; c < P.n_pretile + P.n_pre; ++c) {
+            QRW<REALW> w;
+            w.load(tb + qr_entry(hr[c], P.comps[c], 0u, tid, g_lo, g_hi) * WB);
+            dre += w.re;
+            dim += w.im;
+          }
+          QRW<REALW> d[16];
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            QRW<REALW> w;
-            w.load(wt + u * WB);
-            d[u].re += w.re;
-            d[u].im += w.im;
+            d[u].re = dre;
+            d[u].im = dim;
           }
-        }
+          for (; c < c_diag_end; ++c) {
+            const unsigned char *wt = tb + qr_entry(hr[c], P.comps[c], 4u, tid, g_lo, g_hi) * WB;
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          if (REALW) acc[u] = make_double2(d[u].re * xr[u].x, d[u].re * xr[u].y);
-          else acc[u] = make_double2(d[u].re * xr[u].x - d[u].im * xr[u].y, d[u].re * xr[u].y + d[u].im * xr[u].x);
-        }
-      } else {
+            for (int u = 0; u < 16; ++u) {
+              QRW<REALW> w;
+              w.load(wt + u * WB);
+              d[u].re += w.re;
+              d[u].im += w.im;
+            }
+          }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) acc[u] = make_double2(0.0, 0.0);
-      }
-      const int c_in_end = c_diag_end + P.n_inreg;
-      for (c = c_diag_end; c < c_in_end; ++c) {
-        const QRComp &cd = P.comps[c];
-        const unsigned sr = __popc((cd.kind >> 4) & 15u);
-        const unsigned char *wt = tb + (size_t)(cd.tabE + (qr_index(cd, tid, g_lo, g_hi) << sr)) * WB;
-        switch (cd.kind >> 4) {  // SELR | M << 4, SELR == M
-#define QR_IN(MM) \
-  case (MM | (MM << 4)): qr_inreg<REALW, MM, MM>(acc, xr, wt); break;
-          QR_IN(1) QR_IN(2) QR_IN(4) QR_IN(8) QR_IN(3) QR_IN(5) QR_IN(6) QR_IN(9) QR_IN(10) QR_IN(12)
+          for (int u = 0; u < 16; ++u) d[u].fma_into(acc[u], xr[u]);
+        }
+        const int c_in_end = c_diag_end + P.n_inreg;
+        for (c = c_diag_end; c < c_in_end; ++c) {
+          const uint4 cd = hr[c];
+          const unsigned char *wt = tb + qr_entry(cd, P.comps[c], __popc((cd.x >> 4) & 15u), tid, g_lo, g_hi) * WB;
+          switch (cd.x >> 16) {  // SELR == M
+#define QR_IN(CODE, MM) \
+  case CODE: qr_inreg<REALW, MM, MM>(acc, xr, wt); break;
+            QR_IN(0, 1) QR_IN(1, 2) QR_IN(2, 4) QR_IN(3, 8) QR_IN(4, 3) QR_IN(5, 5) QR_IN(6, 6) QR_IN(7, 9) QR_IN(8, 10) QR_IN(9, 12)
 #undef QR_IN
-          default: break;
+            default: break;
+          }
         }
       }
-    }
-    {
-      const int c0 = P.n_pretile + P.n_pre + P.n_diagr + P.n_inreg, c1 = c0 + P.n_gather;
-      for (int c = c0; c < c1; ++c) {
-        const QRComp &cd = P.comps[c];
-        const unsigned selr = (cd.kind >> 4) & 15u;
-        const unsigned sr = __popc(selr);
-        const unsigned char *wt = tb + (size_t)(cd.tabE + (qr_index(cd, tid, g_lo, g_hi) << sr)) * WB;
-        const unsigned char *xt = xs + (so ^ cd.xorB);   // xorB: thread bits of the mask only
-        const unsigned mxor = ((cd.kind >> 8) & 15u) << 12;  // R bits of the mask
-        if ((cd.kind & 15u) == QR_GATHER) {
-          if (mxor == 0) {
-            switch (selr) {
-#define QR_GA(SS) \
-  case SS: qr_gather<REALW, SS, false>(acc, xt, wt, 0u); break;
-              QR_GA(0) QR_GA(1) QR_GA(2) QR_GA(4) QR_GA(8) QR_GA(3) QR_GA(5) QR_GA(6) QR_GA(9) QR_GA(10) QR_GA(12)
-#undef QR_GA
-              default: break;
-            }
-          } else {
-            switch (selr) {
-#define QR_GA(SS) \
-  case SS: qr_gather<REALW, SS, true>(acc, xt, wt, mxor); break;
-              QR_GA(0) QR_GA(1) QR_GA(2) QR_GA(4) QR_GA(8) QR_GA(3) QR_GA(5) QR_GA(6) QR_GA(9) QR_GA(10) QR_GA(12)
-#undef QR_GA
-              default: break;
-            }
+      {
+        const int c0 = P.n_pretile + P.n_pre + P.n_diagr + P.n_inreg, c1 = c0 + P.n_gather;
+        int c = c0;
+        // ---- plain gathers first (one weight per thread, mask without R bits: the bulk of a pass).  No dispatch, and the
+        // loads of the next half-record are in flight while the DFMAs of the current one run.
+        const int cp = c0 + P.n_plain;
+        if (c < cp) {
+          double2 va[8], vb[8];
+          QRW<REALW> w;
+          const unsigned char *xt;
+          {
+            const uint4 cd = hr[c];
+            w.load(tb + qr_entry(cd, P.comps[c], 0u, tid, g_lo, g_hi) * WB);
+            xt = xs + (so ^ cd.w);
           }
-        } else {
-          qr_gather_slow<REALW>(acc, xt, wt, selr, mxor);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) va[u] = *reinterpret_cast<const double2 *>(xt + u * QR_USTRIDE);
+#pragma unroll 1
+          for (; c < cp; ++c) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) vb[u] = *reinterpret_cast<const double2 *>(xt + (8 + u) * QR_USTRIDE);
+            QRW<REALW> wn = w;
+            const unsigned char *xn = xt;
+            const bool more = c + 1 < cp;
+            if (more) {
+              const uint4 nd = hr[c + 1];
+              wn.load(tb + qr_entry(nd, P.comps[c + 1], 0u, tid, g_lo, g_hi) * WB);
+              xn = xs + (so ^ nd.w);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w.fma_into(acc[u], va[u]);
+            if (more) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) va[u] = *reinterpret_cast<const double2 *>(xn + u * QR_USTRIDE);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w.fma_into(acc[8 + u], vb[u]);
+            w = wn;
+            xt = xn;
+          }
+        }
+        for (; c < c1; ++c) {
+          const uint4 cd = hr[c];
+          const unsigned selr = (cd.x >> 4) & 15u;
+          const unsigned char *wt = tb + qr_entry(cd, P.comps[c], __popc(selr), tid, g_lo, g_hi) * WB;
+          const unsigned char *xt = xs + (so ^ cd.w);          // xorB: thread bits of the mask
+          const unsigned mxor = ((cd.x >> 8) & 15u) * (unsigned)QR_USTRIDE;  // R bits of the mask
+          switch (cd.x >> 16) {  // 0..10: mask without R bits; 11..21: with R bits; 22: any selector pattern
+#define QR_GA(CODE, SS)                                              \
+  case CODE: qr_gather<REALW, SS, false>(acc, xt, wt, 0u); break;    \
+  case CODE + 11: qr_gather<REALW, SS, true>(acc, xt, wt, mxor); break;
+            QR_GA(0, 0) QR_GA(1, 1) QR_GA(2, 2) QR_GA(3, 4) QR_GA(4, 8) QR_GA(5, 3) QR_GA(6, 5) QR_GA(7, 6) QR_GA(8, 9) QR_GA(9, 10) QR_GA(10, 12)
+#undef QR_GA
+            default: qr_gather_slow<REALW>(acc, xt, wt, selr, mxor); break;
+          }
         }
       }
     }
@@ -624,7 +648,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
       yphase ^= 1u;
       double2 yo[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) yo[u] = *reinterpret_cast<const double2 *>(ysb + so + u * 4096);
+      for (int u = 0; u < 16; ++u) yo[u] = *reinterpret_cast<const double2 *>(ysb + so + u * QR_USTRIDE);
       __syncwarp();
       if ((tid & 31u) == 0) qr_mbar_arrive(qr_smem(bars + 5));
       if (P.mode == 1) {
@@ -643,20 +667,22 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
         acc[u] = make_double2(L.alpha.x * acc[u].x - L.alpha.y * acc[u].y, L.alpha.x * acc[u].y + L.alpha.y * acc[u].x);
     }
     {
-      double2 *yp[16];
-      yp[0] = y + tbase + go;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int u = 0; u < (1 << k); ++u) yp[(1 << k) + u] = yp[u] + P.rstride[k];
-      if (P.stream_out) {
-#pragma unroll
-        for (int u = 0; u < 16; ++u)
-          asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(yp[u]), "d"(acc[u].x), "d"(acc[u].y), "l"(pol_stream) : "memory");
-      } else {
-#pragma unroll
-        for (int u = 0; u < 16; ++u) *yp[u] = acc[u];
-      }
+      // stores in Gray-code order of u: one 64-bit add per amplitude, no pointer array held in registers
+      double2 *yp = y + tbase + (it.pass ? go1 : go0);
+      const unsigned long long s0 = P.rstride[0], s1 = P.rstride[1], s2 = P.rstride[2], s3 = P.rstride[3];
+#define QR_ST(U)                                                                                                                  \
+  do {                                                                                                                            \
+    if (P.stream_out)                                                                                                             \
+      asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(yp), "d"(acc[U].x), "d"(acc[U].y), "l"(pol_stream) \
+                   : "memory");                                                                                                   \
+    else                                                                                                                          \
+      *yp = acc[U];                                                                                                               \
+  } while (0)
+      QR_ST(0);  yp += s0; QR_ST(1);  yp += s1; QR_ST(3);  yp -= s0; QR_ST(2);
+      yp += s2; QR_ST(6);  yp += s0; QR_ST(7);  yp -= s1; QR_ST(5);  yp -= s0; QR_ST(4);
+      yp += s3; QR_ST(12); yp += s0; QR_ST(13); yp += s1; QR_ST(15); yp -= s0; QR_ST(14);
+      yp -= s2; QR_ST(10); yp += s0; QR_ST(11); yp -= s1; QR_ST(9);  yp -= s0; QR_ST(8);
+#undef QR_ST
     }
     if (P.signal) {  // one count per consumer warp: no CTA-wide barrier
       __syncwarp();
@@ -812,6 +838,7 @@ static void qr_layout(QRPassHost &ph, int nbits, uint64_t hi_value) {
   for (int i = 0; i < nbits; ++i)
     if (std::find(fb.begin(), fb.end(), i) == fb.end()) fixed.push_back(i);
   qr_segments(fixed, P.xs_l, P.xs_n, P.xs_g, P.nfixed_seg);
+  qr_segments(fb, P.fs_l, P.fs_n, P.fs_g, P.nfree_seg);
   P.hi_or = (nbits >= 64) ? 0ull : (hi_value << nbits);
 }
 
@@ -1089,6 +1116,7 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
     QRPass &P = ph->params;
     memset(&P, 0, sizeof(P));
     qr_layout(*ph, nbits, hi_value);
+    if (P.nfree_seg > QR_MAXSEG || P.nfixed_seg > QR_MAXSEG) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: too many index segments");
     if (!qr_tensor_geometry(*ph, nbits)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: tile shape needs a tensor map of rank > 5");
     std::vector<int> rg;  // flat-index bits of R, ascending
     for (int k : ph->rpos) rg.push_back(ph->free_bits[k]);
@@ -1154,6 +1182,29 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
       r.kind = kind;
       r.nT = (uint32_t)tb_.size();
       r.xorB = xorB;
+      {
+        // fast path: no tile-part selectors and at most one run of thread bits; the table index of the run is shifted past
+        // the selector bits inside R (all 4 of them for a diagR table)
+        const unsigned cls = kind & 15u;
+        const unsigned shift = cls == QR_DIAGR ? 4u : (cls == QR_PRE || cls == QR_PRE_TILE ? 0u : (unsigned)__builtin_popcount((kind >> 4) & 15u));
+        if (r.selG == 0 && (r.selT >> 9) == 0) {
+          const unsigned sh = r.selT & 63u, w = (r.selT >> 6) & 7u;
+          r.fast = (sh & 31u) | (((1u << w) - 1u) << 8) | (shift << 16);
+        } else {
+          r.fast = 1u << 31;
+        }
+        // dense body numbers (see the dispatch switches of the kernel)
+        static const int order[11] = {0, 1, 2, 4, 8, 3, 5, 6, 9, 10, 12};
+        const unsigned selr = (kind >> 4) & 15u, mR = (kind >> 8) & 15u;
+        r.code = 255;
+        if (cls == QR_INREG) {
+          for (int q = 1; q < 11; ++q)
+            if ((unsigned)order[q] == mR) r.code = (uint32_t)(q - 1);
+        } else if (cls == QR_GATHER) {
+          for (int q = 0; q < 11; ++q)
+            if ((unsigned)order[q] == selr) r.code = (uint32_t)(q + (mR ? 11 : 0));
+        }
+      }
       r.tabE = tab_off;
       t.tab_off = tab_off;
       tab_off += 1u << t.bits.size();
@@ -1233,8 +1284,22 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
     for (int id : inreg_ids)
       if (!flip_record(id, QR_INREG)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
     P.n_inreg = (int)inreg_ids.size();
-    for (int id : gather_ids)
-      if (!flip_record(id, QR_GATHER)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
+    {
+      // plain gathers (no selector bit and no mask bit inside R) first: the kernel runs them in its pipelined loop
+      auto is_plain = [&](int id) {
+        const QRCompHost &c = h->comps[id];
+        uint64_t sb = 0;
+        for (int b : c.sel) sb |= 1ull << b;
+        return !(sb & rbits[p]) && !(c.mask & rbits[p]);
+      };
+      std::stable_partition(gather_ids.begin(), gather_ids.end(), is_plain);
+      int nplain = 0;
+      for (int id : gather_ids) {
+        if (!flip_record(id, QR_GATHER)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: selector bits too scattered");
+        if (is_plain(id) && recs.back().code == 0) ++nplain;
+      }
+      P.n_plain = nplain;
+    }
     P.n_gather = (int)gather_ids.size();
     if (recs.size() > QR_MAXC) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: %d lookup records in one pass (max %d)", (int)recs.size(), QR_MAXC);
     for (size_t i = 0; i < recs.size(); ++i) P.comps[i] = recs[i];
@@ -1408,7 +1473,7 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
     Lp.nchunks = g.nchunks;
     Lp.lag = g.lag;
     Lp.total_items = ntiles * (unsigned)g.count;
-    Lp.prefetch = qr_env_int("QOB_QREG_PREFETCH", 0);
+    Lp.prefetch = 0;
     static long long *stats_buf = nullptr;
     const bool want_stats = qr_env_int("QOB_QREG_STATS", 0) != 0;
     if (want_stats && !stats_buf) QOB_CUDA(cudaMalloc(&stats_buf, 16 * 256 * sizeof(long long)));
@@ -1444,7 +1509,7 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
       maps[2] = maps[0];
       maps[3] = maps[1];
     }
-    const size_t smem = 3 * (size_t)QR_TILE_BYTES + tab_off + 16 + 64 + 2 * sizeof(QRItem) + 64 + 128;
+    const size_t smem = 3 * (size_t)QR_TILE_BYTES + tab_off + 16 + 64 + 2 * sizeof(QRItem) + 2 * QR_MAXC * 16 + 128;
     QOB_CUDA(cudaMemsetAsync(sync, 0, (32 + (size_t)g.nchunks) * sizeof(unsigned), s));
     const unsigned grid = std::min<unsigned>((unsigned)sms, ntiles * (unsigned)g.count);
     auto launch = [&](auto kern) -> int {

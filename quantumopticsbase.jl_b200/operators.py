@@ -97,6 +97,27 @@ class CompositeBasis(Basis):
         return ("CompositeBasis", tuple(b._ckey() for b in self.bases))
 
 
+class SumBasis(Basis):
+    """SumBasis(b1, b2, …) (src/spinors.jl:1-17): direct sum of bases, shape = the lengths of the parts."""
+
+    def __init__(self, *bases):
+        if len(bases) == 1 and isinstance(bases[0], (list, tuple)):
+            bases = tuple(bases[0])
+        self.bases = list(bases)
+        Basis.__init__(self, tuple(len(b) for b in self.bases))
+        self._len = sum(len(b) for b in self.bases)
+
+    def _key(self):
+        return ("SumBasis", tuple(b._ckey() for b in self.bases))
+
+
+def directsum(*bases):
+    out = []
+    for b in bases:
+        out.extend(b.bases if isinstance(b, SumBasis) else [b])
+    return SumBasis(out)
+
+
 def tensor(*xs):
     """b1 ⊗ b2 ⊗ …  for bases (composite bases are flattened like the reference's `tensor`)."""
     if all(isinstance(x, Basis) for x in xs):
@@ -481,6 +502,21 @@ def _factor_struct(d, keep):
     return f
 
 
+class LazyDirectSum(AbstractOperator):
+    """LazyDirectSum(op1, op2, …) (src/spinors.jl:158-169): block-diagonal operator on SumBases; nested sums are flattened.
+    `mul_` exists for Ket and Bra states only, like the reference (src/spinors.jl:221-247)."""
+
+    def __init__(self, *ops):
+        flat = []
+        for o in ops:
+            flat.extend(o.operators if isinstance(o, LazyDirectSum) else [o])
+        if not flat:
+            raise ArgumentError("LazyDirectSum needs at least one operator")
+        self.operators = flat
+        self.basis_l = directsum(*[o.basis_l for o in flat])
+        self.basis_r = directsum(*[o.basis_r for o in flat])
+
+
 def handle(op, ctx=None):
     """libqob200 handle of an operator definition (built once, cached on the object)."""
     ctx = _lib.context() if ctx is None else ctx
@@ -527,6 +563,10 @@ def handle(op, ctx=None):
         hs = [handle(o, ctx) for o in op.operators]
         arr = (C.c_void_p * len(hs))(*[x.value if isinstance(x, C.c_void_p) else x for x in hs])
         _lib.check(lib.qob_lazyproduct_create(ctx, len(hs), arr, c64.of(op.factor), C.byref(h)))
+    elif isinstance(op, LazyDirectSum):
+        hs = [handle(o, ctx) for o in op.operators]
+        arr = (C.c_void_p * len(hs))(*[x.value if isinstance(x, C.c_void_p) else x for x in hs])
+        _lib.check(lib.qob_lazydirectsum_create(ctx, len(hs), arr, C.byref(h)))
     else:
         raise MethodError(f"no mul! method for operator type {type(op).__name__}")
     op._handle, op._handle_ctx = h, ctx
@@ -843,17 +883,16 @@ def launch_count():
 
 
 def expect(op, state):
-    """expect(op, state) (src/operators.jl:119-142): <psi|op|psi> for a Ket, tr(op*rho) for a dense device Operator —
-    `mul!` into scratch followed by one device reduction (only the result crosses to the host)."""
+    """expect(op, state) (src/operators.jl:119-142): <psi|op|psi> for a Ket (`qob_expect`: mul! into the handle's scratch and one
+    deterministic device reduction, only the scalar crosses to the host), tr(op*rho) for a dense device Operator."""
     import torch
 
     if isinstance(state, Ket):
-        tmp = getattr(op, "_expect_tmp", None)
-        if tmp is None or tmp.basis != op.basis_l:
-            tmp = Ket(op.basis_l)
-            op._expect_tmp = tmp
-        mul_(tmp, op, state, 1.0, 0.0)
-        return dot(state.data, tmp.data)
+        if op.basis_r != state.basis or op.basis_l != state.basis:
+            raise IncompatibleBases()
+        out = c64()
+        _lib.check(lib.qob_expect(handle(op), C.c_void_p(state.data.data_ptr()), C.byref(out), _stream()))
+        return complex(out.re, out.im)
     if _is_state_op(state):
         tmp = DenseOperator(op.basis_l, state.basis_r)
         mul_(tmp, op, state, 1.0, 0.0)
@@ -862,16 +901,74 @@ def expect(op, state):
 
 
 def variance(op, state):
-    """variance(op, state) = <op^2> - <op>^2 (src/operators.jl:139-150), as ||op psi||^2 - |<op>|^2 ... for a Ket
-    computed with two mul! applications like the reference (op*(op*state))."""
+    """variance(op, state) = psi'(op(op psi)) - (psi'(op psi))^2 (src/operators.jl:139-142): `qob_variance`, two applications
+    like the reference."""
     if not isinstance(state, Ket):
         raise MethodError("variance: only Ket states are supported on the device path")
-    t1, t2 = Ket(op.basis_l), Ket(op.basis_l)
-    mul_(t1, op, state, 1.0, 0.0)
-    mul_(t2, op, t1, 1.0, 0.0)
-    e1 = dot(state.data, t1.data)
-    e2 = dot(state.data, t2.data)
-    return e2 - e1 * e1
+    if op.basis_r != state.basis or op.basis_l != state.basis:
+        raise IncompatibleBases()
+    out = c64()
+    _lib.check(lib.qob_variance(handle(op), C.c_void_p(state.data.data_ptr()), C.byref(out), _stream()))
+    return complex(out.re, out.im)
+
+
+def ptrace(a, indices):
+    """ptrace(a, indices) (src/operators_dense.jl:191-215): partial trace of a dense device Operator, a Ket or a Bra over the
+    1-based subsystem `indices`; the result is a dense device Operator on the remaining subsystems."""
+    import torch
+
+    idx = [int(indices)] if isinstance(indices, (int, np.integer)) else [int(i) for i in indices]
+    tr = (C.c_int32 * max(len(idx), 1))(*idx)
+    ctx = _lib.context()
+
+    def reduced_basis(b):
+        if not isinstance(b, CompositeBasis):
+            raise ArgumentError("Partial trace can only be applied onto operators with composite bases.")
+        kept = [bb for k, bb in enumerate(b.bases) if (k + 1) not in idx]
+        return kept[0] if len(kept) == 1 else CompositeBasis(kept)
+
+    if isinstance(a, (Ket, Bra)):
+        b = a.basis
+        if not isinstance(b, CompositeBasis):
+            raise ArgumentError("Partial trace can only be applied onto states with composite bases.")
+        dims = (C.c_int64 * len(b.shape))(*b.shape)
+        # argument errors (all subsystems traced, bad index) are raised by the library before anything is allocated
+        m = 1
+        for k, d in enumerate(b.shape):
+            if (k + 1) not in idx:
+                m *= d
+        res = torch.empty((m, m), dtype=torch.complex128, device=a.data.device).t()   # column-major m x m
+        _lib.check(lib.qob_ptrace_state(ctx, len(b.shape), dims, len(idx), tr, 1 if isinstance(a, Bra) else 0,
+                                        C.c_void_p(a.data.data_ptr()), C.c_void_p(res.data_ptr()), _stream()))
+        rb = reduced_basis(b) if len(idx) < len(b.shape) else b
+        return DenseOperator(rb, rb, res)
+    if isinstance(a, Operator) and a.is_device_dense:
+        bl, br = a.basis_l, a.basis_r
+        if not isinstance(bl, CompositeBasis) or not isinstance(br, CompositeBasis):
+            raise ArgumentError("Partial trace can only be applied onto operators with composite bases.")
+        if len(bl.shape) != len(br.shape):
+            raise ArgumentError("Partial trace can only be applied onto operators wich have the same number of subsystems in the "
+                                "left basis and right basis.")
+        dl = (C.c_int64 * len(bl.shape))(*bl.shape)
+        dr = (C.c_int64 * len(br.shape))(*br.shape)
+        ml = mr = 1
+        for k in range(len(bl.shape)):
+            if (k + 1) not in idx:
+                ml *= bl.shape[k]
+                mr *= br.shape[k]
+        res = torch.empty((mr, ml), dtype=torch.complex128, device=a.data.device).t()   # column-major ml x mr
+        _lib.check(lib.qob_ptrace_op(ctx, len(bl.shape), dl, dr, len(idx), tr, C.c_void_p(a.data.data_ptr()), C.c_void_p(res.data_ptr()),
+                                     _stream()))
+        return DenseOperator(reduced_basis(bl), reduced_basis(br), res)
+    raise MethodError(f"ptrace: unsupported argument type {type(a).__name__}")
+
+
+def reduced(a, indices):
+    """reduced(a, indices) (QuantumInterface): the state of the subsystems `indices` = ptrace over their complement."""
+    idx = [int(indices)] if isinstance(indices, (int, np.integer)) else [int(i) for i in indices]
+    b = a.basis if isinstance(a, (Ket, Bra)) else a.basis_l
+    n = len(b.shape)
+    return ptrace(a, [k for k in range(1, n + 1) if k not in idx])
 
 
 def profile_enable(on=True):
