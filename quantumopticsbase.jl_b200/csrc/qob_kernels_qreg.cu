@@ -35,8 +35,9 @@
 #define QR_TILE (1 << QR_T)
 #define QR_TILE_BYTES (QR_TILE * 16)
 #define QR_CTHREADS 256                 // consumer threads (8 warps), 16 amplitudes each
-#define QR_THREADS (QR_CTHREADS + 32)   // + one producer warp
+#define QR_THREADS (QR_CTHREADS + 64)   // + one loader warp and one storer warp
 #define QR_USTRIDE 4096                 // byte distance in the staged tile between consecutive amplitudes u of a thread
+#define QR_NSTAGE 3                     // tile buffers: one being loaded, one being worked on, one being stored
 #define QR_MAXC 40                      // lookup records per pass (kernel parameter space)
 #define QR_MAXSEG 8
 #define QR_DIAG_WINDOW 6
@@ -149,6 +150,28 @@ __device__ __forceinline__ void qr_tma_load(unsigned dst, const CUtensorMap *map
       break;
   }
 }
+// result tile: shared memory -> global through the tensor map, either a plain store (first pass, beta == 0: y is never read)
+// or an f64 add performed by the L2 (every other pass: y += tile) — no y load, no per-thread global stores
+__device__ __forceinline__ void qr_tma_store(const CUtensorMap *map, unsigned src, int rank, const int *c, bool add) {
+  const unsigned long long m = (unsigned long long)map;
+#define QR_TS(N, COORDS, ...)                                                                                                          \
+  if (add)                                                                                                                             \
+    asm volatile("cp.reduce.async.bulk.tensor." N ".global.shared::cta.add.tile.bulk_group [%0, " COORDS "], [%1];\n" ::"l"(m), "r"(src), \
+                 __VA_ARGS__                                                                                                           \
+                 : "memory");                                                                                                          \
+  else                                                                                                                                 \
+    asm volatile("cp.async.bulk.tensor." N ".global.shared::cta.tile.bulk_group [%0, " COORDS "], [%1];\n" ::"l"(m), "r"(src), __VA_ARGS__ \
+                 : "memory");
+  switch (rank) {
+    case 1: QR_TS("1d", "{%2}", "r"(c[0])) break;
+    case 2: QR_TS("2d", "{%2, %3}", "r"(c[0]), "r"(c[1])) break;
+    case 3: QR_TS("3d", "{%2, %3, %4}", "r"(c[0]), "r"(c[1]), "r"(c[2])) break;
+    case 4: QR_TS("4d", "{%2, %3, %4, %5}", "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3])) break;
+    default: QR_TS("5d", "{%2, %3, %4, %5, %6}", "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])) break;
+  }
+#undef QR_TS
+}
+
 // pull a tile into L2 without occupying shared memory (the DRAM latency is paid here, several tiles ahead)
 __device__ __forceinline__ void qr_tma_prefetch(const CUtensorMap *map, int rank, const int *c) {
   const unsigned long long m = (unsigned long long)map;
@@ -312,12 +335,14 @@ __device__ __forceinline__ void qr_gather_slow(double2 (&acc)[16], const unsigne
   }
 }
 
-struct QRItem {     // 32 bytes, written by the producer for the consumers
+struct QRItem {     // 64 bytes, written by the producer for the consumers
   int pass;         // -1: no more work
   unsigned tile;    // compact tile id
   unsigned chunk;
   unsigned pad;
   double dre, dim;  // diagonal weight that is the same for every amplitude of the tile
+  int co[5];        // tensor-map coordinates of the tile (the result goes out through the same box)
+  int pad2[3];
 };
 
 // work item -> (pass, chunk, tile within chunk); false when the queue is exhausted
@@ -353,29 +378,27 @@ __device__ __forceinline__ bool qr_decode(const QRLaunch &L, unsigned item, int 
 template <bool REALW>
 __global__ void __launch_bounds__(QR_THREADS, 1)
     qreg_kernel(const __grid_constant__ QRLaunch L, const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUtensorMap my0,
-                const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap my1, double2 *__restrict__ y) {
+                const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap my1) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((128u - (qr_smem(smem_raw) & 127u)) & 127u);  // TMA destinations: 128-byte aligned
-  unsigned char *xs0 = smem;                              // two x stages
-  unsigned char *ysb = smem + 2 * QR_TILE_BYTES;          // y of a read-modify-write tile
-  unsigned char *tabs = smem + 3 * QR_TILE_BYTES;         // weight tables of the pass(es)
+  unsigned char *xs0 = smem;                              // QR_NSTAGE tile buffers: x comes in, the result tile leaves from the same one
+  unsigned char *tabs = smem + QR_NSTAGE * QR_TILE_BYTES; // weight tables of the pass(es)
   const unsigned tab_total = L.pass[0].tab_bytes + (L.npass > 1 ? L.pass[1].tab_bytes : 0u);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(tabs + ((tab_total + 15u) & ~15u));
-  // bars[0,1]: x full; [2,3]: x empty; [4]: y full; [5]: y empty
-  QRItem *slots = reinterpret_cast<QRItem *>(bars + 8);
+  // bars[s]: x of stage s has landed; [3+s]: stage s is free; [6+s]: the result tile of stage s is staged
+  QRItem *slots = reinterpret_cast<QRItem *>(bars + 12);
   // hot half of every lookup record {kind | code << 16, tabE, fast, xorB}: read with one broadcast LDS.128 instead of
   // indexed constant-bank loads (7 KB of parameters do not stay in the immediate-constant cache)
-  uint4 *recs = reinterpret_cast<uint4 *>(slots + 2);
+  uint4 *recs = reinterpret_cast<uint4 *>(slots + QR_NSTAGE);
   const unsigned tid = threadIdx.x;
   constexpr int WB = REALW ? 8 : 16;
 
   if (tid == 0) {
-    qr_mbar_init(qr_smem(bars + 0), 1);
-    qr_mbar_init(qr_smem(bars + 1), 1);
-    qr_mbar_init(qr_smem(bars + 2), QR_CTHREADS / 32);
-    qr_mbar_init(qr_smem(bars + 3), QR_CTHREADS / 32);
-    qr_mbar_init(qr_smem(bars + 4), 1);
-    qr_mbar_init(qr_smem(bars + 5), QR_CTHREADS / 32);
+    for (int st = 0; st < QR_NSTAGE; ++st) {
+      qr_mbar_init(qr_smem(bars + st), 1);
+      qr_mbar_init(qr_smem(bars + 3 + st), 1);
+      qr_mbar_init(qr_smem(bars + 6 + st), QR_CTHREADS / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
   }
   for (int p = 0; p < L.npass; ++p) {
@@ -389,6 +412,34 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
   }
   __syncthreads();
 
+  if (tid >= QR_CTHREADS + 32) {
+    // ------------------------------------------------------------------ storer (one thread)
+    // Sends every staged result tile to global memory with one TMA instruction — a plain store for the pass that defines y,
+    // an f64 add performed by the L2 for every other pass — frees the staging buffer as soon as the copy engine has read it,
+    // and announces finished pass-1 tiles of a chained pair once their writes are complete.
+    if (tid == QR_CTHREADS + 32) {
+      unsigned stage = 0, ophase = 0;   // bit s of ophase: parity of the next wait on staged[s]
+      while (true) {
+        qr_mbar_wait(qr_smem(bars + 6 + stage), (ophase >> stage) & 1u);
+        ophase ^= 1u << stage;
+        const QRItem it = slots[stage];
+        if (it.pass < 0) break;
+        const QRPass &P = L.pass[it.pass];
+        qr_tma_store(it.pass ? &my1 : &my0, qr_smem(xs0 + stage * QR_TILE_BYTES), P.rank, it.co, P.mode != 0);
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        qr_mbar_arrive(qr_smem(bars + 3 + stage));   // the buffer may be loaded again
+        if (P.signal) {
+          asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+          __threadfence();
+          atomicAdd(L.done + it.chunk, 1u);
+        }
+        stage = stage + 1 == QR_NSTAGE ? 0 : stage + 1;
+      }
+      asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    }
+    return;
+  }
   if (tid >= QR_CTHREADS) {
     // ------------------------------------------------------------------ producer warp
     // Lane 0 claims work items from the ordered queue (the next one while the current loads are in flight, so the latency
@@ -398,7 +449,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
     unsigned long long pol_keep, pol_stream;
     asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_keep));
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-    unsigned stage = 0, xphase = 0, yphase = 0;  // bit s of xphase: parity of the next wait on x-empty[s]
+    unsigned stage = 0, xphase = 0;  // bit s of xphase: parity of the next wait on x-empty[s]
     long long st_ex = 0, st_dep = 0, st_ey = 0, st_n = 0;
     const long long st_t0 = clock64();
     unsigned item = 0;
@@ -410,7 +461,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
       const bool more = qr_decode(L, item, p, c, j);   // every lane decodes
       if (lane == 0) {
         const long long q0 = clock64();
-        qr_mbar_wait(qr_smem(bars + 2 + stage), ((xphase >> stage) & 1u) ^ 1u);
+        qr_mbar_wait(qr_smem(bars + 3 + stage), ((xphase >> stage) & 1u) ^ 1u);
         st_ex += clock64() - q0;
         xphase ^= 1u << stage;
       }
@@ -420,6 +471,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
           it.pass = -1;
           it.tile = it.chunk = it.pad = 0;
           it.dre = it.dim = 0.0;
+          for (int d = 0; d < 5; ++d) it.co[d] = 0;
           slots[stage] = it;
           qr_mbar_arrive(qr_smem(bars + stage));
           if (L.stats) {
@@ -451,6 +503,9 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
         }
       }
       if (lane == 0) {
+        int co[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) co[d] = (int)(((t >> P.dim_tshift[d]) & ((1u << P.dim_tbits[d]) - 1u)) << P.dim_boxlog[d]);
         QRItem it;
         it.pass = p;
         it.tile = t;
@@ -458,9 +513,11 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
         it.pad = 0;
         it.dre = dre;
         it.dim = dim;
+#pragma unroll
+        for (int d = 0; d < 5; ++d) it.co[d] = co[d];
         slots[stage] = it;
         if (P.wait) {
-          const unsigned need = (QR_CTHREADS / 32u) << L.tpc_log2;   // every consumer warp of every pass-1 tile of the chunk
+          const unsigned need = 1u << L.tpc_log2;   // every pass-1 tile of the chunk
           unsigned have;
           const long long q0 = clock64();
           do {
@@ -470,41 +527,20 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
           st_dep += clock64() - q0;
           asm volatile("fence.proxy.async;\n" ::: "memory");  // the tiles written by other CTAs are read by the async proxy
         }
-        int co[5];
-#pragma unroll
-        for (int d = 0; d < 5; ++d) co[d] = (int)(((t >> P.dim_tshift[d]) & ((1u << P.dim_tbits[d]) - 1u)) << P.dim_boxlog[d]);
         const unsigned long long pol = P.stream_out ? pol_stream : pol_keep;
         qr_mbar_expect(qr_smem(bars + stage), QR_TILE_BYTES);
         qr_tma_load(qr_smem(xs0 + stage * QR_TILE_BYTES), p ? &mx1 : &mx0, qr_smem(bars + stage), P.rank, co, pol);
-        item = atomicAdd(L.queue, 1u);   // the next item: its latency overlaps the wait below and the consumers' work
-        if (P.mode != 0) {
-          const long long q0 = clock64();
-          qr_mbar_wait(qr_smem(bars + 5), (yphase & 1u) ^ 1u);
-          st_ey += clock64() - q0;
-          yphase ^= 1u;
-          qr_mbar_expect(qr_smem(bars + 4), QR_TILE_BYTES);
-          qr_tma_load(qr_smem(ysb), p ? &my1 : &my0, qr_smem(bars + 4), P.rank, co, pol);
-        }
+        item = atomicAdd(L.queue, 1u);   // the next item: its latency overlaps the consumers' work
       }
       __syncwarp();
-      stage ^= 1u;
+      stage = stage + 1 == QR_NSTAGE ? 0 : stage + 1;
     }
     return;
   }
 
   // -------------------------------------------------------------------- consumers
-  unsigned long long pol_stream;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-  // element offset in global memory of this thread's amplitude u = 0, for either pass
-  unsigned long long go0 = 0, go1 = 0;
-#pragma unroll
-  for (int b = 0; b < 8; ++b)
-    if ((tid >> b) & 1u) {
-      go0 |= 1ull << L.pass[0].tgbit[b];
-      go1 |= 1ull << L.pass[1].tgbit[b];
-    }
   const unsigned so = tid * 16u;
-  unsigned stage = 0, xphase = 0, yphase = 0;
+  unsigned stage = 0, xphase = 0;
   long long sc_wx = 0, sc_cmp = 0, sc_wy = 0, sc_epi = 0;
 #pragma unroll 1
   while (true) {
@@ -543,24 +579,37 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
             dre += w.re;
             dim += w.im;
           }
-          QRW<REALW> d[16];
+          if (REALW) {
+            double d[16];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            d[u].re = dre;
-            d[u].im = dim;
-          }
-          for (; c < c_diag_end; ++c) {
-            const unsigned char *wt = tb + qr_entry(hr[c], P.comps[c], 4u, tid, g_lo, g_hi) * WB;
+            for (int u = 0; u < 16; ++u) d[u] = dre;
+            for (; c < c_diag_end; ++c) {
+              const unsigned char *wt = tb + qr_entry(hr[c], P.comps[c], 4u, tid, g_lo, g_hi) * WB;
+#pragma unroll
+              for (int u = 0; u < 16; ++u) d[u] += *reinterpret_cast<const double *>(wt + u * 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc[u] = make_double2(d[u] * xr[u].x, d[u] * xr[u].y);
+          } else {
+            QRW<REALW> d[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
-              QRW<REALW> w;
-              w.load(wt + u * WB);
-              d[u].re += w.re;
-              d[u].im += w.im;
+              d[u].re = dre;
+              d[u].im = dim;
             }
-          }
+            for (; c < c_diag_end; ++c) {
+              const unsigned char *wt = tb + qr_entry(hr[c], P.comps[c], 4u, tid, g_lo, g_hi) * WB;
 #pragma unroll
-          for (int u = 0; u < 16; ++u) d[u].fma_into(acc[u], xr[u]);
+              for (int u = 0; u < 16; ++u) {
+                QRW<REALW> w;
+                w.load(wt + u * WB);
+                d[u].re += w.re;
+                d[u].im += w.im;
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) d[u].fma_into(acc[u], xr[u]);
+          }
         }
         const int c_in_end = c_diag_end + P.n_inreg;
         for (c = c_diag_end; c < c_in_end; ++c) {
@@ -633,67 +682,25 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
         }
       }
     }
-    // all reads of this x stage are done
-    __syncwarp();
-    if ((tid & 31u) == 0) qr_mbar_arrive(qr_smem(bars + 2 + stage));
+    // all reads of this tile are done by every consumer warp: its buffer now takes the result tile, alpha * acc, which the
+    // storer thread sends off through TMA; the buffer returns to the loader when the copy engine has read it
+    asm volatile("bar.sync 1, %0;\n" ::"n"(QR_CTHREADS) : "memory");
     q0 = clock64();
     sc_cmp += q0 - q1;
-
-    // ---- epilogue
-    if (P.mode != 0) {
-      qr_mbar_wait(qr_smem(bars + 4), yphase & 1u);
-      q1 = clock64();
-      sc_wy += q1 - q0;
-      q0 = q1;
-      yphase ^= 1u;
-      double2 yo[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) yo[u] = *reinterpret_cast<const double2 *>(ysb + so + u * QR_USTRIDE);
-      __syncwarp();
-      if ((tid & 31u) == 0) qr_mbar_arrive(qr_smem(bars + 5));
-      if (P.mode == 1) {
-#pragma unroll
-        for (int u = 0; u < 16; ++u)
-          yo[u] = make_double2(L.beta.x * yo[u].x - L.beta.y * yo[u].y, L.beta.x * yo[u].y + L.beta.y * yo[u].x);
-      }
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        acc[u] = make_double2(fma(L.alpha.x, acc[u].x, fma(-L.alpha.y, acc[u].y, yo[u].x)),
-                              fma(L.alpha.x, acc[u].y, fma(L.alpha.y, acc[u].x, yo[u].y)));
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < 16; ++u)
-        acc[u] = make_double2(L.alpha.x * acc[u].x - L.alpha.y * acc[u].y, L.alpha.x * acc[u].y + L.alpha.y * acc[u].x);
+    for (int u = 0; u < 16; ++u) {
+      const double2 o = make_double2(L.alpha.x * acc[u].x - L.alpha.y * acc[u].y, L.alpha.x * acc[u].y + L.alpha.y * acc[u].x);
+      *reinterpret_cast<double2 *>(const_cast<unsigned char *>(xs) + so + u * QR_USTRIDE) = o;
     }
-    {
-      // stores in Gray-code order of u: one 64-bit add per amplitude, no pointer array held in registers
-      double2 *yp = y + tbase + (it.pass ? go1 : go0);
-      const unsigned long long s0 = P.rstride[0], s1 = P.rstride[1], s2 = P.rstride[2], s3 = P.rstride[3];
-#define QR_ST(U)                                                                                                                  \
-  do {                                                                                                                            \
-    if (P.stream_out)                                                                                                             \
-      asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(yp), "d"(acc[U].x), "d"(acc[U].y), "l"(pol_stream) \
-                   : "memory");                                                                                                   \
-    else                                                                                                                          \
-      *yp = acc[U];                                                                                                               \
-  } while (0)
-      QR_ST(0);  yp += s0; QR_ST(1);  yp += s1; QR_ST(3);  yp -= s0; QR_ST(2);
-      yp += s2; QR_ST(6);  yp += s0; QR_ST(7);  yp -= s1; QR_ST(5);  yp -= s0; QR_ST(4);
-      yp += s3; QR_ST(12); yp += s0; QR_ST(13); yp += s1; QR_ST(15); yp -= s0; QR_ST(14);
-      yp -= s2; QR_ST(10); yp += s0; QR_ST(11); yp -= s1; QR_ST(9);  yp -= s0; QR_ST(8);
-#undef QR_ST
-    }
-    if (P.signal) {  // one count per consumer warp: no CTA-wide barrier
-      __syncwarp();
-      if ((tid & 31u) == 0) {
-        __threadfence();
-        atomicAdd(L.done + it.chunk, 1u);
-      }
-    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the bulk copy engine
+    __syncwarp();
+    if ((tid & 31u) == 0) qr_mbar_arrive(qr_smem(bars + 6 + stage));
     sc_epi += clock64() - q0;
-    stage ^= 1u;
+    stage = stage + 1 == QR_NSTAGE ? 0 : stage + 1;
   }
+  // the loader's end marker sits in slots[stage]: pass it on to the storer
+  __syncwarp();
+  if ((tid & 31u) == 0) qr_mbar_arrive(qr_smem(bars + 6 + stage));
   if (L.stats && (tid & 31u) == 0) {
     long long *o = L.stats + 16 * blockIdx.x + 8;
     if (tid == 0) o[0] = sc_wx, o[1] = sc_cmp, o[2] = sc_wy, o[3] = sc_epi;
@@ -1098,9 +1105,12 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
             break;
           }
         if (best < 0) {
+          // the pass that runs alone (the last of an odd count) streams x through DRAM with shared-memory time to spare,
+          // the chained ones are bound by the shared-memory pipe: the lone pass may carry two gathers more than the others
+          auto eff = [&](int p) { return load[p] - ((np % 2 == 1 && np >= 3 && p == np - 1) ? 2 : 0); };
           best = cand[0];
           for (int p : cand)
-            if (load[p] < load[best] || (load[p] == load[best] && p > best)) best = p;
+            if (eff(p) < eff(best) || (eff(p) == eff(best) && p > best)) best = p;
           load[best]++;
         }
         c.pass = best;
@@ -1319,6 +1329,12 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
 
   // ---- group consecutive passes into chained launches: the union of their free bits must span <= chain_bits index bits
   const int chain_bits = qr_env_int("QOB_QREG_CHAIN_BITS", 20);
+  // With an odd number of passes one of them runs alone, bound by DRAM (it streams x and y once) with shared-memory time to
+  // spare, while a chained pair is bound by the shared-memory pipe with DRAM time to spare.  The lone pass goes FIRST: the
+  // first launch only writes y (32 B/amplitude instead of 48), so the DRAM-bound launch is the one that saves a third of its
+  // traffic; the pair after it accumulates into y through the L2.
+  if (chain_bits >= QR_T && h->passes.size() >= 3 && h->passes.size() % 2 == 1)
+    std::rotate(h->passes.begin(), h->passes.end() - 1, h->passes.end());
   for (size_t i = 0; i < h->passes.size();) {
     QRegProgramHost::Group g;
     g.first = (int)i;
@@ -1453,6 +1469,9 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
       sync = it->second;
     }
   }
+  // y = alpha*H x + beta*y: beta == 0 -> the first pass stores (y is never read); beta == 1 -> every pass adds; any other
+  // beta -> y is scaled first (one extra light pass), then every pass adds
+  if (beta != cplx(0.0, 0.0) && beta != cplx(1.0, 0.0)) QOB_TRY(launch_scale(y, (int64_t)1 << h.nbits, beta, s));
   bool first = true;
   int gi = 0;
   for (const auto &g : h.groups) {
@@ -1497,7 +1516,7 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
       }
       Lp.pass[q] = ph.params;
       QRPass &P = Lp.pass[q];
-      P.mode = first ? (beta == cplx(0.0, 0.0) ? 0 : 1) : 2;
+      P.mode = (first && beta == cplx(0.0, 0.0)) ? 0 : 2;   // 0: the tile is stored; 2: the tile is added to y by the L2
       first = false;
       P.signal = (g.count == 2 && q == 0) ? 1 : 0;
       P.wait = (g.count == 2 && q == 1) ? 1 : 0;
@@ -1509,12 +1528,12 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
       maps[2] = maps[0];
       maps[3] = maps[1];
     }
-    const size_t smem = 3 * (size_t)QR_TILE_BYTES + tab_off + 16 + 64 + 2 * sizeof(QRItem) + 2 * QR_MAXC * 16 + 128;
+    const size_t smem = QR_NSTAGE * (size_t)QR_TILE_BYTES + tab_off + 16 + 96 + QR_NSTAGE * sizeof(QRItem) + 2 * QR_MAXC * 16 + 128;
     QOB_CUDA(cudaMemsetAsync(sync, 0, (32 + (size_t)g.nchunks) * sizeof(unsigned), s));
     const unsigned grid = std::min<unsigned>((unsigned)sms, ntiles * (unsigned)g.count);
     auto launch = [&](auto kern) -> int {
       QOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<grid, QR_THREADS, smem, s>>>(Lp, maps[0], maps[1], maps[2], maps[3], (double2 *)y);
+      kern<<<grid, QR_THREADS, smem, s>>>(Lp, maps[0], maps[1], maps[2], maps[3]);
       QOB_LAUNCHED();
       QOB_CUDA(cudaGetLastError());
       return QOB_STATUS_OK;

@@ -99,6 +99,8 @@ def test_planner_pass_structure(Q, monkeypatch):
     assert "qreg[bits=28,T=12,passes=3,launches=2,components=56]" in d, d
     assert "{chained chunks=256 x 256 tiles, lag=1: [free:0-11 R:8,9,10,11" in d and "[free:0-2,11-19 R:16,17,18,19" in d, d
     assert "{single [free:0-2,19-27 R:24,25,26,27" in d, d
+    # the lone pass (DRAM bound) runs first and only writes y; the chained pair (shared-memory bound) accumulates behind it
+    assert d.index("{single") < d.index("{chained"), d
     assert sum(int(v) for v in re.findall(r"in-register:(\d+)", d)) == 9
     assert sum(int(v) for v in re.findall(r"gathers:(\d+)", d)) == 19
     # the per-GPU slab of config 5 (2^30 amplitudes): 4 tile passes in 2 chained launches = 2 trips through DRAM
