@@ -899,6 +899,29 @@ def ptrace_bra(dims, psi, indices):
     return ptrace_op(dims, dims, np.outer(np.conj(v), v), indices)
 
 
+def directsum_mul(result, operators, b, alpha=1.0, beta=0.0, bra=False):
+    """mul!(result::Ket, M::LazyDirectSum, b::Ket, alpha, beta) — src/spinors.jl:221-233 (bra=True: :234-247).  `result` and
+    `b` are flat arrays over the SumBasis; block i acts on slice i.  Like the reference, BOTH vectors are sliced by the lengths
+    of the right bases (`index = cumsum([0; length.(bases_r)...])`), so a non-square block raises DimensionMismatch (the
+    reference's `Ket(bases_l[i], result.data[...])` constructor throws)."""
+    lens_r = [int(np.prod(o.dims_r)) for o in operators]
+    index = np.concatenate([[0], np.cumsum(lens_r)])
+    for i, o in enumerate(operators):
+        sl = slice(int(index[i]), int(index[i + 1]))
+        if int(np.prod(o.dims_l)) != lens_r[i]:
+            raise DimensionMismatch("LazyDirectSum block is not square")
+        if not bra:
+            tmpket = Ket(o.dims_r, np.array(b[sl], dtype=C128))
+            tmpres = Ket(o.dims_l, np.array(result[sl], dtype=C128))
+            mul(tmpres, o, tmpket, alpha, beta)
+        else:
+            tmpket = Bra(o.dims_l, np.array(b[sl], dtype=C128))
+            tmpres = Bra(o.dims_r, np.array(result[sl], dtype=C128))
+            mul(tmpres, tmpket, o, alpha, beta)
+        result[sl] = tmpres.data
+    return result
+
+
 def lindblad_rhs(H, J, rho, rates=None):
     """The master-equation right-hand side as the mul! call pattern of test/test_sciml_broadcast_interfaces.jl:36-43 builds
     it, -i[H, rho] + sum_k g_k (J_k rho J_k^+ - (J_k^+ J_k rho + rho J_k^+ J_k)/2), with dense matrices (the fused device

@@ -321,6 +321,7 @@ def test_config1_tfim_n12(Q, dense):
 def test_qtile_chain_vs_oracle(Q, monkeypatch, n, T, L, kind):
     """The tile kernel (forced on for small chains) against the reference's per-term sparse recursion."""
     monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    monkeypatch.setenv("QOB_DISABLE_QREG", "1")   # this test pins the round-1 tile kernel (tests/test_gpu_qreg.py covers the round-2 one)
     monkeypatch.setenv("QOB_QTILE_T", str(T))
     monkeypatch.setenv("QOB_QTILE_L", str(L))
     rng = np.random.default_rng(50 + n)
@@ -334,6 +335,7 @@ def test_qtile_chain_vs_oracle(Q, monkeypatch, n, T, L, kind):
 
 def test_qtile_general_2x2_factors_and_three_site_terms(Q, monkeypatch):
     monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    monkeypatch.setenv("QOB_DISABLE_QREG", "1")   # this test pins the round-1 tile kernel (tests/test_gpu_qreg.py covers the round-2 one)
     rng = np.random.default_rng(60)
     n = 14
     dims = (2,) * n
@@ -462,6 +464,7 @@ def test_tile_planner_declines_and_generic_kernel_takes_over(Q, monkeypatch):
     """78 terms X_1 Z_j Z_k share one flip mask with 78 different selector sets: more shared-mask lookups than one tile pass
     carries -> the planner declines and the generic fused kernel computes the same map."""
     monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    monkeypatch.setenv("QOB_DISABLE_QREG", "1")   # this test pins the round-1 tile kernel (tests/test_gpu_qreg.py covers the round-2 one)
     rng = np.random.default_rng(96)
     n = 14
     dims = (2,) * n
@@ -485,6 +488,7 @@ def test_qtile_random_term_sets_vs_oracle(Q, monkeypatch, seed):
     n = int(rng.integers(12, 17))
     T = int(rng.integers(10, min(n, 13) + 1))
     monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    monkeypatch.setenv("QOB_DISABLE_QREG", "1")   # this test pins the round-1 tile kernel (tests/test_gpu_qreg.py covers the round-2 one)
     monkeypatch.setenv("QOB_QTILE_T", str(T))
     dims = (2,) * n
     terms, coefs = [], []
@@ -518,6 +522,7 @@ def test_qtile_random_term_sets_vs_oracle(Q, monkeypatch, seed):
 def test_qtile_density_matrix_commutator(Q, monkeypatch, n):
     """-i[H, rho] on a full 2^n x 2^n density matrix: left and right application run as tile passes over 2n index bits."""
     monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    monkeypatch.setenv("QOB_DISABLE_QREG", "1")   # this test pins the round-1 tile kernel (tests/test_gpu_qreg.py covers the round-2 one)
     rng = np.random.default_rng(77 + n)
     dims, coefs, terms = _chain_terms(n, "heis", False, rng)
     s = H.lazysum(dims, dims, coefs, terms)
@@ -557,6 +562,7 @@ def test_qtile_more_masks_than_records_per_pass(Q, monkeypatch, n):
     """All-to-all sigma_x sigma_x couplings: 91 distinct flip masks, more than the 56 lookup records a pass carries in its
     kernel parameters -> the planner chunks them into extra passes over the same tiles."""
     monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    monkeypatch.setenv("QOB_DISABLE_QREG", "1")   # this test pins the round-1 tile kernel (tests/test_gpu_qreg.py covers the round-2 one)
     rng = np.random.default_rng(98)
     dims = (2,) * n
     sx, sy, sz = _pauli()
@@ -577,6 +583,7 @@ def test_time_dependent_sum_coefficient_updates(Q, monkeypatch):
     """TimeDependentSum: set_time! rewrites the LazySum factors (time_dependent_operator.jl:279-290); the device plan keeps
     its passes and only refills its weight tables.  Checked on the tile-kernel path at several times."""
     monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    monkeypatch.setenv("QOB_DISABLE_QREG", "1")   # this test pins the round-1 tile kernel (tests/test_gpu_qreg.py covers the round-2 one)
     rng = np.random.default_rng(99)
     n = 13
     dims, coefs, terms = _chain_terms(n, "heis", False, rng)

@@ -370,3 +370,37 @@ def test_lindblad_host_assembly(Q):
         Q.LindbladRHS(Q.Operator(bas, bas, Hm), [Q.Operator(bas, bas, J1)], [-0.1], ctx=ctx)
     st = Q.lib.qob_lindblad_apply(L._handle, Q._lib.c64.of(1), ctypes.c_void_p(4096), Q._lib.c64.of(0), ctypes.c_void_p(1 << 40), None)
     assert st == 5 and b"no CPU fallback" in Q.lib.qob_last_error()
+
+
+def test_ptrace_argument_checks_and_directsum_planning(Q):
+    """check_ptrace_arguments (src/operators.jl:153-176) is enforced by the library before any device work, so it can be
+    exercised on a planning-only context; LazyDirectSum handles add up their blocks' dimensions."""
+    import ctypes as C
+
+    from qob200 import _lib
+
+    ctx = Q.context(-1)
+    dl, dr = (C.c_int64 * 3)(2, 3, 4), (C.c_int64 * 3)(5, 3, 2)
+
+    def call(tr):
+        t = (C.c_int32 * max(len(tr), 1))(*tr)
+        st = _lib.lib.qob_ptrace_op(ctx, 3, dl, dr, len(tr), t, None, None, None)
+        return st, _lib.lib.qob_last_error().decode()
+
+    assert call([1]) == (3, "Partial trace can only be applied onto subsystems that have the same left and right dimension.")
+    assert call([1, 2, 3])[0] == 3 and "use tr() instead" in call([1, 2, 3])[1]
+    assert call([4])[0] == 3 and call([2, 2])[0] == 3 and call([0])[0] == 3
+    assert call([2])[0] == 5          # valid arguments: only the missing GPU stops it (no CPU fallback)
+    st = _lib.lib.qob_ptrace_state(ctx, 3, dl, 3, (C.c_int32 * 3)(1, 2, 3), 0, None, None, None)
+    assert st == 3
+    # LazyDirectSum of a 3x3 sparse block and a 2-spin LazyTensor (4x4)
+    b3, bs = Q.GenericBasis(3), Q.SpinBasis(0.5)
+    import scipy.sparse as sp
+    A = Q.SparseOperator(b3, b3, sp.identity(3, dtype=complex, format="csc"))
+    B = Q.LazyTensor(Q.tensor(bs, bs), [1], (Q.sigmax(bs),))
+    S = Q.LazyDirectSum(A, B)
+    assert len(S.basis_l) == 7 and len(S.basis_r) == 7
+    d = Q.describe(S, ctx=ctx)
+    assert d.startswith("lazydirectsum[") and "sparse 3x3" in d, d
+    S2 = Q.LazyDirectSum(S, A)      # nested sums are flattened (src/spinors.jl:166-168)
+    assert len(S2.operators) == 3 and len(S2.basis_l) == 10
