@@ -341,6 +341,91 @@ def run_product_dist(args, rank, world, local_rank):
     run_common(args, Q, rank, world, step, x, y, n, nloc, plan, warmup, args.steps, peak, peak_src, H, alpha, sharded=sh, extra=extra)
 
 
+PAULI = None
+
+
+def spot_parity(ys, n, nloc, rank, alpha, seed=7, nsamples=64):
+    """Exact per-amplitude oracle at sampled indices of this rank's slab: every output amplitude of the
+    Heisenberg LazySum depends on <= 1 + n_terms inputs, and the input is the counter-based state both sides generate
+    bit-identically (qob_fill_state / orc_state_at).  Returns the max relative error over the samples."""
+    global PAULI
+    import numpy as np
+    import torch
+
+    from oracle import qob_oracle as O
+
+    if PAULI is None:
+        PAULI = [np.array([[0, 1], [1, 0]], dtype=complex), np.array([[0, -1j], [1j, 0]], dtype=complex),
+                 np.array([[1, 0], [0, -1]], dtype=complex)]
+    spec = chain_spec(n)
+    scale = 2.0 ** (-n / 2)
+    D = 1 << nloc
+    rng = np.random.default_rng(4242 + rank)
+    local = [0, 1, 7, 8, 4095, 4096, D - 1, D - 2, D // 2, D // 2 - 1, (1 << (nloc - 1)) + 5, 0x5555555 % D, 0xAAAAAAA % D]
+    local += [int(v) for v in rng.integers(0, D, max(0, nsamples - len(local)))]
+    got = ys[torch.tensor(local, device=ys.device)].cpu().numpy()
+    base = rank << nloc
+    worst, ref_max = 0.0, 0.0
+    refs = []
+    for li in local:
+        index = base + li
+        acc = 0.0 + 0.0j
+        for c, idx, a in spec:
+            A = PAULI[a]
+            k1, k2 = idx[0] - 1, idx[1] - 1
+            i1, i2 = (index >> k1) & 1, (index >> k2) & 1
+            for j1 in (0, 1):
+                for j2 in (0, 1):
+                    w = A[i1, j1] * A[i2, j2]
+                    if w != 0:
+                        jidx = (index & ~((1 << k1) | (1 << k2))) | (j1 << k1) | (j2 << k2)
+                        acc += c * w * O.state_at(seed, jidx, scale)
+        refs.append(alpha * acc)
+    refs = np.array(refs)
+    ref_max = float(np.abs(refs).max())
+    worst = float(np.abs(got - refs).max() / ref_max) if ref_max > 0 else float(np.abs(got).max())
+    return worst, len(local)
+
+
+def extra_configs(Q, peak):
+    """BASELINE configs 1-3 (and config 2 in its bandwidth regime) measured in the same run, each with its oracle check and the
+    roofline that bounds it: launch latency for the tiny states, HBM for the large sparse gemm!, FP64 tensor
+    (DMMA) for the dense d=48 factors."""
+    import bench_configs as BC
+    from oracle import qob_oracle as O
+
+    recs = []
+    try:
+        BC.config1(Q, O, recs.append)
+        BC.config2(Q, O, recs.append, cutoffs=(64, 4096))
+        BC.config3(Q, O, recs.append)
+    except Exception as e:  # noqa: BLE001
+        recs.append({"config": "error", "error": f"{type(e).__name__}: {e}"})
+    out = []
+    for r in recs:
+        c = r.get("config", "")
+        e = {"config": c, "rel_err_vs_oracle": r.get("rel_err_vs_oracle"), "speedup_vs_cpu_port": r.get("speedup_vs_cpu_port")}
+        if c.startswith("1:"):
+            e.update(us_per_mul=r["us_per_mul"], us_per_mul_cuda_graph_replay=r.get("us_per_mul_cuda_graph_replay"),
+                     amplitude_updates_per_s=r["amplitude_updates_per_s"],
+                     roofline={"bound": "launch latency", "note": "64 KiB state, one fused launch: a bandwidth fraction is meaningless"})
+        elif c.startswith("2:"):
+            e.update(us_per_commutator=r["us_per_commutator"], us_per_commutator_cuda_graph_replay=r.get("us_per_commutator_cuda_graph_replay"),
+                     roofline=({"bound": "hbm", "achieved": r["GBps"], "peak": peak, "unit": "GB/s", "frac": r["GBps"] / peak,
+                                "algorithmic_GB": r["algorithmic_GB"]} if r.get("bound") == "HBM" else
+                               {"bound": "launch latency", "note": "264 KiB operands: a bandwidth fraction is meaningless"}))
+        elif c.startswith("3:"):
+            e.update(ms_per_mul=r["ms_per_mul"], fp64_TFLOPs=r["fp64_TFLOPs"], plan=r.get("plan"),
+                     roofline={"bound": "tensor", "achieved": r["fp64_TFLOPs"], "peak": 37.2, "unit": "TFLOP/s",
+                               "frac": r["fp64_TFLOPs"] / 37.2,
+                               "peak_source": "register-only DMMA.8x8x4 loop measured on this pool's B200 (tools/fp64_peak.cu); "
+                                              "tcgen05 has no FP64 kind"})
+        else:
+            e.update(r)
+        out.append(e)
+    return out
+
+
 def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps, peak, peak_src, H, alpha, sharded=None, extra=None):
     import numpy as np
     import torch
@@ -434,30 +519,46 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
         dist.all_reduce(mn, op=dist.ReduceOp.MIN)
         e2e_s = float(t.item()) if float(mn.item()) > 0 else None
 
+    # ---- parity where the driver sees it: exact per-amplitude oracle at 64 sampled indices of EVERY rank's slab (the last
+    # step left y = alpha * H x in ys); the run fails above 1e-12
+    step()
+    torch.cuda.synchronize()
+    par_err, par_n = spot_parity(ys, n, nloc, rank if sharded is not None else 0, alpha)
+    if world > 1:
+        t = torch.tensor([par_err], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        par_err = float(t.item())
+        par_n *= world
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (the tile-pass kernel), from the live per-launch CUDA-event times
+    # ---- roofline: achieved = algorithmic bytes of ONE complete mul! (32 B per amplitude: x read once, y
+    # written once) / time of the mul!, against the measured HBM peak.  The per-launch figures (live CUDA events around every
+    # launch of the tile kernel) use each launch's DRAM-level algorithmic bytes: 32 B/amplitude for the launch that defines y,
+    # 48 B/amplitude for a launch that accumulates into it — however many tile passes are chained through L2 inside it.
     tot_ms = sum(p[0] for p in prof)
-    tot_bytes = sum(p[2] for p in prof)
-    achieved = (tot_bytes / 1e9) / (tot_ms * 1e-3) if tot_ms > 0 else 0.0
     by_pass = {}
     for ms, pi, by in prof:
         by_pass.setdefault(pi, []).append((ms, by))
-    passes = [{"pass": k, "ms": sum(m for m, _ in v) / len(v), "GBps": (v[0][1] / 1e9) / (sum(m for m, _ in v) / len(v) * 1e-3)}
-              for k, v in sorted(by_pass.items())]
+    per_launch = [{"launch": k, "ms": sum(m for m, _ in v) / len(v), "algorithmic_GB": v[0][1] / 1e9,
+                   "GBps": (v[0][1] / 1e9) / (sum(m for m, _ in v) / len(v) * 1e-3),
+                   "frac": (v[0][1] / 1e9) / (sum(m for m, _ in v) / len(v) * 1e-3) / peak}
+                  for k, v in sorted(by_pass.items())]
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tp):
+    tp = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    if world == 1 and n == 28 and os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("dram_bytes_per_mul")
         except Exception:
             traffic = None
+    achieved = 32.0 * (1 << nloc) / 1e9 / (ms_step * 1e-3)
+    kernel = "qreg_kernel" if "qreg[" in plan else "qtile_kernel"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "qtile_kernel (all tile passes of the fused LazySum)",
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": tot_bytes / max(len(prof), 1),
-                "kernel_share_of_step": tot_ms / ms_total if ms_total > 0 else None, "per_pass": passes,
-                "whole_mul_GBps_at_32B_per_amplitude": 32.0 * (1 << nloc) / 1e9 / (ms_step * 1e-3),
-                "whole_mul_frac_of_peak": 32.0 * (1 << nloc) / 1e9 / (ms_step * 1e-3) / peak}
+                "traffic": traffic,
+                "definition": "32 B per amplitude (x read once, y written once; beta = 0) x 2^n amplitudes per GPU / ms_per_step "
+                              "(SURVEY.md section 8d); traffic = ncu dram bytes of one whole mul! (all launches)",
+                "kernel": f"{kernel} (all launches of the fused LazySum apply; {len(per_launch)} per mul!)",
+                "peak_source": peak_src, "algorithmic_bytes_per_mul": 32.0 * (1 << nloc),
+                "kernel_share_of_step": tot_ms / ms_total if ms_total > 0 else None, "per_launch": per_launch}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -470,7 +571,7 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
                    f"chain that fits); remote terms " + ("exchanged by the fused peer-memory tile pass over NVLink"
                                                          if plan.startswith("exchange=fused") else "through NCCL all-to-all axis swaps")},
         "term_updates_per_s": value * nterms,
-        "hbm_GBps_algorithmic": 32.0 * (1 << nloc) / 1e9 / (ms_step * 1e-3),
+        "hbm_GBps_algorithmic": 32.0 * (1 << nloc) * world / 1e9 / (ms_step * 1e-3),
         "clocks": clocks,
         "e2e": {"value": (amps / e2e_s) if e2e_s else None, "unit": UNIT, "h2d_bytes_per_step": slab_bytes * world,
                 "d2h_bytes_per_step": slab_bytes * world, "ms_per_step": (1e3 * e2e_s) if e2e_s else None,
@@ -481,16 +582,26 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
                 **({"error": e2e_err} if e2e_err else {})},
         "gpu_launches": launches,
         "roofline": roofline,
+        "parity": {"max_rel_err": par_err, "n_samples": par_n, "tolerance": 1e-12,
+                   "oracle": "exact per-amplitude evaluation of the LazySum definition on the counter-based input "
+                             "(oracle/qob_oracle.c: orc_state_at), slab / tile boundaries + random indices on every rank"},
     }
     if extra:
         line.update(extra)
         if "single_gpu_same_slab" in extra:
             line["weak_scaling_efficiency_vs_same_slab"] = value / (world * extra["single_gpu_same_slab"]["value"])
+    if world == 1 and not args.no_extra_configs:
+        del xs, ys
+        torch.cuda.empty_cache()
+        line["extra_configs"] = extra_configs(Q, peak)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(n, nterms)
     else:
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "reported at N=1 only"}
     print(json.dumps(line), flush=True)
+    if not (par_err <= 1e-12):
+        print(f"[bench] PARITY FAILURE: max relative error {par_err:.3e} at {par_n} sampled amplitudes", file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -501,6 +612,7 @@ def main():
     ap.add_argument("--impl", default="qob200", choices=["qob200", "reference"])
     ap.add_argument("--spins", type=int, default=0, help="override the chain length (testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip BASELINE configs 1-3 (N=1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

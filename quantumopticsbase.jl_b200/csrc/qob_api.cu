@@ -544,7 +544,13 @@ int TensorGroup::apply(int side, cplx alpha, const void *x, cplx beta, void *y, 
   // The lock is held until every launch of this apply is enqueued: the kernels' variant flags (real weight tables) are
   // read consistently with the tables they were computed from, and the event bookkeeping below is atomic per apply.
   std::unique_lock<std::recursive_mutex> lk(mu);
-  const bool on_device = !t_planning_only && ctx && ctx->device >= 0;
+  bool on_device = !t_planning_only && ctx && ctx->device >= 0;
+  if (on_device) {
+    // while the stream is being captured into a CUDA graph the cross-stream bookkeeping is off: events recorded outside the
+    // capture cannot be waited on inside it, and a replayed graph owns its ordering (tables must be loaded before capture)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) on_device = false;
+  }
   if (coefs_dirty || coefs != last_coefs) {
     if (on_device) {
       // kernels still reading the old tables on other streams must finish before the tables are overwritten
@@ -679,6 +685,10 @@ struct LazySumOp : qob_op {
     int nloc = 0;
     int nterms = 0;
     QTileProgram prog;
+    // the round-2 kernel for plain launches of this plan (no peer addressing, no extra addend, no tile ranges, no SM budget):
+    // the communication-free group of a sharded apply is the bulk of its HBM traffic
+    bool has_qreg = false;
+    QRegProgram qreg;
   };
   std::vector<std::unique_ptr<LayoutPlan>> layouts;
   LazySumOp(qob_ctx *c) : qob_op(c, OP_LAZYSUM) {}
@@ -1528,6 +1538,11 @@ int qob_layout_plan_create(qob_op *sum, int32_t nbits_local, const int32_t *bitp
   lp->nloc = nbits_local;
   lp->nterms = (int)qt.size();
   QOB_TRY(qtile_build(lp->prog, nbits_local, hi_value, qt, S->ctx->sm_count));
+  if (!qt.empty() && nbits_local >= env_i("QOB_QREG_MIN_BITS", 20) && !env_i("QOB_DISABLE_QREG", 0)) {
+    const int st = qreg_build(lp->qreg, nbits_local, hi_value, qt, S->ctx->sm_count);
+    if (st == QOB_STATUS_OK) lp->has_qreg = true;
+    else if (st != QOB_STATUS_UNSUPPORTED) return st;
+  }
   S->layouts.push_back(std::move(lp));
   *plan_id = (int)S->layouts.size() - 1;
   return QOB_STATUS_OK;
@@ -1546,7 +1561,16 @@ int qob_layout_plan_apply(qob_op *sum, int32_t plan_id, qob_c64 alpha, const voi
   QOB_TRY(check_alias(x, n, y, n));
   QOB_DEVICE(S->ctx->device);
   if (C(alpha) == ZERO) return launch_scale(y, n, C(beta), s);
-  QOB_TRY(qtile_set_coefs(lp.prog, S->coefs, s));
+  std::vector<cplx> cf;
+  {
+    std::lock_guard<std::mutex> lk(S->coef_mu);
+    cf = S->coefs;
+  }
+  if (lp.has_qreg) {
+    QOB_TRY(qreg_set_coefs(lp.qreg, cf, s));
+    return qreg_launch(lp.qreg, C(alpha), x, C(beta), y, s);
+  }
+  QOB_TRY(qtile_set_coefs(lp.prog, cf, s));
   return qtile_launch(lp.prog, C(alpha), x, C(beta), y, s);
 }
 
@@ -1588,7 +1612,16 @@ int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const 
     if (zadd) return launch_axpby(zadd, y, n, ONE, C(beta), s);
     return launch_scale(y, n, C(beta), s);
   }
-  QOB_TRY(qtile_set_coefs(lp.prog, S->coefs, s));
+  std::vector<cplx> cf;
+  {
+    std::lock_guard<std::mutex> lk(S->coef_mu);
+    cf = S->coefs;
+  }
+  if (lp.has_qreg && npeers == 0 && !zadd && o.nchunks <= 1 && sm_budget <= 0) {
+    QOB_TRY(qreg_set_coefs(lp.qreg, cf, s));
+    return qreg_launch(lp.qreg, C(alpha), x, C(beta), y, s);
+  }
+  QOB_TRY(qtile_set_coefs(lp.prog, cf, s));
   return qtile_launch(lp.prog, C(alpha), x, C(beta), y, s, &o);
 }
 
@@ -1615,7 +1648,9 @@ int qob_layout_plan_describe(qob_op *sum, int32_t plan_id, char *buf, int64_t bu
   LazySumOp *S = nullptr;
   QOB_TRY(qubit_sum(sum, &S));
   if (plan_id < 0 || plan_id >= (int)S->layouts.size() || !buf) QOB_FAIL(QOB_STATUS_INVALID_ARG, "bad layout plan id");
-  snprintf(buf, (size_t)buflen, "%s", S->layouts[plan_id]->prog.describe.c_str());
+  const LazySumOp::LayoutPlan &lp = *S->layouts[plan_id];
+  if (lp.has_qreg) snprintf(buf, (size_t)buflen, "%s (plain launches) / %s (peer-addressed, chunked or budgeted launches)", lp.qreg.describe.c_str(), lp.prog.describe.c_str());
+  else snprintf(buf, (size_t)buflen, "%s", lp.prog.describe.c_str());
   return QOB_STATUS_OK;
 }
 

@@ -215,3 +215,68 @@ def test_qreg_vs_gather_kernel_full_vector(Q, monkeypatch, n):
     diff = yt.data - yg.data
     assert np.sqrt(Q.norm2(diff) / Q.norm2(yg.data)) <= TOL
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("world,n", [(2, 14), (4, 16), (8, 17)])
+@pytest.mark.parametrize("beta", [0.0, 0.5 + 0.25j])
+def test_qreg_in_sharded_layout_plans(monkeypatch, world, n, beta):
+    """The communication-free groups and the swapped-layout group of a sharded apply, with every rank's tile programs run on ONE
+    GPU: plain launches of a layout plan go through the round-2 kernel (rank-dependent diagonal weights enter through the index
+    bits above the local address)."""
+    monkeypatch.setenv("QOB_QREG_MIN_BITS", "12")
+    import test_gpu_dist as TD
+
+    import qob200 as Q
+    from qob200.dist import ShardedLazySum
+
+    sh = ShardedLazySum(TD.build_q(Q, n, TD.chain_spec(n, 21)), 1, world)
+    assert "qreg[" in sh.describe(), sh.describe()
+    TD.test_sharded_apply_all_ranks_on_one_gpu(world, n, beta)
+
+
+@pytest.mark.parametrize("n,force_old", [(22, False), (18, True)])
+def test_coefficient_updates_are_ordered_across_streams(Q, monkeypatch, n, force_old):
+    """One handle, two streams, coefficients changed between the launches (TimeDependentSum set_time! with per-task streams):
+    the weight tables are one device buffer per program, so the upload for the second launch must wait for the first launch's
+    kernels, and the second stream must see the upload — whatever stream it was issued on."""
+    import torch
+
+    if force_old:
+        monkeypatch.setenv("QOB_DISABLE_QREG", "1")
+        monkeypatch.setenv("QOB_QTILE_MIN_BITS", "10")
+    b = Q.SpinBasis(0.5)
+    B = Q.tensor(*[b] * n)
+    sig = (Q.sigmax(b), Q.sigmay(b), Q.sigmaz(b))
+    rng = np.random.default_rng(1234 + n)
+    terms = []
+    for i in range(1, n + 1):
+        j = i % n + 1
+        for s in sig:
+            terms.append(Q.LazyTensor(B, sorted([i, j]), (s, s)))
+    c1 = list(rng.uniform(0.5, 1.5, len(terms)))
+    c2 = list(rng.uniform(-1.5, -0.5, len(terms)))
+    Hs = Q.LazySum(list(c1), terms)
+    x = Q.randstate(B, seed=11)
+    ref1, ref2 = Q.Ket(B), Q.Ket(B)
+    Q.mul_(ref1, Hs, x, 1.0, 0.0)
+    Hs.factors[:] = c2
+    Q.mul_(ref2, Hs, x, 1.0, 0.0)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for trial in range(6):
+        y1, y2 = Q.Ket(B), Q.Ket(B)
+        torch.cuda.synchronize()
+        Hs.factors[:] = c1
+        with torch.cuda.stream(s1):
+            for _ in range(3):
+                Q.mul_(y1, Hs, x, 1.0, 0.0)
+        Hs.factors[:] = c2
+        with torch.cuda.stream(s2):
+            Q.mul_(y2, Hs, x, 1.0, 0.0)
+        with torch.cuda.stream(s1):      # equal coefficients again on the first stream: it must see stream 2's upload
+            y3 = Q.Ket(B)
+            Q.mul_(y3, Hs, x, 1.0, 0.0)
+        torch.cuda.synchronize()
+        assert np.sqrt(Q.norm2(y1.data - ref1.data) / Q.norm2(ref1.data)) <= TOL
+        assert np.sqrt(Q.norm2(y2.data - ref2.data) / Q.norm2(ref2.data)) <= TOL
+        assert np.sqrt(Q.norm2(y3.data - ref2.data) / Q.norm2(ref2.data)) <= TOL
