@@ -442,6 +442,9 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
     barrier()
     # ---- timed region: exactly `steps` steps
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+    if sharded is not None:
+        sharded.time_exchange = True
+        sharded._ex_events = []
     l0 = Q.launch_count()
     Q.profile_enable(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -452,6 +455,19 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+    nvlink = None
+    if sharded is not None:
+        sharded.time_exchange = False
+        ex_ms, per_dir = sharded.exchange_stats()
+        if ex_ms:
+            t = torch.tensor([ex_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ex_ms = float(t.item())
+            gbps = per_dir / 1e9 / (ex_ms * 1e-3)
+            nvlink = {"bytes_per_direction_per_gpu": per_dir, "exchange_ms": ex_ms, "GBps_per_direction": gbps,
+                      "frac_of_measured_770": gbps / 770.0, "frac_of_nominal_900": gbps / 900.0,
+                      "note": "fused exchange kernel(s) of one mul!, CUDA events on their stream, max over ranks; runs beside the "
+                              "local tile passes; 770 GB/s = measured peer-copy rate per direction (B200_PROFILING.md)"}
     Q.profile_enable(False)
     prof = Q.profile_read()
     launches = Q.launch_count() - l0
@@ -586,6 +602,8 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
                    "oracle": "exact per-amplitude evaluation of the LazySum definition on the counter-based input "
                              "(oracle/qob_oracle.c: orc_state_at), slab / tile boundaries + random indices on every rank"},
     }
+    if nvlink is not None:
+        line["nvlink"] = nvlink
     if extra:
         line.update(extra)
         if "single_gpu_same_slab" in extra:

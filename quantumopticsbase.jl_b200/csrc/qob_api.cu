@@ -1617,9 +1617,9 @@ int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const 
     std::lock_guard<std::mutex> lk(S->coef_mu);
     cf = S->coefs;
   }
-  if (lp.has_qreg && npeers == 0 && !zadd && o.nchunks <= 1 && sm_budget <= 0) {
+  if (lp.has_qreg && npeers == 0 && !zadd && o.nchunks <= 1) {
     QOB_TRY(qreg_set_coefs(lp.qreg, cf, s));
-    return qreg_launch(lp.qreg, C(alpha), x, C(beta), y, s);
+    return qreg_launch(lp.qreg, C(alpha), x, C(beta), y, s, sm_budget > 0 ? sm_budget : 0);
   }
   QOB_TRY(qtile_set_coefs(lp.prog, cf, s));
   return qtile_launch(lp.prog, C(alpha), x, C(beta), y, s, &o);

@@ -229,7 +229,8 @@ struct QRegProgram {
 // Returns QOB_STATUS_UNSUPPORTED when the terms do not fit the scheme (the caller then uses the qtile kernel).
 int qreg_build(QRegProgram &p, int nbits, uint64_t hi_value, const std::vector<QTerm> &terms, int sm_count);
 int qreg_set_coefs(QRegProgram &p, const std::vector<cplx> &coefs, cudaStream_t s);
-int qreg_launch(const QRegProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s);
+// max_ctas > 0: another kernel runs beside this one: use two tile buffers instead of three so that its CTAs fit on every SM
+int qreg_launch(const QRegProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, int max_ctas = 0);
 
 // per-launch event timing of the tile kernels (qob_profile_enable / qob_profile_read); thread safe
 bool qprof_enabled();

@@ -90,7 +90,8 @@ struct QRLaunch {
   unsigned tpc_log2;     // log2(tiles per chunk and pass)
   unsigned nchunks, lag; // chunks; pass 2 runs `lag` chunks behind pass 1
   unsigned total_items;
-  int prefetch;          // work items the producer runs ahead with L2 prefetches of their tiles
+  int prefetch;          // (unused)
+  int nstage;            // tile buffers in use: 3, or 2 when a kernel of another stream has to fit beside this one on every SM
   unsigned *queue;       // work counter
   unsigned *done;        // per chunk: finished pass-1 tiles
   long long *stats;      // debug (QOB_QREG_STATS=1): per-CTA cycle counts of the pipeline phases, 16 per CTA
@@ -382,7 +383,8 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((128u - (qr_smem(smem_raw) & 127u)) & 127u);  // TMA destinations: 128-byte aligned
   unsigned char *xs0 = smem;                              // QR_NSTAGE tile buffers: x comes in, the result tile leaves from the same one
-  unsigned char *tabs = smem + QR_NSTAGE * QR_TILE_BYTES; // weight tables of the pass(es)
+  const unsigned nst = (unsigned)L.nstage;
+  unsigned char *tabs = smem + nst * QR_TILE_BYTES;       // weight tables of the pass(es)
   const unsigned tab_total = L.pass[0].tab_bytes + (L.npass > 1 ? L.pass[1].tab_bytes : 0u);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(tabs + ((tab_total + 15u) & ~15u));
   // bars[s]: x of stage s has landed; [3+s]: stage s is free; [6+s]: the result tile of stage s is staged
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
           __threadfence();
           atomicAdd(L.done + it.chunk, 1u);
         }
-        stage = stage + 1 == QR_NSTAGE ? 0 : stage + 1;
+        stage = stage + 1 == nst ? 0 : stage + 1;
       }
       asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
     }
@@ -533,7 +535,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
         item = atomicAdd(L.queue, 1u);   // the next item: its latency overlaps the consumers' work
       }
       __syncwarp();
-      stage = stage + 1 == QR_NSTAGE ? 0 : stage + 1;
+      stage = stage + 1 == nst ? 0 : stage + 1;
     }
     return;
   }
@@ -696,7 +698,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
     __syncwarp();
     if ((tid & 31u) == 0) qr_mbar_arrive(qr_smem(bars + 6 + stage));
     sc_epi += clock64() - q0;
-    stage = stage + 1 == QR_NSTAGE ? 0 : stage + 1;
+    stage = stage + 1 == nst ? 0 : stage + 1;
   }
   // the loader's end marker sits in slots[stage]: pass it on to the storer
   __syncwarp();
@@ -1453,7 +1455,7 @@ int qreg_set_coefs(QRegProgram &prog, const std::vector<cplx> &coefs, cudaStream
 }
 
 
-int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s) {
+int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, int max_ctas) {
   QRegProgramHost &h = *prog.h;
   int dev = 0, sms = 148;
   QOB_CUDA(cudaGetDevice(&dev));
@@ -1528,8 +1530,12 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
       maps[2] = maps[0];
       maps[3] = maps[1];
     }
-    const size_t smem = QR_NSTAGE * (size_t)QR_TILE_BYTES + tab_off + 16 + 96 + QR_NSTAGE * sizeof(QRItem) + 2 * QR_MAXC * 16 + 128;
+    Lp.nstage = max_ctas > 0 ? 2 : QR_NSTAGE;
+    const size_t smem = (size_t)Lp.nstage * QR_TILE_BYTES + tab_off + 16 + 96 + QR_NSTAGE * sizeof(QRItem) + 2 * QR_MAXC * 16 + 128;
     QOB_CUDA(cudaMemsetAsync(sync, 0, (32 + (size_t)g.nchunks) * sizeof(unsigned), s));
+    // one persistent CTA per SM.  A caller that runs another kernel beside this one (the fused exchange of a sharded apply,
+    // max_ctas > 0) gets the two-buffer variant: 130 KB of shared memory per SM instead of 195 KB, so that one 64 KB CTA of
+    // the other kernel fits on every SM next to it
     const unsigned grid = std::min<unsigned>((unsigned)sms, ntiles * (unsigned)g.count);
     auto launch = [&](auto kern) -> int {
       QOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -141,7 +141,9 @@ class ShardedLazySum:
         # fused exchange (symmetric memory): peers' pointer tables, keyed by the local tensor's data_ptr
         self._symm = {}
         self._zbuf = None
-        self.swap_sms = int(os.environ.get("QOB_DIST_SWAP_SMS", "32")) if swap_sms is None else int(swap_sms)
+        self.swap_sms = int(os.environ.get("QOB_DIST_SWAP_SMS", "64")) if swap_sms is None else int(swap_sms)
+        self.time_exchange = False     # bench.py: bracket the exchange kernels with CUDA events on their stream
+        self._ex_events = []
         self.local_budget = int(os.environ.get("QOB_DIST_LOCAL_SMS", "0"))   # 0: full grid (one CTA per tile)
 
     # ------------------------------------------------------------------ fused exchange over NVLink peer memory
@@ -233,15 +235,24 @@ class ShardedLazySum:
             events = []
             with torch.cuda.stream(side):
                 zh.barrier(channel=0)                  # ... and on every rank; last call's contributions are consumed
+                if self.time_exchange:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e0.record(side)
                 for c in range(nc):
                     self._apply_ex(self.plan_swapped, alpha, None, 0.0, None, peers=(xptrs, zptrs), sm_budget=k, chunk=(c, nc))
                     zh.barrier(channel=1)              # chunk c of every rank's contributions has landed
                     ev = torch.cuda.Event()
                     ev.record(side)
                     events.append(ev)
+                if self.time_exchange:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record(side)
+                    self._ex_events.append((e0, e1))
             # beside the exchange: the local passes use a full grid; the exchange kernel is persistent with k*occupancy
             # CTAs on a high-priority stream, so it keeps its share of the slots while local CTAs come and go
-            self._apply_ex(self.plan_local, alpha, x, beta, y, sm_budget=self.local_budget)
+            # (slabs of >= 2^20 amplitudes run the persistent one-CTA-per-SM kernel: it is capped to the SMs the exchange leaves)
+            budget = self.local_budget if (self.local_budget or self.nloc < 20) else total - k
+            self._apply_ex(self.plan_local, alpha, x, beta, y, sm_budget=budget)
             for c in range(nc):                        # fold the contributions in, chunk by chunk, behind the exchange
                 main.wait_event(events[c])
                 self._apply_ex(self.plan_local_b, alpha, x, 1.0, y, zadd=self._zbuf, chunk=(c, nc))
@@ -255,6 +266,18 @@ class ShardedLazySum:
             else:
                 self._apply_ex(self.plan_local, alpha, x, beta, y, zadd=self._zbuf)
         return y
+
+    def exchange_stats(self):
+        """(mean ms of the timed exchanges, bytes that crossed NVLink per direction on this GPU per apply): the remote-term pass
+        loads the (1 - 1/P) share of its swapped-layout x tiles from the peers and stores the same share of its results into
+        the peers' contribution buffers; the peers do the same to this GPU."""
+        import torch
+
+        torch.cuda.synchronize()
+        ms = [a.elapsed_time(b) for a, b in self._ex_events]
+        self._ex_events = []
+        per_dir = 2.0 * (1.0 - 1.0 / self.world) * 16.0 * (1 << self.nloc)
+        return (sum(ms) / len(ms) if ms else None), per_dir
 
     def describe(self):
         buf = C.create_string_buffer(1 << 14)

@@ -232,6 +232,9 @@ def test_qreg_in_sharded_layout_plans(monkeypatch, world, n, beta):
     sh = ShardedLazySum(TD.build_q(Q, n, TD.chain_spec(n, 21)), 1, world)
     assert "qreg[" in sh.describe(), sh.describe()
     TD.test_sharded_apply_all_ranks_on_one_gpu(world, n, beta)
+    # the same with the fused peer exchange: the local group then runs the two-buffer variant that leaves room for the
+    # exchange kernel's CTAs on every SM (sm_budget > 0)
+    TD.test_fused_peer_exchange_all_ranks_on_one_gpu(world, n, beta)
 
 
 @pytest.mark.parametrize("n,force_old", [(22, False), (18, True)])
