@@ -209,9 +209,9 @@ int qob_layout_plan_describe(qob_op *sum, int32_t plan_id, char *buf, int64_t bu
  *            of an address select the owning rank; the tile kernel loads x straight from x_peers[owner] and stores its
  *            result straight into y_peers[owner] (device pointers into every rank's symmetric / IPC-mapped memory).
  *            x and y are ignored in that case.
- *   sm_budget>0 limits the persistent tile kernel to that many SMs so that another kernel runs beside it (the exchange pass is
- *            confined to its share; the local passes of a >= 2^20-amplitude slab run one persistent CTA per SM and are capped to
- *            the rest, so that the chunked exchange launches always find their SMs free).
+ *   sm_budget>0 limits the persistent tile kernel to that many SMs so that another kernel (the local passes) runs beside it;
+ *   sm_budget<0 says that this launch itself runs beside another kernel: the library then uses the tile kernel whose small CTAs
+ *            share SMs with it (the one-CTA-per-SM kernel used for plain launches would serialise with the other kernel).
  *   chunk_index/nchunks: run one of nchunks equal tile ranges (nchunks <= 1: the whole pass). */
 int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const void *x, qob_c64 beta, void *y,
                              const void *zadd, int32_t npeers, const void *const *x_peers, void *const *y_peers,

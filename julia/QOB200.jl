@@ -8,7 +8,11 @@
 #   * device-resident states: `Ket{B,<:CuVector{ComplexF64}}`, `Operator{BL,BR,<:CuMatrix{ComplexF64}}`
 #     (made by `Adapt.adapt(CuArray, x)`, reference src/states.jl:315-316, src/operators_dense.jl:47);
 #   * operator definitions (LazyTensor / LazySum / LazyProduct / SparseOperator / dense site operators) stay
-#     host objects; the first `mul!` compiles them into a libqob200 handle cached by `objectid(op)`;
+#     host objects; the first `mul!` compiles them into a libqob200 handle cached per (operator object, device) in a
+#     WeakKeyDict, so the handle (and its device tables) is released when the operator is collected;
+#     the definition is SNAPSHOTTED at that point: cheap scalars (`LazySum.factors`) are re-sent on every call, a change of
+#     `LazyTensor.factor` / `LazyProduct.factor` or of the operator lists is detected by a fingerprint and rebuilds the handle,
+#     in-place edits of a site operator's `.data` need `QOB200.invalidate!(op)`;
 #   * `mul!(result, op, state, alpha, beta)` methods with the SAME signatures as
 #     src/operators_lazytensor.jl:539-609, src/operators_lazysum.jl:189-238,
 #     src/operators_lazyproduct.jl:103-163, src/operators_sparse.jl:199-202 forward to `qob_op_apply`.
@@ -20,7 +24,8 @@ using CUDA
 using FillArrays: Eye
 using QuantumOpticsBase
 using QuantumOpticsBase: Ket, Bra, Operator, LazyTensor, LazySum, LazyProduct, DataOperator, AbstractOperator,
-                         Basis, CompositeBasis, IncompatibleBases
+                         Basis, CompositeBasis, IncompatibleBases, LazyDirectSum
+import QuantumOpticsBase: expect, variance, ptrace
 
 const libqob200 = get(ENV, "LIBQOB200", joinpath(@__DIR__, "..", "quantumopticsbase.jl_b200", "libqob200.so"))
 
@@ -83,23 +88,54 @@ factor(d::Eye, trans=OP_N) = (QobFactor(FACTOR_EYE, trans, size(d, 1), size(d, 2
 factor(d::Adjoint, trans=OP_N) = factor(parent(d), trans == OP_N ? OP_C : error("nested adjoint"))
 factor(d::Transpose, trans=OP_N) = factor(parent(d), trans == OP_N ? OP_T : error("nested transpose"))
 
-# ---------------------------------------------------------------- handles, cached per operator object
+# ---------------------------------------------------------------- handles, cached per (operator object, device)
 mutable struct Handle
     ptr::Ptr{Cvoid}
-    children::Vector{Any}
-    function Handle(p, children=Any[])
-        h = new(p, children)
+    children::Vector{Any}      # child handles: kept alive as long as the parent handle lives
+    fingerprint::UInt          # of the cheap, mutable parts of the definition (see `fingerprint`)
+    function Handle(p, children=Any[], fp=UInt(0))
+        h = new(p, children, fp)
         finalizer(x -> ccall((:qob_op_destroy, libqob200), Cint, (Ptr{Cvoid},), x.ptr), h)
         h
     end
 end
-const HANDLES = IdDict{Any,Handle}()
+# WeakKeyDict: an entry does not keep its operator alive, so operators built per time step are collected together with
+# their device tables (the reference's LazyTensor / LazySum / LazyProduct are mutable structs: valid weak keys).  One
+# dictionary per device: a handle belongs to the context (device) it was created on.
+const HANDLES = Dict{Int,WeakKeyDict{Any,Handle}}()
+const HANDLES_LOCK = ReentrantLock()
+handles() = lock(HANDLES_LOCK) do
+    get!(() -> WeakKeyDict{Any,Handle}(), HANDLES, Int(CUDA.deviceid(CUDA.device())))
+end
+"Forget the compiled handle of `op` (call after editing a site operator's `.data` in place)."
+invalidate!(op) = (lock(HANDLES_LOCK) do; for d in values(HANDLES); delete!(d, op); end; end; op)
+
+# what may change between two `mul!` calls without the object changing identity
+fingerprint(op::LazyTensor) = hash((op.factor, op.indices, map(objectid, op.operators)))
+fingerprint(op::LazyProduct) = hash((op.factor, map(objectid, op.operators)))
+fingerprint(op::LazySum) = hash(map(objectid, op.operators))          # the factors are re-sent on every call
+fingerprint(op::LazyDirectSum) = hash(map(objectid, op.operators))
+fingerprint(op) = UInt(0)
+
+function cached(build, op)
+    d = handles()
+    fp = fingerprint(op)
+    lock(HANDLES_LOCK) do
+        h = get(d, op, nothing)
+        if h === nothing || h.fingerprint != fp
+            h = build()
+            h.fingerprint = fp
+            d[op] = h
+        end
+        h
+    end
+end
 
 shape(b::CompositeBasis) = Int64[length(x) for x in b.bases]
 shape(b::Basis) = Int64[length(b)]
 
 function handle(op::LazyTensor)
-    get!(HANDLES, op) do
+    cached(op) do
         facs = QobFactor[]
         keep = Any[]
         for o in op.operators
@@ -119,8 +155,8 @@ function handle(op::LazyTensor)
     end
 end
 
-function handle(op::Operator)   # SparseOperator / dense operator definition
-    get!(HANDLES, op) do
+function handle(op::Operator)   # SparseOperator / dense operator definition (mutable struct in the reference: a valid weak key)
+    cached(op) do
         f, keep = factor(op.data)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         fn = f.kind == FACTOR_CSC ? :qob_sparse_create : :qob_dense_create
@@ -136,7 +172,7 @@ function handle(op::Operator)   # SparseOperator / dense operator definition
 end
 
 function handle(op::LazySum)
-    h = get!(HANDLES, op) do
+    h = cached(op) do
         hs = [handle(o) for o in op.operators]
         ptrs = Ptr{Cvoid}[x.ptr for x in hs]
         coefs = C64[C64(f) for f in op.factors]
@@ -153,12 +189,23 @@ function handle(op::LazySum)
 end
 
 function handle(op::LazyProduct)
-    get!(HANDLES, op) do
+    cached(op) do
         hs = [handle(o) for o in op.operators]
         ptrs = Ptr{Cvoid}[x.ptr for x in hs]
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:qob_lazyproduct_create, libqob200), Cint, (Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}, C64, Ref{Ptr{Cvoid}}),
                     context(), length(ptrs), ptrs, C64(op.factor), out))
+        Handle(out[], hs)
+    end
+end
+
+function handle(op::LazyDirectSum)
+    cached(op) do
+        hs = [handle(o) for o in op.operators]
+        ptrs = Ptr{Cvoid}[x.ptr for x in hs]
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:qob_lazydirectsum_create, libqob200), Cint, (Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}),
+                    context(), length(ptrs), ptrs, out))
         Handle(out[], hs)
     end
 end
@@ -211,6 +258,54 @@ mul!(result::Ket{B1,<:DevVec}, M::HostSparseOrDense{B1,B2}, b::Ket{B2,<:DevVec},
 mul!(result::Bra{B2,<:DevVec}, b::Bra{B1,<:DevVec}, M::HostSparseOrDense{B1,B2}, alpha, beta) where {B1,B2} =
     (apply!(result.data, M, SIDE_RIGHT, b.data, alpha, beta, 1); result)
 
+# LazyDirectSum (src/spinors.jl:221-247): Ket and Bra only, like the reference
+mul!(result::Ket{B1,<:DevVec}, M::LazyDirectSum{B1,B2}, b::Ket{B2,<:DevVec}, alpha, beta) where {B1,B2} =
+    (apply!(result.data, M, SIDE_LEFT, b.data, alpha, beta, 1); result)
+mul!(result::Bra{B2,<:DevVec}, b::Bra{B1,<:DevVec}, M::LazyDirectSum{B1,B2}, alpha, beta) where {B1,B2} =
+    (apply!(result.data, M, SIDE_RIGHT, b.data, alpha, beta, 1); result)
+
+# expect / variance of a lazy or sparse operator in a device Ket (src/operators.jl:119,139-142): one ccall each, only the scalar
+# crosses to the host
+const LazyOrSparse{B} = Union{LazyTensor{B,B},LazySum{B,B},LazyProduct{B,B},HostSparseOrDense{B,B}}
+function expect(op::LazyOrSparse{B}, state::Ket{B,<:DevVec}) where B
+    h = handle(op); out = Ref(C64(0))
+    GC.@preserve h check(ccall((:qob_expect, libqob200), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, Ref{C64}, Ptr{Cvoid}),
+                               h.ptr, pointer(state.data), out, CUDA.stream().handle))
+    ComplexF64(out[].re, out[].im)
+end
+function variance(op::LazyOrSparse{B}, state::Ket{B,<:DevVec}) where B
+    h = handle(op); out = Ref(C64(0))
+    GC.@preserve h check(ccall((:qob_variance, libqob200), Cint, (Ptr{Cvoid}, CuPtr{Cvoid}, Ref{C64}, Ptr{Cvoid}),
+                               h.ptr, pointer(state.data), out, CUDA.stream().handle))
+    ComplexF64(out[].re, out[].im)
+end
+
+# ptrace of device-resident states (src/operators_dense.jl:191-215): the result is a device-resident dense Operator
+function ptrace(a::DevOp, indices)
+    QuantumOpticsBase.check_ptrace_arguments(a, indices)
+    dl, dr = shape(a.basis_l), shape(a.basis_r)
+    tr = Int32[i for i in indices]
+    bl, br = ptrace(a.basis_l, indices), ptrace(a.basis_r, indices)
+    res = CUDA.zeros(ComplexF64, length(bl), length(br))
+    check(ccall((:qob_ptrace_op, libqob200), Cint,
+                (Ptr{Cvoid}, Int32, Ptr{Int64}, Ptr{Int64}, Int32, Ptr{Int32}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}),
+                context(), length(dl), dl, dr, length(tr), tr, pointer(a.data), pointer(res), CUDA.stream().handle))
+    Operator(bl, br, res)
+end
+function _ptrace_state(psi, indices, bra::Bool)
+    QuantumOpticsBase.check_ptrace_arguments(psi, indices)
+    d = shape(psi.basis)
+    tr = Int32[i for i in indices]
+    b = ptrace(psi.basis, indices)
+    res = CUDA.zeros(ComplexF64, length(b), length(b))
+    check(ccall((:qob_ptrace_state, libqob200), Cint,
+                (Ptr{Cvoid}, Int32, Ptr{Int64}, Int32, Ptr{Int32}, Int32, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}),
+                context(), length(d), d, length(tr), tr, Int32(bra), pointer(psi.data), pointer(res), CUDA.stream().handle))
+    Operator(b, b, res)
+end
+ptrace(psi::Ket{B,<:DevVec}, indices) where B = _ptrace_state(psi, indices, false)
+ptrace(psi::Bra{B,<:DevVec}, indices) where B = _ptrace_state(psi, indices, true)
+
 # ---- fused master-equation right-hand side (include/qob200.h: qob_lindblad_*; no single reference function — it replaces the
 # mul! sequence of test/test_sciml_broadcast_interfaces.jl:36-43 / QuantumOptics.jl's dmaster_h!)
 struct LindbladRHS
@@ -236,8 +331,8 @@ function LindbladRHS(H::HostSparseOrDense{B,B}, J::Vector; rates=nothing) where 
 end
 "drho = alpha * L(rho) + beta * drho on device-resident dense operators"
 function apply!(drho::DevOp{B,B}, L::LindbladRHS, rho::DevOp{B,B}, alpha=true, beta=false) where B
-    check(ccall((:qob_lindblad_apply, libqob200), Cint, (Ptr{Cvoid}, C64, CuPtr{Cvoid}, C64, CuPtr{Cvoid}, Ptr{Cvoid}),
-                L.handle.ptr, C64(alpha), pointer(rho.data), C64(beta), pointer(drho.data), CUDA.stream().handle))
+    GC.@preserve L check(ccall((:qob_lindblad_apply, libqob200), Cint, (Ptr{Cvoid}, C64, CuPtr{Cvoid}, C64, CuPtr{Cvoid}, Ptr{Cvoid}),
+                               L.handle.ptr, C64(alpha), pointer(rho.data), C64(beta), pointer(drho.data), CUDA.stream().handle))
     drho
 end
 

@@ -327,8 +327,10 @@ struct TensorGroup {
   }
 
   int compile(int side, int64_t batch, Compiled **out);
+  // expect_out != nullptr: compute <x| group |x> instead (fused reduction, nothing written); QOB_STATUS_UNSUPPORTED when the
+  // compiled program is not a single round-2 tile program (the caller then applies into scratch and reduces)
   int apply(int side, cplx alpha, const void *x, cplx beta, void *y, int64_t batch, const std::vector<cplx> &coefs,
-            cudaStream_t s);
+            cudaStream_t s, cplx *expect_out = nullptr);
 };
 
 static const int GATHER_MAXF = 4;
@@ -537,10 +539,11 @@ int TensorGroup::compile(int side, int64_t batch, Compiled **out) {
 }
 
 int TensorGroup::apply(int side, cplx alpha, const void *x, cplx beta, void *y, int64_t batch,
-                       const std::vector<cplx> &coefs, cudaStream_t s) {
+                       const std::vector<cplx> &coefs, cudaStream_t s, cplx *expect_out) {
   Compiled *cp = nullptr;
   QOB_TRY(compile(side, batch, &cp));
   Compiled &c = *cp;
+  if (expect_out && !(c.has_qreg && !c.has_qtile && !c.has_dtile && !c.has_gather && c.seq.empty())) return QOB_STATUS_UNSUPPORTED;
   // The lock is held until every launch of this apply is enqueued: the kernels' variant flags (real weight tables) are
   // read consistently with the tables they were computed from, and the event bookkeeping below is atomic per apply.
   std::unique_lock<std::recursive_mutex> lk(mu);
@@ -592,6 +595,7 @@ int TensorGroup::apply(int side, cplx alpha, const void *x, cplx beta, void *y, 
     first = false;
     return b;
   };
+  if (expect_out) return qreg_expect(c.qreg, x, expect_out, s);
   if (c.has_qreg) QOB_TRY(qreg_launch(c.qreg, alpha, x, beta_now(), y, s));
   if (c.has_qtile) QOB_TRY(qtile_launch(c.qtile, alpha, x, beta_now(), y, s));
   if (c.has_dtile) QOB_TRY(dtile_launch(c.dtile, alpha, x, beta_now(), y, s));
@@ -1418,10 +1422,29 @@ int qob_expect(qob_op *op, const void *x, qob_c64 *out, void *stream) {
   if (op->ctx->device < 0) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
   QOB_DEVICE(op->ctx->device);
   cudaStream_t s = (cudaStream_t)stream;
+  cplx r;
+  // a LazySum of LazyTensors on a large spin-1/2 state: every tile pass reduces conj(x) * (its share of op x) on the fly —
+  // one sweep over x per launch, no result vector written, no second pass for the dot product
+  if (op->kind == OP_LAZYSUM) {
+    LazySumOp *S = static_cast<LazySumOp *>(op);
+    if (S->group && S->others.empty() && !S->terms.empty()) {
+      std::vector<cplx> cf;
+      {
+        std::lock_guard<std::mutex> lk(S->coef_mu);
+        cf = S->coefs;
+      }
+      const int st = S->group->apply(QOB_SIDE_LEFT, ONE, x, ZERO, nullptr, 1, cf, s, &r);
+      if (st == QOB_STATUS_OK) {
+        out->re = r.real();
+        out->im = r.imag();
+        return QOB_STATUS_OK;
+      }
+      if (st != QOB_STATUS_UNSUPPORTED) return st;
+    }
+  }
   void *tmp = nullptr;
   QOB_TRY(op->ctx->get_scratch(s, op->slot_base + 4, (size_t)std::max<int64_t>(1, op->dl) * 16, &tmp));
   QOB_TRY(op->apply(QOB_SIDE_LEFT, ONE, x, ZERO, tmp, 1, s));
-  cplx r;
   QOB_TRY(launch_dot(x, tmp, op->dl, &r, s));
   out->re = r.real();
   out->im = r.imag();
@@ -1617,10 +1640,14 @@ int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const 
     std::lock_guard<std::mutex> lk(S->coef_mu);
     cf = S->coefs;
   }
-  if (lp.has_qreg && npeers == 0 && !zadd && o.nchunks <= 1) {
+  // sm_budget < 0: the launch runs BESIDE another kernel (the fused exchange).  The round-2 kernel keeps 168 registers x 320
+  // threads and >= 130 KB of shared memory per SM for the whole launch, so no CTA of the other kernel fits next to it and the
+  // two would serialise (measured: 8 GPUs, N=33: 80 ms instead of 53 ms); the round-1 kernel (3 small CTAs per SM) shares SMs.
+  if (lp.has_qreg && npeers == 0 && !zadd && o.nchunks <= 1 && sm_budget == 0) {
     QOB_TRY(qreg_set_coefs(lp.qreg, cf, s));
-    return qreg_launch(lp.qreg, C(alpha), x, C(beta), y, s, sm_budget > 0 ? sm_budget : 0);
+    return qreg_launch(lp.qreg, C(alpha), x, C(beta), y, s);
   }
+  if (o.sm_budget < 0) o.sm_budget = 0;
   QOB_TRY(qtile_set_coefs(lp.prog, cf, s));
   return qtile_launch(lp.prog, C(alpha), x, C(beta), y, s, &o);
 }

@@ -232,6 +232,9 @@ int qreg_set_coefs(QRegProgram &p, const std::vector<cplx> &coefs, cudaStream_t 
 // max_ctas > 0: another kernel runs beside this one: use two tile buffers instead of three so that its CTAs fit on every SM
 int qreg_launch(const QRegProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, int max_ctas = 0);
 
+// <x| op |x> in one sweep over x (no result vector is written): every pass reduces conj(x)*acc; deterministic
+int qreg_expect(const QRegProgram &p, const void *x, cplx *out, cudaStream_t s);
+
 // per-launch event timing of the tile kernels (qob_profile_enable / qob_profile_read); thread safe
 bool qprof_enabled();
 void *qprof_begin(cudaStream_t s, int pass, double alg_bytes);

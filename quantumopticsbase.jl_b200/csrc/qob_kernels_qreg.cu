@@ -75,7 +75,7 @@ struct QRPass {
   uint32_t tab_smem_off;          // byte offset of this pass's tables inside the shared-memory table area
   uint32_t tab_bytes;
   const unsigned char *tab;       // device copy of the tables
-  int mode;                       // 0: y = a*acc ; 1: y = a*acc + beta*y ; 2: y = a*acc + y
+  int mode;                       // 0: y = a*acc (TMA store); 2: y += a*acc (TMA reduce-add); 3: no output, sum conj(x)*acc (expect)
   int signal;                     // 1: count finished tiles per chunk (first pass of a chained pair)
   int wait;                       // 1: tiles wait for their chunk's counter (second pass of a chained pair)
   int stream_out;                 // 1: last use of x and y in this launch: L2 evict_first on loads and stores
@@ -94,6 +94,8 @@ struct QRLaunch {
   int nstage;            // tile buffers in use: 3, or 2 when a kernel of another stream has to fit beside this one on every SM
   unsigned *queue;       // work counter
   unsigned *done;        // per chunk: finished pass-1 tiles
+  int static_queue;      // 1: tiles are dealt round-robin (item = blockIdx.x + k*gridDim.x): reproducible partial sums
+  double2 *partials;     // mode 3: one partial sum per consumer warp, [blockIdx.x * 8 + warp]
   long long *stats;      // debug (QOB_QREG_STATS=1): per-CTA cycle counts of the pipeline phases, 16 per CTA
   double2 alpha, beta;
   QRPass pass[2];
@@ -427,9 +429,11 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
         const QRItem it = slots[stage];
         if (it.pass < 0) break;
         const QRPass &P = L.pass[it.pass];
-        qr_tma_store(it.pass ? &my1 : &my0, qr_smem(xs0 + stage * QR_TILE_BYTES), P.rank, it.co, P.mode != 0);
-        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        if (P.mode != 3) {
+          qr_tma_store(it.pass ? &my1 : &my0, qr_smem(xs0 + stage * QR_TILE_BYTES), P.rank, it.co, P.mode != 0);
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+        }
         qr_mbar_arrive(qr_smem(bars + 3 + stage));   // the buffer may be loaded again
         if (P.signal) {
           asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
     long long st_ex = 0, st_dep = 0, st_ey = 0, st_n = 0;
     const long long st_t0 = clock64();
     unsigned item = 0;
-    if (lane == 0) item = atomicAdd(L.queue, 1u);
+    if (lane == 0) item = L.static_queue ? blockIdx.x : atomicAdd(L.queue, 1u);
     while (true) {
       item = __shfl_sync(0xffffffffu, item, 0);
       int p = 0;
@@ -532,7 +536,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
         const unsigned long long pol = P.stream_out ? pol_stream : pol_keep;
         qr_mbar_expect(qr_smem(bars + stage), QR_TILE_BYTES);
         qr_tma_load(qr_smem(xs0 + stage * QR_TILE_BYTES), p ? &mx1 : &mx0, qr_smem(bars + stage), P.rank, co, pol);
-        item = atomicAdd(L.queue, 1u);   // the next item: its latency overlaps the consumers' work
+        item = L.static_queue ? item + gridDim.x : atomicAdd(L.queue, 1u);   // the next item: the atomic's latency overlaps the consumers' work
       }
       __syncwarp();
       stage = stage + 1 == nst ? 0 : stage + 1;
@@ -543,6 +547,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
   // -------------------------------------------------------------------- consumers
   const unsigned so = tid * 16u;
   unsigned stage = 0, xphase = 0;
+  double2 esum = make_double2(0.0, 0.0);   // mode 3: this thread's share of <x| op x>
   long long sc_wx = 0, sc_cmp = 0, sc_wy = 0, sc_epi = 0;
 #pragma unroll 1
   while (true) {
@@ -684,6 +689,19 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
         }
       }
     }
+    if (P.mode == 3) {
+      // expect(op, psi): nothing is written — every pass contributes sum_i conj(x_i) * acc_i, and the passes add up
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const double2 xo = *reinterpret_cast<const double2 *>(xs + so + u * QR_USTRIDE);
+        esum.x = fma(xo.x, acc[u].x, fma(xo.y, acc[u].y, esum.x));
+        esum.y = fma(xo.x, acc[u].y, fma(-xo.y, acc[u].x, esum.y));
+      }
+      __syncwarp();
+      if ((tid & 31u) == 0) qr_mbar_arrive(qr_smem(bars + 6 + stage));
+      stage = stage + 1 == nst ? 0 : stage + 1;
+      continue;
+    }
     // all reads of this tile are done by every consumer warp: its buffer now takes the result tile, alpha * acc, which the
     // storer thread sends off through TMA; the buffer returns to the loader when the copy engine has read it
     asm volatile("bar.sync 1, %0;\n" ::"n"(QR_CTHREADS) : "memory");
@@ -699,6 +717,14 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
     if ((tid & 31u) == 0) qr_mbar_arrive(qr_smem(bars + 6 + stage));
     sc_epi += clock64() - q0;
     stage = stage + 1 == nst ? 0 : stage + 1;
+  }
+  if (L.partials) {  // fixed-order reduction: lanes of a warp, then one slot per warp; the host adds the slots in order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      esum.x += __shfl_xor_sync(0xffffffffu, esum.x, o);
+      esum.y += __shfl_xor_sync(0xffffffffu, esum.y, o);
+    }
+    if ((tid & 31u) == 0) L.partials[blockIdx.x * (QR_CTHREADS / 32) + (tid >> 5)] = esum;
   }
   // the loader's end marker sits in slots[stage]: pass it on to the storer
   __syncwarp();
@@ -761,9 +787,12 @@ struct QRegProgramHost {
   bool real_tables = false;
   std::mutex mu;
   std::map<cudaStream_t, unsigned *> sync_bufs;      // per stream: work counter + per-chunk counters
+  std::map<cudaStream_t, double2 *> part_bufs;       // per stream: partial sums of the fused expect
   size_t sync_words = 0;
   ~QRegProgramHost() {
     for (auto &kv : sync_bufs)
+      if (kv.second) cudaFree(kv.second);
+    for (auto &kv : part_bufs)
       if (kv.second) cudaFree(kv.second);
   }
 };
@@ -1455,7 +1484,18 @@ int qreg_set_coefs(QRegProgram &prog, const std::vector<cplx> &coefs, cudaStream
 }
 
 
+static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, int max_ctas,
+                            cplx *expect_out);
 int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, int max_ctas) {
+  return qreg_launch_impl(prog, alpha, x, beta, y, s, max_ctas, nullptr);
+}
+// <x| op |x> without writing op*x: every launch runs in mode 3 and leaves per-warp partial sums; tiles are dealt statically
+// and the partials are added in a fixed order, so the result is reproducible bit for bit
+int qreg_expect(const QRegProgram &prog, const void *x, cplx *out, cudaStream_t s) {
+  return qreg_launch_impl(prog, cplx(1.0, 0.0), x, cplx(0.0, 0.0), nullptr, s, 0, out);
+}
+static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, int max_ctas,
+                            cplx *expect_out) {
   QRegProgramHost &h = *prog.h;
   int dev = 0, sms = 148;
   QOB_CUDA(cudaGetDevice(&dev));
@@ -1473,7 +1513,21 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
   }
   // y = alpha*H x + beta*y: beta == 0 -> the first pass stores (y is never read); beta == 1 -> every pass adds; any other
   // beta -> y is scaled first (one extra light pass), then every pass adds
-  if (beta != cplx(0.0, 0.0) && beta != cplx(1.0, 0.0)) QOB_TRY(launch_scale(y, (int64_t)1 << h.nbits, beta, s));
+  if (!expect_out && beta != cplx(0.0, 0.0) && beta != cplx(1.0, 0.0)) QOB_TRY(launch_scale(y, (int64_t)1 << h.nbits, beta, s));
+  double2 *partials = nullptr;
+  const size_t part_per_launch = (size_t)sms * (QR_CTHREADS / 32);
+  if (expect_out) {
+    std::lock_guard<std::mutex> lk(h.mu);
+    auto it = h.part_bufs.find(s);
+    if (it == h.part_bufs.end()) {
+      QOB_CUDA(cudaMalloc(&partials, 8 * part_per_launch * sizeof(double2)));
+      h.part_bufs[s] = partials;
+    } else {
+      partials = it->second;
+    }
+    if (h.groups.size() > 8) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: too many launches for the fused expect");
+    QOB_CUDA(cudaMemsetAsync(partials, 0, 8 * part_per_launch * sizeof(double2), s));
+  }
   bool first = true;
   int gi = 0;
   for (const auto &g : h.groups) {
@@ -1509,7 +1563,7 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
           QOB_TRY(qr_encode_map(ph, x, &ph.map_x));
           ph.map_x_ptr = x;
         }
-        if (ph.map_y_ptr != y) {
+        if (!expect_out && ph.map_y_ptr != y) {
           QOB_TRY(qr_encode_map(ph, y, &ph.map_y));
           ph.map_y_ptr = y;
         }
@@ -1518,10 +1572,10 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
       }
       Lp.pass[q] = ph.params;
       QRPass &P = Lp.pass[q];
-      P.mode = (first && beta == cplx(0.0, 0.0)) ? 0 : 2;   // 0: the tile is stored; 2: the tile is added to y by the L2
+      P.mode = expect_out ? 3 : ((first && beta == cplx(0.0, 0.0)) ? 0 : 2);   // 0: stored; 2: added to y by the L2; 3: reduced
       first = false;
-      P.signal = (g.count == 2 && q == 0) ? 1 : 0;
-      P.wait = (g.count == 2 && q == 1) ? 1 : 0;
+      P.signal = (g.count == 2 && q == 0 && !expect_out) ? 1 : 0;   // mode 3 writes nothing: the chunk order alone keeps x in L2
+      P.wait = (g.count == 2 && q == 1 && !expect_out) ? 1 : 0;
       P.stream_out = (q == g.count - 1) ? 1 : 0;
       P.tab_smem_off = tab_off;
       tab_off += (P.tab_bytes + 15u) & ~15u;
@@ -1531,6 +1585,8 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
       maps[3] = maps[1];
     }
     Lp.nstage = max_ctas > 0 ? 2 : QR_NSTAGE;
+    Lp.static_queue = expect_out ? 1 : 0;
+    Lp.partials = expect_out ? partials + (size_t)(gi - 1) * part_per_launch : nullptr;
     const size_t smem = (size_t)Lp.nstage * QR_TILE_BYTES + tab_off + 16 + 96 + QR_NSTAGE * sizeof(QRItem) + 2 * QR_MAXC * 16 + 128;
     QOB_CUDA(cudaMemsetAsync(sync, 0, (32 + (size_t)g.nchunks) * sizeof(unsigned), s));
     // one persistent CTA per SM.  A caller that runs another kernel beside this one (the fused exchange of a sharded apply,
@@ -1547,7 +1603,7 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
     if (h.real_tables) QOB_TRY(launch(qreg_kernel<true>));
     else QOB_TRY(launch(qreg_kernel<false>));
     qprof_end(s, prof_token);
-    if (want_stats) {
+    if (want_stats && !expect_out) {
       std::vector<long long> hs(16 * 256);
       cudaStreamSynchronize(s);
       cudaMemcpy(hs.data(), stats_buf, hs.size() * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -1557,6 +1613,17 @@ int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, v
                 gi - 1, b, o[4], o[3], o[0], o[1], o[2], o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]);
       }
     }
+  }
+  if (expect_out) {
+    std::vector<double2> hp(h.groups.size() * part_per_launch);
+    QOB_CUDA(cudaMemcpyAsync(hp.data(), partials, hp.size() * sizeof(double2), cudaMemcpyDeviceToHost, s));
+    QOB_CUDA(cudaStreamSynchronize(s));
+    double re = 0.0, im = 0.0;
+    for (const double2 &v : hp) {
+      re += v.x;
+      im += v.y;
+    }
+    *expect_out = cplx(re, im);
   }
   return QOB_STATUS_OK;
 }

@@ -141,7 +141,7 @@ class ShardedLazySum:
         # fused exchange (symmetric memory): peers' pointer tables, keyed by the local tensor's data_ptr
         self._symm = {}
         self._zbuf = None
-        self.swap_sms = int(os.environ.get("QOB_DIST_SWAP_SMS", "64")) if swap_sms is None else int(swap_sms)
+        self.swap_sms = int(os.environ.get("QOB_DIST_SWAP_SMS", "32")) if swap_sms is None else int(swap_sms)
         self.time_exchange = False     # bench.py: bracket the exchange kernels with CUDA events on their stream
         self._ex_events = []
         self.local_budget = int(os.environ.get("QOB_DIST_LOCAL_SMS", "0"))   # 0: full grid (one CTA per tile)
@@ -250,9 +250,9 @@ class ShardedLazySum:
                     self._ex_events.append((e0, e1))
             # beside the exchange: the local passes use a full grid; the exchange kernel is persistent with k*occupancy
             # CTAs on a high-priority stream, so it keeps its share of the slots while local CTAs come and go
-            # (slabs of >= 2^20 amplitudes run the persistent one-CTA-per-SM kernel: it is capped to the SMs the exchange leaves)
-            budget = self.local_budget if (self.local_budget or self.nloc < 20) else total - k
-            self._apply_ex(self.plan_local, alpha, x, beta, y, sm_budget=budget)
+            # sm_budget = -1: "runs beside another kernel" -> the library picks the tile kernel whose CTAs share SMs with the
+            # exchange kernel's (the persistent one-CTA-per-SM kernel would serialise with it)
+            self._apply_ex(self.plan_local, alpha, x, beta, y, sm_budget=self.local_budget if self.local_budget else -1)
             for c in range(nc):                        # fold the contributions in, chunk by chunk, behind the exchange
                 main.wait_event(events[c])
                 self._apply_ex(self.plan_local_b, alpha, x, 1.0, y, zadd=self._zbuf, chunk=(c, nc))

@@ -283,3 +283,31 @@ def test_coefficient_updates_are_ordered_across_streams(Q, monkeypatch, n, force
         assert np.sqrt(Q.norm2(y1.data - ref1.data) / Q.norm2(ref1.data)) <= TOL
         assert np.sqrt(Q.norm2(y2.data - ref2.data) / Q.norm2(ref2.data)) <= TOL
         assert np.sqrt(Q.norm2(y3.data - ref2.data) / Q.norm2(ref2.data)) <= TOL
+
+
+@pytest.mark.parametrize("n,kind", [(13, "tfim"), (18, "heis"), (16, "heis")])
+def test_qreg_fused_expect(Q, monkeypatch, n, kind):
+    """expect(op, psi) on the round-2 kernel: every tile pass reduces conj(x) * (its share of op x) — no result vector is written,
+    no separate dot product; the launch count is the plan's launch count and the value is reproducible bit for bit."""
+    import re
+
+    monkeypatch.setenv("QOB_QREG_MIN_BITS", "12")
+    rng = np.random.default_rng(1500 + n)
+    dims, coefs, terms = _chain(n, kind, rng, complex_coefs=(n == 16))
+    s = H.lazysum(dims, dims, coefs, terms)
+    d = Q.describe(s.q)
+    assert "qreg[" in d
+    nlaunch = int(re.search(r"launches=(\d+)", d).group(1))
+    x = H.rnd(rng, 1 << n)
+    x /= np.linalg.norm(x)
+    hx = H.ket(dims, np.zeros(1 << n, dtype=complex))
+    O.mul(hx.o, s.o, H.ket(dims, x).o, 1.0, 0.0)
+    ref = np.vdot(x, hx.o.data)
+    st = H.ket(dims, x).q
+    Q.expect(s.q, st)                      # builds the handle, loads the tables
+    l0 = Q.launch_count()
+    e1 = Q.expect(s.q, st)
+    assert Q.launch_count() - l0 == nlaunch, (Q.launch_count() - l0, nlaunch)
+    e2 = Q.expect(s.q, st)
+    assert e1 == e2                        # static tile assignment + fixed-order reduction
+    assert abs(e1 - ref) <= 1e-12 * max(1.0, abs(ref))
