@@ -31,12 +31,11 @@
 
 #include "qob_internal.h"
 
-#define QR_T 12
-#define QR_TILE (1 << QR_T)
-#define QR_TILE_BYTES (QR_TILE * 16)
-#define QR_CTHREADS 256                 // consumer threads (8 warps), 16 amplitudes each
-#define QR_THREADS (QR_CTHREADS + 64)   // + one loader warp and one storer warp
-#define QR_USTRIDE 4096                 // byte distance in the staged tile between consecutive amplitudes u of a thread
+// Tile size: 2^T amplitudes, T = 12 (64 KiB tiles, one CTA per SM) or T = 11 (32 KiB tiles, TWO CTAs per SM: the same work per
+// thread and per amplitude, but two independent pipelines per SM, so one CTA's register-only phases, barriers and waits are
+// covered by the other's shared-memory traffic).  The kernel is a template on T; everything else derives from it:
+//   consumer threads 2^(T-4) (16 amplitudes each), byte distance between a thread's amplitudes = 16 * 2^(T-4).
+#define QR_TMAX 12
 #define QR_NSTAGE 3                     // tile buffers: one being loaded, one being worked on, one being stored
 #define QR_MAXC 40                      // lookup records per pass (kernel parameter space)
 #define QR_MAXSEG 8
@@ -302,7 +301,7 @@ __device__ __forceinline__ void qr_inreg(double2 (&acc)[16], const double2 (&xr)
 }
 // bond that leaves the thread: one LDS.128 per amplitude, weights hoisted.  The partner of amplitude u sits at
 // [xt + (u ^ M)*4096]: an immediate offset when the mask has no R bit (MR == false), one XOR per amplitude otherwise.
-template <bool REALW, int SELR, bool MR>
+template <bool REALW, int SELR, bool MR, unsigned US>
 __device__ __forceinline__ void qr_gather(double2 (&acc)[16], const unsigned char *xt, const unsigned char *wt, unsigned mxor) {
   constexpr int NW = 1 << qr_popc(SELR);
   QRW<REALW> w[NW];
@@ -313,13 +312,13 @@ __device__ __forceinline__ void qr_gather(double2 (&acc)[16], const unsigned cha
     double2 v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
-      v[u] = *reinterpret_cast<const double2 *>(xt + (MR ? (((8 * h + u) * (unsigned)QR_USTRIDE) ^ mxor) : (8 * h + u) * (unsigned)QR_USTRIDE));
+      v[u] = *reinterpret_cast<const double2 *>(xt + (MR ? (((8 * h + u) * US) ^ mxor) : (8 * h + u) * US));
 #pragma unroll
     for (int u = 0; u < 8; ++u) w[qr_pext(8 * h + u, SELR)].fma_into(acc[8 * h + u], v[u]);
   }
 }
 // any selector pattern: weight looked up per amplitude
-template <bool REALW>
+template <bool REALW, unsigned US>
 __device__ __forceinline__ void qr_gather_slow(double2 (&acc)[16], const unsigned char *xt, const unsigned char *wt, unsigned selr,
                                                unsigned mxor) {
 #pragma unroll
@@ -333,7 +332,7 @@ __device__ __forceinline__ void qr_gather_slow(double2 (&acc)[16], const unsigne
       }
     QRW<REALW> w;
     w.load(wt + r * (REALW ? 8 : 16));
-    const double2 v = *reinterpret_cast<const double2 *>(xt + ((u * (unsigned)QR_USTRIDE) ^ mxor));
+    const double2 v = *reinterpret_cast<const double2 *>(xt + ((u * US) ^ mxor));
     w.fma_into(acc[u], v);
   }
 }
@@ -378,10 +377,14 @@ __device__ __forceinline__ bool qr_decode(const QRLaunch &L, unsigned item, int 
   return true;
 }
 
-template <bool REALW>
-__global__ void __launch_bounds__(QR_THREADS, 1)
+template <bool REALW, int T>
+__global__ void __launch_bounds__((1 << (T - 4)) + 64, T == 12 ? 1 : 2)
     qreg_kernel(const __grid_constant__ QRLaunch L, const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUtensorMap my0,
                 const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap my1) {
+  constexpr unsigned QR_CTHREADS = 1u << (T - 4);        // consumer threads (8 or 4 warps), 16 amplitudes each
+  constexpr unsigned QR_THREADS = QR_CTHREADS + 64;      // + one loader warp and one storer warp
+  constexpr unsigned QR_TILE_BYTES = 16u << T;
+  constexpr unsigned QR_USTRIDE = QR_CTHREADS * 16u;     // byte distance in the staged tile between consecutive amplitudes u of a thread
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *smem = smem_raw + ((128u - (qr_smem(smem_raw) & 127u)) & 127u);  // TMA destinations: 128-byte aligned
   unsigned char *xs0 = smem;                              // QR_NSTAGE tile buffers: x comes in, the result tile leaves from the same one
@@ -677,14 +680,14 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
           const unsigned selr = (cd.x >> 4) & 15u;
           const unsigned char *wt = tb + qr_entry(cd, P.comps[c], __popc(selr), tid, g_lo, g_hi) * WB;
           const unsigned char *xt = xs + (so ^ cd.w);          // xorB: thread bits of the mask
-          const unsigned mxor = ((cd.x >> 8) & 15u) * (unsigned)QR_USTRIDE;  // R bits of the mask
+          const unsigned mxor = ((cd.x >> 8) & 15u) * QR_USTRIDE;  // R bits of the mask
           switch (cd.x >> 16) {  // 0..10: mask without R bits; 11..21: with R bits; 22: any selector pattern
 #define QR_GA(CODE, SS)                                              \
-  case CODE: qr_gather<REALW, SS, false>(acc, xt, wt, 0u); break;    \
-  case CODE + 11: qr_gather<REALW, SS, true>(acc, xt, wt, mxor); break;
+  case CODE: qr_gather<REALW, SS, false, QR_USTRIDE>(acc, xt, wt, 0u); break;    \
+  case CODE + 11: qr_gather<REALW, SS, true, QR_USTRIDE>(acc, xt, wt, mxor); break;
             QR_GA(0, 0) QR_GA(1, 1) QR_GA(2, 2) QR_GA(3, 4) QR_GA(4, 8) QR_GA(5, 3) QR_GA(6, 5) QR_GA(7, 6) QR_GA(8, 9) QR_GA(9, 10) QR_GA(10, 12)
 #undef QR_GA
-            default: qr_gather_slow<REALW>(acc, xt, wt, selr, mxor); break;
+            default: qr_gather_slow<REALW, QR_USTRIDE>(acc, xt, wt, selr, mxor); break;
           }
         }
       }
@@ -704,7 +707,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
     }
     // all reads of this tile are done by every consumer warp: its buffer now takes the result tile, alpha * acc, which the
     // storer thread sends off through TMA; the buffer returns to the loader when the copy engine has read it
-    asm volatile("bar.sync 1, %0;\n" ::"n"(QR_CTHREADS) : "memory");
+    asm volatile("bar.sync 1, %0;\n" ::"n"(1 << (T - 4)) : "memory");
     q0 = clock64();
     sc_cmp += q0 - q1;
 #pragma unroll
@@ -732,7 +735,7 @@ __global__ void __launch_bounds__(QR_THREADS, 1)
   if (L.stats && (tid & 31u) == 0) {
     long long *o = L.stats + 16 * blockIdx.x + 8;
     if (tid == 0) o[0] = sc_wx, o[1] = sc_cmp, o[2] = sc_wy, o[3] = sc_epi;
-    if (tid == 224) o[4] = sc_wx, o[5] = sc_cmp, o[6] = sc_wy, o[7] = sc_epi;
+    if (tid == QR_CTHREADS - 32) o[4] = sc_wx, o[5] = sc_cmp, o[6] = sc_wy, o[7] = sc_epi;
   }
 }
 
@@ -758,7 +761,7 @@ struct QRTableHost {
   uint32_t tab_off = 0;  // entries
 };
 struct QRPassHost {
-  std::vector<int> free_bits;  // ascending, QR_T of them
+  std::vector<int> free_bits;  // ascending, T of them
   std::vector<int> rpos;       // the 4 tile-local positions that form R (ascending)
   std::vector<QRTableHost> tables;
   QRPass params;
@@ -776,6 +779,7 @@ struct QRPassHost {
 };
 struct QRegProgramHost {
   int nbits = 0;
+  int T = 12;                 // log2 of the tile size (11: two CTAs per SM, 12: one)
   uint64_t hi_value = 0;
   std::vector<QRCompHost> comps;
   std::vector<std::unique_ptr<QRPassHost>> passes;   // execution order
@@ -866,12 +870,13 @@ static void qr_fill_tables(QRegProgramHost &h, const std::vector<cplx> &coefs) {
   h.real_tables = real && !getenv("QOB_QTILE_NO_REALW");
 }
 
-// tile-local bit positions 0..7 belong to the thread id, 8..11 are the R bits (the thread's 16 amplitudes)
+// tile-local bit positions 0..T-5 belong to the thread id, the top four are the R bits (the thread's 16 amplitudes)
 static void qr_layout(QRPassHost &ph, int nbits, uint64_t hi_value) {
   QRPass &P = ph.params;
   const std::vector<int> &fb = ph.free_bits;
-  for (int k = 0; k < 4; ++k) P.rstride[k] = 1ull << fb[8 + k];
-  for (int b = 0; b < 8; ++b) P.tgbit[b] = (unsigned char)fb[b];
+  const int tb = (int)fb.size() - 4;   // thread bits: tile-local positions below the 4 R bits
+  for (int k = 0; k < 4; ++k) P.rstride[k] = 1ull << fb[tb + k];
+  for (int b = 0; b < tb; ++b) P.tgbit[b] = (unsigned char)fb[b];
   std::vector<int> fixed;
   for (int i = 0; i < nbits; ++i)
     if (std::find(fb.begin(), fb.end(), i) == fb.end()) fixed.push_back(i);
@@ -1006,7 +1011,9 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
   auto h = std::make_shared<QRegProgramHost>();
   h->nbits = nbits;
   h->hi_value = hi_value;
-  const int T = QR_T;
+  int T = qr_env_int("QOB_QREG_T", 12);
+  if (T != 11 && T != 12) T = 12;
+  h->T = T;
   if (nbits < T) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg needs at least %d index bits (got %d)", T, nbits);
   if (nbits - T > 31) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: too many tiles");
   const int L = 3;
@@ -1104,7 +1111,7 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
   std::vector<std::vector<int>> rpos(np);
   std::vector<uint64_t> rbits(np, 0);
   for (int p = 0; p < np; ++p) {
-    rpos[p] = {8, 9, 10, 11};
+    rpos[p] = {T - 4, T - 3, T - 2, T - 1};
     for (int k : rpos[p]) rbits[p] |= 1ull << fbits[p][k];
   }
 
@@ -1163,7 +1170,7 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
     for (int k : ph->rpos) rg.push_back(ph->free_bits[k]);
     // a selector bit is an R bit, a thread bit (tile-local position < 8, i.e. a bit of the thread id) or a tile / rank bit
     auto tpos_of = [&](int bit) {  // position in the thread id, -1 if none
-      for (int q = 0; q < 8; ++q)
+      for (int q = 0; q < T - 4; ++q)
         if (ph->free_bits[q] == bit) return q;
       return -1;
     };
@@ -1313,7 +1320,7 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
         if (std::find(c.sel.begin(), c.sel.end(), rg[k]) != c.sel.end()) selr |= 1u << k;
         if (c.mask >> rg[k] & 1) mR |= 1u << k;
       }
-      for (int pos = 0; pos < 8; ++pos)   // thread bits of the mask; its R bits travel in `kind` (mR)
+      for (int pos = 0; pos < T - 4; ++pos)   // thread bits of the mask; its R bits travel in `kind` (mR)
         if (c.mask >> ph->free_bits[pos] & 1) xorB |= 16u << pos;
       if (cls == QR_GATHER && __builtin_popcount(selr) > 2) cls = QR_GATHER_SLOW;
       QRTableHost t;
@@ -1364,20 +1371,20 @@ int qreg_build(QRegProgram &prog, int nbits, uint64_t hi_value, const std::vecto
   // spare, while a chained pair is bound by the shared-memory pipe with DRAM time to spare.  The lone pass goes FIRST: the
   // first launch only writes y (32 B/amplitude instead of 48), so the DRAM-bound launch is the one that saves a third of its
   // traffic; the pair after it accumulates into y through the L2.
-  if (chain_bits >= QR_T && h->passes.size() >= 3 && h->passes.size() % 2 == 1)
+  if (chain_bits >= T && h->passes.size() >= 3 && h->passes.size() % 2 == 1)
     std::rotate(h->passes.begin(), h->passes.end() - 1, h->passes.end());
   for (size_t i = 0; i < h->passes.size();) {
     QRegProgramHost::Group g;
     g.first = (int)i;
     g.count = 1;
-    if (i + 1 < h->passes.size() && chain_bits >= QR_T) {
+    if (i + 1 < h->passes.size() && chain_bits >= T) {
       uint64_t u = 0;
       for (int b : h->passes[i]->free_bits) u |= 1ull << b;
       for (int b : h->passes[i + 1]->free_bits) u |= 1ull << b;
       const int ub = __builtin_popcountll(u);
       if (ub <= chain_bits) {
         g.count = 2;
-        g.tpc_log2 = (unsigned)(ub - QR_T);
+        g.tpc_log2 = (unsigned)(ub - T);
         g.nchunks = 1u << (nbits - ub);
         const unsigned tpc = 1u << g.tpc_log2;
         g.lag = std::max(1u, (unsigned)((qr_env_int("QOB_QREG_LAG_TILES", 192) + tpc - 1) / tpc));
@@ -1515,7 +1522,7 @@ static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, 
   // beta -> y is scaled first (one extra light pass), then every pass adds
   if (!expect_out && beta != cplx(0.0, 0.0) && beta != cplx(1.0, 0.0)) QOB_TRY(launch_scale(y, (int64_t)1 << h.nbits, beta, s));
   double2 *partials = nullptr;
-  const size_t part_per_launch = (size_t)sms * (QR_CTHREADS / 32);
+  const size_t part_per_launch = (size_t)sms * 8;   // consumer warps per SM: 1 CTA x 8 (T = 12) or 2 CTAs x 4 (T = 11)
   if (expect_out) {
     std::lock_guard<std::mutex> lk(h.mu);
     auto it = h.part_bufs.find(s);
@@ -1543,7 +1550,7 @@ static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, 
     Lp.beta = make_double2(beta.real(), beta.imag());
     Lp.queue = sync;
     Lp.done = sync + 32;
-    const unsigned ntiles = 1u << (h.nbits - QR_T);
+    const unsigned ntiles = 1u << (h.nbits - h.T);
     Lp.tpc_log2 = g.tpc_log2;
     Lp.nchunks = g.nchunks;
     Lp.lag = g.lag;
@@ -1587,21 +1594,26 @@ static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, 
     Lp.nstage = max_ctas > 0 ? 2 : QR_NSTAGE;
     Lp.static_queue = expect_out ? 1 : 0;
     Lp.partials = expect_out ? partials + (size_t)(gi - 1) * part_per_launch : nullptr;
-    const size_t smem = (size_t)Lp.nstage * QR_TILE_BYTES + tab_off + 16 + 96 + QR_NSTAGE * sizeof(QRItem) + 2 * QR_MAXC * 16 + 128;
+    const size_t smem = (size_t)Lp.nstage * ((size_t)16 << h.T) + tab_off + 16 + 96 + QR_NSTAGE * sizeof(QRItem) + 2 * QR_MAXC * 16 + 128;
     QOB_CUDA(cudaMemsetAsync(sync, 0, (32 + (size_t)g.nchunks) * sizeof(unsigned), s));
     // one persistent CTA per SM.  A caller that runs another kernel beside this one (the fused exchange of a sharded apply,
     // max_ctas > 0) gets the two-buffer variant: 130 KB of shared memory per SM instead of 195 KB, so that one 64 KB CTA of
     // the other kernel fits on every SM next to it
-    const unsigned grid = std::min<unsigned>((unsigned)sms, ntiles * (unsigned)g.count);
+    const unsigned grid = std::min<unsigned>((unsigned)sms * (h.T == 11 ? 2u : 1u), ntiles * (unsigned)g.count);
     auto launch = [&](auto kern) -> int {
       QOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<grid, QR_THREADS, smem, s>>>(Lp, maps[0], maps[1], maps[2], maps[3]);
+      kern<<<grid, (1u << (h.T - 4)) + 64u, smem, s>>>(Lp, maps[0], maps[1], maps[2], maps[3]);
       QOB_LAUNCHED();
       QOB_CUDA(cudaGetLastError());
       return QOB_STATUS_OK;
     };
-    if (h.real_tables) QOB_TRY(launch(qreg_kernel<true>));
-    else QOB_TRY(launch(qreg_kernel<false>));
+    if (h.T == 11) {
+      if (h.real_tables) QOB_TRY(launch(qreg_kernel<true, 11>));
+      else QOB_TRY(launch(qreg_kernel<false, 11>));
+    } else {
+      if (h.real_tables) QOB_TRY(launch(qreg_kernel<true, 12>));
+      else QOB_TRY(launch(qreg_kernel<false, 12>));
+    }
     qprof_end(s, prof_token);
     if (want_stats && !expect_out) {
       std::vector<long long> hs(16 * 256);
