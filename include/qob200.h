@@ -223,6 +223,31 @@ int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const 
  * in every plan configured with the same chunk bits. */
 int qob_layout_plan_info(qob_op *sum, int32_t plan_id, int32_t *npasses, uint64_t *fixed_mask);
 int qob_layout_plan_set_chunk_bits(qob_op *sum, int32_t plan_id, uint64_t chunk_mask);
+/* ---- the whole sharded apply behind the ABI: planning, CUDA-IPC mapping, device-side barriers, stream choreography ------
+ * For hosts without torch.distributed (the Julia glue, a C program): each process
+ *   1. builds the same LazySum and calls qob_dist_create(sum, rank, world);
+ *   2. allocates its state slab, contribution slab and signal pad with qob_dist_alloc (sizes from qob_dist_info; the pad must be
+ *      zeroed), exports them with qob_ipc_export (64-byte cudaIpcMemHandle_t), moves the handles to the other processes by any
+ *      means it has (MPI, sockets, files), maps the peers' buffers with qob_ipc_open, and hands all pointers to qob_dist_bind;
+ *   3. calls qob_dist_apply(dist, alpha, beta, y, stream) collectively: y_local = alpha*(H x)_local + beta*y_local with x = its
+ *      bound state slab.  The exchange of the terms that act on sharded axes is fused into the tile kernel (peer loads / stores
+ *      over NVLink); the ranks meet in device-side barriers (a kernel that signals every peer's pad and waits on its own); the
+ *      host never blocks and nothing goes through NCCL.
+ * IPC / peer-mapping failures return QOB_STATUS_NCCL_ERROR (the "communication layer" status). */
+typedef struct qob_dist qob_dist;
+int qob_dist_alloc(qob_ctx *ctx, int64_t bytes, void **ptr);
+int qob_dist_free(qob_ctx *ctx, void *ptr);
+int qob_ipc_export(void *ptr, uint8_t *handle64);
+int qob_ipc_open(qob_ctx *ctx, const uint8_t *handle64, void **ptr);
+int qob_ipc_close(qob_ctx *ctx, void *ptr);
+int qob_dist_create(qob_op *sum, int32_t rank, int32_t world, qob_dist **out);
+int qob_dist_info(qob_dist *d, int32_t *nbits_local, int32_t *n_exchanged_terms, int32_t *nchunks, int64_t *slab_bytes,
+                  int64_t *flag_bytes);
+int qob_dist_bind(qob_dist *d, void *const *x_peers, void *const *z_peers, void *const *flag_peers);
+int qob_dist_apply(qob_dist *d, qob_c64 alpha, qob_c64 beta, void *y, void *stream);
+int qob_dist_describe(qob_dist *d, char *buf, int64_t buflen);
+int qob_dist_destroy(qob_dist *d);
+
 /* SMs the persistent tile kernels may occupy by default (0 = all). */
 int qob_set_sm_budget(int32_t sms);
 

@@ -115,6 +115,17 @@ _sigs = {
     "qob_layout_plan_info": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(C.c_uint64)]),
     "qob_layout_plan_set_chunk_bits": (C.c_int, [_vp, _i32, C.c_uint64]),
     "qob_set_sm_budget": (C.c_int, [_i32]),
+    "qob_dist_alloc": (C.c_int, [_vp, _i64, C.POINTER(_vp)]),
+    "qob_dist_free": (C.c_int, [_vp, _vp]),
+    "qob_ipc_export": (C.c_int, [_vp, C.POINTER(C.c_uint8)]),
+    "qob_ipc_open": (C.c_int, [_vp, C.POINTER(C.c_uint8), C.POINTER(_vp)]),
+    "qob_ipc_close": (C.c_int, [_vp, _vp]),
+    "qob_dist_create": (C.c_int, [_vp, _i32, _i32, C.POINTER(_vp)]),
+    "qob_dist_info": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64)]),
+    "qob_dist_bind": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "qob_dist_apply": (C.c_int, [_vp, c64, c64, _vp, _vp]),
+    "qob_dist_describe": (C.c_int, [_vp, C.c_char_p, _i64]),
+    "qob_dist_destroy": (C.c_int, [_vp]),
     "qob_lazydirectsum_create": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_vp)]),
     "qob_expect": (C.c_int, [_vp, _vp, C.POINTER(c64), _vp]),
     "qob_variance": (C.c_int, [_vp, _vp, C.POINTER(c64), _vp]),

@@ -8,7 +8,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
        --fmad=true -cudart static)
 mkdir -p "$HERE/../build"
 OBJS=()
-for f in qob_api qob_kernels_gather qob_kernels_qtile qob_kernels_qreg qob_kernels_dtile qob_kernels_axis qob_kernels_lindblad qob_kernels_ptrace; do
+for f in qob_api qob_kernels_gather qob_kernels_qtile qob_kernels_qreg qob_kernels_dtile qob_kernels_axis qob_kernels_lindblad qob_kernels_ptrace qob_dist; do
   if [ ! -f "$HERE/../build/$f.o" ] || [ "$HERE/$f.cu" -nt "$HERE/../build/$f.o" ] || [ "$HERE/qob_internal.h" -nt "$HERE/../build/$f.o" ] || [ "$HERE/../../include/qob200.h" -nt "$HERE/../build/$f.o" ]; then
     "$NVCC" "${FLAGS[@]}" "$@" -c "$HERE/$f.cu" -o "$HERE/../build/$f.o" &
   fi

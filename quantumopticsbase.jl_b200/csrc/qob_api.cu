@@ -250,6 +250,7 @@ struct DeviceGuard {
   if (device_guard__.err != cudaSuccess)                                                                      \
   QOB_FAIL(QOB_STATUS_CUDA_ERROR, "cudaSetDevice(%d) failed: %s", (int)(dev), cudaGetErrorString(device_guard__.err))
 
+qob_ctx *qob_op_context(const qob_op *op) { return op ? op->ctx : nullptr; }
 static void op_retain(qob_op *o) { o->refs.fetch_add(1); }
 static void op_release(qob_op *o) {
   if (o->refs.fetch_sub(1) == 1) delete o;

@@ -262,6 +262,9 @@ int launch_ptrace_op(qob_ctx *ctx, int slot, int nsub, const int64_t *dims_l, co
 int launch_ptrace_state(qob_ctx *ctx, int slot, int nsub, const int64_t *dims, int ntraced, const int32_t *traced, bool bra, const void *psi,
                         void *result, cudaStream_t s);
 
+// the context an operator handle was created on (qob_dist.cu)
+qob_ctx *qob_op_context(const qob_op *op);
+
 // misc device helpers
 int launch_fill_state(void *x, int64_t offset, int64_t n, uint64_t seed, double scale, cudaStream_t s);
 int launch_norm2(const void *x, int64_t n, double *host_out, cudaStream_t s);

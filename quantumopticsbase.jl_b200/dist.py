@@ -327,3 +327,105 @@ class ShardedLazySum:
             w.wait()
         y.add_(b1)
         return y
+
+
+class _DevBuf:
+    """A raw device allocation seen through __cuda_array_interface__, so that torch can view it without copying."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class DistLazySum:
+    """The sharded apply THROUGH THE C ABI (`qob_dist_*`, csrc/qob_dist.cu): planning, CUDA-IPC mapping of the peers' slabs,
+    device-side barriers and the stream choreography of the fused exchange all live in libqob200.  This class only
+    allocates, moves the 64-byte IPC handles between the processes (torch.distributed all_gather — any channel would do) and
+    forwards `mul_`.  It is what a Julia / C host does with MPI or sockets instead.
+
+        sh = DistLazySum(H, rank, world)     # collective
+        sh.x                                 # this rank's slab of the state (torch complex128 view of library memory)
+        sh.mul_(y, alpha, beta)              # y_local = alpha * (H x)_local + beta * y_local, collective
+    """
+
+    def __init__(self, H: LazySum, rank: int, world: int, group=None, ctx=None):
+        import torch
+        import torch.distributed as dist
+
+        self.H, self.rank, self.world, self.group = H, rank, world, group
+        self.ctx = _lib.context() if ctx is None else ctx
+        self.h = handle(H, self.ctx)
+        d = C.c_void_p()
+        _lib.check(lib.qob_dist_create(self.h, rank, world, C.byref(d)))
+        self.d = d
+        nloc, nrem, nch = C.c_int32(), C.c_int32(), C.c_int32()
+        slab, flagb = C.c_int64(), C.c_int64()
+        _lib.check(lib.qob_dist_info(d, C.byref(nloc), C.byref(nrem), C.byref(nch), C.byref(slab), C.byref(flagb)))
+        self.nloc, self.n_remote, self.nchunks = nloc.value, nrem.value, nch.value
+        self.n = len(H.basis_l.shape)
+        self._own, self._peers = [], []
+
+        def alloc(nbytes):
+            p = C.c_void_p()
+            _lib.check(lib.qob_dist_alloc(self.ctx, nbytes, C.byref(p)))
+            self._own.append(p)
+            return p
+
+        px = alloc(slab.value)
+        self.x = torch.view_as_complex(torch.as_tensor(_DevBuf(px.value, slab.value), device="cuda").view(-1, 2))
+        tables = [[px.value] * world, None, None]
+        if self.n_remote and world > 1:
+            pz, pf = alloc(slab.value), alloc(flagb.value)
+            torch.as_tensor(_DevBuf(pf.value, flagb.value), device="cuda").zero_()
+            torch.cuda.synchronize()
+            mine = torch.empty(3 * 64, dtype=torch.uint8)
+            for k, p in enumerate((px, pz, pf)):
+                hb = (C.c_uint8 * 64)()
+                _lib.check(lib.qob_ipc_export(p, hb))
+                mine[64 * k:64 * (k + 1)] = torch.frombuffer(bytearray(hb), dtype=torch.uint8)
+            backend = dist.get_backend(group)
+            dev = "cuda" if backend == "nccl" else "cpu"
+            allh = torch.empty(world * 3 * 64, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine.to(dev), group=group)
+            allh = allh.cpu().view(world, 3, 64)
+            own = (px.value, pz.value, pf.value)
+            tables = [[], [], []]
+            for q in range(world):
+                for k in range(3):
+                    if q == rank:
+                        tables[k].append(own[k])
+                        continue
+                    hb = (C.c_uint8 * 64)(*allh[q, k].tolist())
+                    pp = C.c_void_p()
+                    _lib.check(lib.qob_ipc_open(self.ctx, hb, C.byref(pp)))
+                    self._peers.append(pp)
+                    tables[k].append(pp.value)
+            dist.barrier(group=group)   # every pad is zeroed and every mapping exists before the first apply
+        arr = [None if t is None else (C.c_void_p * world)(*t) for t in tables]
+        _lib.check(lib.qob_dist_bind(d, arr[0], arr[1], arr[2]))
+
+    def describe(self):
+        buf = C.create_string_buffer(1 << 15)
+        _lib.check(lib.qob_dist_describe(self.d, buf, len(buf)))
+        return buf.value.decode()
+
+    def mul_(self, y, alpha=1.0, beta=0.0):
+        import torch
+
+        handle(self.H, self.ctx)   # coefficients may have been mutated (TimeDependentSum): re-sent here
+        _lib.check(lib.qob_dist_apply(self.d, c64.of(complex(alpha)), c64.of(complex(beta)), C.c_void_p(y.data_ptr()),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return y
+
+    def close(self):
+        import torch
+
+        if getattr(self, "d", None):
+            torch.cuda.synchronize()
+            lib.qob_dist_destroy(self.d)
+            self.d = None
+            self.x = None
+            for p in self._peers:
+                lib.qob_ipc_close(self.ctx, p)
+            for p in self._own:
+                lib.qob_dist_free(self.ctx, p)
+            self._peers, self._own = [], []

@@ -172,22 +172,33 @@ def _nccl_worker(rank, world, port, n, beta, out_dir, fused):
         p = world.bit_length() - 1
         nloc = n - p
         spec = chain_spec(n, 21)
-        sh = ShardedLazySum(build_q(Q, n, spec), rank, world)
-        x = sh.empty_state() if fused else torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
+        if fused == "capi":   # everything behind the C ABI: qob_dist_* (IPC mapping, device barriers, choreography)
+            from qob200.dist import DistLazySum
+
+            sh = DistLazySum(build_q(Q, n, spec), rank, world)
+            x = sh.x
+        else:
+            sh = ShardedLazySum(build_q(Q, n, spec), rank, world)
+            x = sh.empty_state() if fused else torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
         Q.fill_state(x, 3, 2.0 ** (-n / 2), offset=rank << nloc)
         y = torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
         Q.fill_state(y, 4, 1.0, offset=rank << nloc)
         for _ in range(2):   # twice: the second call reuses the contribution buffer
             Q.fill_state(y, 4, 1.0, offset=rank << nloc)
-            (sh.mul_fused_ if fused else sh.mul_)(y, x, 0.7 - 0.2j, beta)
+            if fused == "capi":
+                sh.mul_(y, 0.7 - 0.2j, beta)
+            else:
+                (sh.mul_fused_ if fused else sh.mul_)(y, x, 0.7 - 0.2j, beta)
         torch.cuda.synchronize()
+        if fused == "capi":
+            sh.close()
         np.save(os.path.join(out_dir, f"y{rank}.npy"), y.cpu().numpy())
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("n", [18, 21])   # 21 spins: the fused schedule runs its exchange / fold-in passes in 4 chunks
-@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("fused", [False, True, "capi"])
 @pytest.mark.parametrize("beta", [0.0, 0.5 + 0.25j])
 def test_sharded_apply_nccl(tmp_path, beta, fused, n):
     import torch
@@ -288,3 +299,60 @@ def test_sharded_apply_full_size_spot_oracle(tmp_path):
     if os.path.isdir(out):
         with open(os.path.join(out, f"full_size_spot_{world}gpu.txt"), "w") as f:
             f.write("\n".join(lines) + "\n")
+
+
+def test_two_devices_in_one_process():
+    """One process, one qob_ctx per device (what the Julia glue's per-device CONTEXTS does): the shared-memory opt-in of the tile
+    kernels and the SM count are per-device state, so the FIRST launch on the second device must configure it again."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    import qob200 as Q
+
+    n = 21
+    spec = chain_spec(n, 31)
+    results = []
+    for dev in (1, 0, 1):      # the second device first: nothing is configured for it yet
+        torch.cuda.set_device(dev)
+        Hs = build_q(Q, n, spec)
+        b = Q.SpinBasis(0.5)
+        B = Q.tensor(*[b] * n)
+        x = Q.Ket(B)
+        Q.fill_state(x.data, 9, 2.0 ** (-n / 2))
+        y = Q.Ket(B)
+        assert x.data.device.index == dev
+        Q.mul_(y, Hs, x, 0.7 - 0.2j, 0.0)
+        # the same operator through the round-1 tile kernel and the mixed-radix / gather kernels on this device
+        e = Q.expect(Hs, x)
+        torch.cuda.synchronize()
+        results.append((y.data.cpu().numpy(), e))
+    torch.cuda.set_device(0)
+    for yv, e in results[1:]:
+        assert H.rel_err(yv, results[0][0]) <= 1e-14
+        assert abs(e - results[0][1]) <= 1e-12 * max(1.0, abs(results[0][1]))
+    xfull = O.fill_state(1 << n, 9, 2.0 ** (-n / 2))
+    ref = oracle_result(n, spec, 0.7 - 0.2j, 0.0, xfull, np.zeros(1 << n, dtype=complex))
+    assert H.rel_err(results[0][0], ref) <= 1e-12
+
+
+@pytest.mark.parametrize("n", [16, 20])
+def test_dist_c_abi_single_rank(n):
+    """qob_dist_* with world = 1 on any box: library-owned slab (qob_dist_alloc), bind, apply == the ordinary mul!."""
+    import torch
+
+    import qob200 as Q
+    from qob200.dist import DistLazySum
+
+    spec = chain_spec(n, 41)
+    Hs = build_q(Q, n, spec)
+    sh = DistLazySum(Hs, 0, 1)
+    assert sh.nloc == n and sh.n_remote == 0
+    Q.fill_state(sh.x, 3, 2.0 ** (-n / 2))
+    y = torch.empty(1 << n, dtype=torch.complex128, device="cuda")
+    Q.fill_state(y, 4, 1.0)
+    sh.mul_(y, 0.7 - 0.2j, 0.5 + 0.25j)
+    torch.cuda.synchronize()
+    ref = oracle_result(n, spec, 0.7 - 0.2j, 0.5 + 0.25j, O.fill_state(1 << n, 3, 2.0 ** (-n / 2)), O.fill_state(1 << n, 4, 1.0))
+    assert H.rel_err(y.cpu().numpy(), ref) <= 1e-12
+    sh.close()

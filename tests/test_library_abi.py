@@ -404,3 +404,33 @@ def test_ptrace_argument_checks_and_directsum_planning(Q):
     assert d.startswith("lazydirectsum[") and "sparse 3x3" in d, d
     S2 = Q.LazyDirectSum(S, A)      # nested sums are flattened (src/spinors.jl:166-168)
     assert len(S2.operators) == 3 and len(S2.basis_l) == 10
+
+
+def test_dist_planning_behind_the_abi(Q):
+    """qob_dist_create: term classification, swap window and chunking of the sharded apply are planned inside the library
+    (planning-only context: no GPU needed); 8 ranks x 2^30 amplitudes = BASELINE config 5."""
+    import ctypes as C
+
+    from qob200 import _lib
+    from qob200.operators import handle
+
+    ctx = Q.context(-1)
+    _, Hs = chain(Q, 33)
+    h = handle(Hs, ctx)
+    d = C.c_void_p()
+    _lib.check(_lib.lib.qob_dist_create(h, 5, 8, C.byref(d)))
+    nloc, nrem, nch = C.c_int32(), C.c_int32(), C.c_int32()
+    slab, flagb = C.c_int64(), C.c_int64()
+    _lib.check(_lib.lib.qob_dist_info(d, C.byref(nloc), C.byref(nrem), C.byref(nch), C.byref(slab), C.byref(flagb)))
+    assert (nloc.value, slab.value) == (30, 16 << 30) and flagb.value >= 64
+    assert nrem.value == 8          # XX and YY of the four bonds that touch a sharded axis; their ZZ parts are rank-dependent weights
+    assert nch.value == 4
+    buf = C.create_string_buffer(1 << 15)
+    _lib.check(_lib.lib.qob_dist_describe(d, buf, len(buf)))
+    text = buf.value.decode()
+    assert text.startswith("dist[rank 5/8, 2^30 amplitudes per rank, 91 local + 8 exchanged terms, chunks=4]"), text[:200]
+    assert "exchanged (window bit" in text and "qreg[bits=30" in text
+    # apply without bound buffers / on a planning-only context fails loudly
+    assert _lib.lib.qob_dist_apply(d, _lib.c64.of(1.0), _lib.c64.of(0.0), C.c_void_p(16), None) == 3
+    assert _lib.lib.qob_dist_create(h, 3, 6, C.byref(C.c_void_p())) == 3      # world must be a power of two
+    _lib.check(_lib.lib.qob_dist_destroy(d))
