@@ -275,6 +275,28 @@ def run_product(args, rank, world, local_rank):
     run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps, peak, peak_src, H, alpha)
 
 
+DEFAULT_EXCHANGE = "capi"   # the sharded apply behind the C ABI (qob_dist_*), direct mode; "fused": the Python orchestration over
+                            # torch symmetric memory; "nccl": all-to-all axis swaps
+
+
+def host_memory_available():
+    """bytes of host memory this process tree may still take: min(MemAvailable, cgroup limit - cgroup usage)"""
+    avail = float("inf")
+    try:
+        import psutil
+
+        avail = float(psutil.virtual_memory().available)
+    except Exception:
+        pass
+    try:
+        lim = open("/sys/fs/cgroup/memory.max").read().strip()
+        if lim != "max":
+            avail = min(avail, float(lim) - float(open("/sys/fs/cgroup/memory.current").read().strip()))
+    except Exception:
+        pass
+    return avail
+
+
 def run_product_dist(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -290,14 +312,28 @@ def run_product_dist(args, rank, world, local_rank):
     p = world.bit_length() - 1
     free, _total = torch.cuda.mem_get_info()
     n = args.spins or 33
-    nbuf = 3 if os.environ.get("QOB_DIST_EXCHANGE", "fused") == "fused" else 4   # x, y, contributions (+ staging for NCCL)
+    mode = os.environ.get("QOB_DIST_EXCHANGE", DEFAULT_EXCHANGE)
+    # slabs per rank: x, y (capi in direct mode: the exchange adds into the owners' y); + contributions (fused); + staging (nccl)
+    nbuf = {"capi": 2 if os.environ.get("QOB_DIST_DIRECT", "1") != "0" else 3, "fused": 3}.get(mode, 4)
     while nbuf * 16 * (1 << (n - p)) > 0.85 * free and n > 20:
         n -= 1
     nloc = n - p
     B, H = build_chain(Q, n)
-    sh = ShardedLazySum(H, rank, world)
-    exchange = os.environ.get("QOB_DIST_EXCHANGE", "fused")
+    exchange = mode
     x = None
+    if exchange == "capi":
+        # the whole sharded apply behind the C ABI (qob_dist_*): the library owns planning, IPC mapping, barriers and streams
+        from qob200.dist import DistLazySum
+
+        try:
+            sh = DistLazySum(H, rank, world)
+            x = sh.x
+        except Exception as e:     # CUDA IPC between the ranks' processes unavailable on this box
+            if rank == 0:
+                print(f"[bench] qob_dist_* unavailable ({type(e).__name__}: {e}); using the torch symmetric-memory orchestration", file=sys.stderr)
+            exchange = "fused"
+    if exchange != "capi":
+        sh = ShardedLazySum(H, rank, world)
     if exchange == "fused":
         try:
             x = sh.empty_state()   # symmetric memory: peers load their tiles straight from this slab over NVLink
@@ -308,11 +344,15 @@ def run_product_dist(args, rank, world, local_rank):
     if x is None:
         x = torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
     Q.fill_state(x, 7, 2.0 ** (-n / 2), offset=rank << nloc)
-    y = torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
+    y = sh.y if exchange == "capi" and sh.direct else torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
+    if exchange == "capi":
+        exchange = "capi-direct" if sh.direct else "capi"
     plan = f"exchange={exchange}: " + sh.describe()
 
     def step():
-        if exchange == "fused":
+        if exchange.startswith("capi"):
+            sh.mul_(y, alpha, 0.0)
+        elif exchange == "fused":
             sh.mul_fused_(y, x, alpha, 0.0)
         else:
             sh.mul_(y, x, alpha, 0.0)
@@ -442,7 +482,7 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
     barrier()
     # ---- timed region: exactly `steps` steps
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
-    if sharded is not None:
+    if sharded is not None and hasattr(sharded, "exchange_stats"):
         sharded.time_exchange = True
         sharded._ex_events = []
     l0 = Q.launch_count()
@@ -456,7 +496,7 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     nvlink = None
-    if sharded is not None:
+    if sharded is not None and hasattr(sharded, "exchange_stats"):
         sharded.time_exchange = False
         ex_ms, per_dir = sharded.exchange_stats()
         if ex_ms:
@@ -491,7 +531,11 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
     e2e_steps = max(1, min(3, steps)) if world == 1 else 1
     slab_bytes = 16 * (1 << nloc)
     e2e_s, e2e_err, t_e2e, e2e_single_s, kets = None, None, [], None, 1
+    if rank == 0:
+        print(f"[bench] timed region: {ms_step:.3f} ms per step; end-to-end leg next", file=sys.stderr, flush=True)
     try:
+        if os.environ.get("QOB_BENCH_SKIP_E2E"):   # tuning sweeps only; the contract run never sets it
+            raise RuntimeError("skipped (QOB_BENCH_SKIP_E2E)")
         if sharded is None:
             kets = max(1, int(os.environ.get("QOB_BENCH_E2E_KETS", "4")))
             hx = torch.empty((kets, 1 << nloc), dtype=torch.complex128, pin_memory=True)
@@ -511,11 +555,16 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
                 if i > 0:
                     t_e2e.append((time.perf_counter() - t0) / kets)
         else:
+            # one pinned slab per rank serves both directions (upload, mul!, download are ordered on the stream); skip the leg
+            # rather than let the kernel's OOM killer end the run when the ranks of this node cannot pin that much
+            need = slab_bytes * world
+            if need > 0.6 * host_memory_available():
+                raise MemoryError(f"e2e leg needs {need >> 30} GiB of pinned host memory on this node")
             hx = torch.empty(1 << nloc, dtype=torch.complex128, pin_memory=True)
-            hy = torch.empty(1 << nloc, dtype=torch.complex128, pin_memory=True)
-            hx.copy_(xs)
-            torch.cuda.synchronize()
+            hy = hx
             for i in range(e2e_steps + 1):
+                hx.copy_(xs)               # (untimed) the shared pinned slab holds x again: the last download put y there
+                torch.cuda.synchronize()
                 barrier()
                 t0 = time.perf_counter()
                 xs.copy_(hx, non_blocking=True)

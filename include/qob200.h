@@ -139,6 +139,9 @@ int qob_op_apply_host(qob_op *op, int32_t side, qob_c64 alpha, const qob_c64 *x,
 /* Introspection used by tests/bench: number of kernel launches issued by this library in this
  * process, and a text description of the plan chosen for `op` (passes, tiles, kernels). */
 int64_t qob_launch_count(void);
+/* launches per kernel family: 1 round-1 tile kernel, 2 round-2 tile kernel (qreg), 3 round-2 tile kernel peer-addressed (the
+ * exchange of a sharded apply over NVLink), 4 round-1 tile kernel peer-addressed; -1 for an unknown family */
+int64_t qob_launch_count_of(int32_t family);
 int qob_op_describe(qob_op *op, int32_t side, int64_t batch, char *buf, int64_t buflen);
 
 /* Per-kernel timing for the roofline report: while enabled, every tile-pass launch is bracketed by
@@ -244,8 +247,19 @@ int qob_dist_create(qob_op *sum, int32_t rank, int32_t world, qob_dist **out);
 int qob_dist_info(qob_dist *d, int32_t *nbits_local, int32_t *n_exchanged_terms, int32_t *nchunks, int64_t *slab_bytes,
                   int64_t *flag_bytes);
 int qob_dist_bind(qob_dist *d, void *const *x_peers, void *const *z_peers, void *const *flag_peers);
+/* Direct mode (when qob_dist_direct_capable says yes): also allocate the RESULT slab with qob_dist_alloc, exchange its handle
+ * like the state's and pass the table to qob_dist_bind_result.  qob_dist_apply with y = this rank's entry then needs no
+ * contribution slab (z_peers may be NULL in qob_dist_bind): the exchange pass adds its results into the owners' result slabs
+ * (cp.reduce.async.bulk, an f64 add performed by the owner's L2), so a rank holds 2 slabs instead of 3 — N=33 fits on 2 GPUs.
+ * The order in which the contributions are added is not fixed: results are reproducible to rounding, not bit for bit. */
+int qob_dist_direct_capable(qob_dist *d, int32_t *yes);
+int qob_dist_bind_result(qob_dist *d, void *const *y_peers);
 int qob_dist_apply(qob_dist *d, qob_c64 alpha, qob_c64 beta, void *y, void *stream);
 int qob_dist_describe(qob_dist *d, char *buf, int64_t buflen);
+/* CUDA-event timing of the exchange step (first barrier passed -> every rank's contributions landed) of the applies issued while
+ * enabled; qob_dist_exchange_ms returns the mean over them and the bytes that cross this GPU's NVLink per direction per apply. */
+int qob_dist_exchange_timing(qob_dist *d, int32_t enable);
+int qob_dist_exchange_ms(qob_dist *d, double *mean_ms, int32_t *count, int64_t *bytes_per_direction);
 int qob_dist_destroy(qob_dist *d);
 
 /* SMs the persistent tile kernels may occupy by default (0 = all). */

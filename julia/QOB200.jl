@@ -336,4 +336,80 @@ function apply!(drho::DevOp{B,B}, L::LindbladRHS, rho::DevOp{B,B}, alpha=true, b
     drho
 end
 
+# ---- sharded apply across processes / GPUs (include/qob200.h: qob_dist_*).  The state of a LazySum over 2-level sites is cut
+# into `world` slabs on its most significant index bits, one process per GPU.  The library plans the exchange, maps the peers'
+# slabs through CUDA IPC and runs the fused exchange; the host only has to move 192 bytes per rank once.  `allgather` is any
+# function Vector{UInt8} -> Vector{Vector{UInt8}} ordered by rank (MPI.Allgather, a socket, a shared file) and `barrier` any
+# zero-argument function that returns once all ranks called it.
+mutable struct ShardedLazySum
+    dist::Ptr{Cvoid}
+    op::LazySum
+    rank::Int
+    world::Int
+    nbits_local::Int
+    x::CuVector{ComplexF64}       # this rank's slab of the state (library memory, visible to the peers)
+    own::Vector{Ptr{Cvoid}}
+    peers::Vector{Ptr{Cvoid}}
+end
+function _dist_alloc(bytes)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qob_dist_alloc, libqob200), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), context(), bytes, p))
+    p[]
+end
+function ShardedLazySum(op::LazySum, rank::Integer, world::Integer; allgather, barrier)
+    h = handle(op)
+    d = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:qob_dist_create, libqob200), Cint, (Ptr{Cvoid}, Int32, Int32, Ref{Ptr{Cvoid}}), h.ptr, rank, world, d))
+    nloc, nrem, nch = Ref{Int32}(0), Ref{Int32}(0), Ref{Int32}(0)
+    slab, flagb = Ref{Int64}(0), Ref{Int64}(0)
+    check(ccall((:qob_dist_info, libqob200), Cint, (Ptr{Cvoid}, Ref{Int32}, Ref{Int32}, Ref{Int32}, Ref{Int64}, Ref{Int64}),
+                d[], nloc, nrem, nch, slab, flagb))
+    own, peers = Ptr{Cvoid}[], Ptr{Cvoid}[]
+    px = _dist_alloc(slab[]); push!(own, px)
+    x = unsafe_wrap(CuArray, CuPtr{ComplexF64}(UInt(px)), slab[] >> 4)
+    tx, tz, tf = fill(px, world), nothing, nothing
+    if nrem[] > 0 && world > 1
+        pz, pf = _dist_alloc(slab[]), _dist_alloc(flagb[]); push!(own, pz, pf)
+        fill!(unsafe_wrap(CuArray, CuPtr{UInt8}(UInt(pf)), flagb[]), 0x00); CUDA.synchronize()
+        mine = Vector{UInt8}(undef, 192)
+        for (k, p) in enumerate((px, pz, pf))
+            GC.@preserve mine check(ccall((:qob_ipc_export, libqob200), Cint, (Ptr{Cvoid}, Ptr{UInt8}), p, pointer(mine, 64k - 63)))
+        end
+        all = allgather(mine)
+        tabs = (Ptr{Cvoid}[], Ptr{Cvoid}[], Ptr{Cvoid}[])
+        for q in 0:world-1, k in 1:3
+            if q == rank
+                push!(tabs[k], (px, pz, pf)[k])
+            else
+                pp = Ref{Ptr{Cvoid}}(C_NULL)
+                hb = all[q+1][64k-63:64k]
+                check(ccall((:qob_ipc_open, libqob200), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ref{Ptr{Cvoid}}), context(), hb, pp))
+                push!(peers, pp[]); push!(tabs[k], pp[])
+            end
+        end
+        tx, tz, tf = tabs
+        barrier()   # every pad is zeroed and every mapping exists before the first apply
+    end
+    check(ccall((:qob_dist_bind, libqob200), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
+                d[], tx, tz === nothing ? C_NULL : tz, tf === nothing ? C_NULL : tf))
+    sh = ShardedLazySum(d[], op, rank, world, nloc[], x, own, peers)
+    finalizer(close!, sh)
+end
+"y_local = alpha * (op * x)_local + beta * y_local with x = `sh.x` on every rank; collective over the ranks"
+function apply!(y::DevVec, sh::ShardedLazySum, alpha=true, beta=false)
+    handle(sh.op)   # re-sends mutated coefficients (time-dependent sums)
+    GC.@preserve sh check(ccall((:qob_dist_apply, libqob200), Cint, (Ptr{Cvoid}, C64, C64, CuPtr{Cvoid}, Ptr{Cvoid}),
+                                sh.dist, C64(alpha), C64(beta), pointer(y), CUDA.stream().handle))
+    y
+end
+function close!(sh::ShardedLazySum)
+    sh.dist == C_NULL && return
+    CUDA.synchronize()
+    ccall((:qob_dist_destroy, libqob200), Cint, (Ptr{Cvoid},), sh.dist); sh.dist = C_NULL
+    foreach(p -> ccall((:qob_ipc_close, libqob200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), context(), p), sh.peers)
+    foreach(p -> ccall((:qob_dist_free, libqob200), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), context(), p), sh.own)
+    empty!(sh.peers); empty!(sh.own)
+    nothing
+end
+
 end # module

@@ -100,6 +100,7 @@ _sigs = {
     "qob_op_apply": (C.c_int, [_vp, _i32, c64, _vp, c64, _vp, _i64, _vp]),
     "qob_op_apply_host": (C.c_int, [_vp, _i32, c64, _vp, c64, _vp, _i64]),
     "qob_launch_count": (_i64, []),
+    "qob_launch_count_of": (_i64, [_i32]),
     "qob_op_describe": (C.c_int, [_vp, _i32, _i64, C.c_char_p, _i64]),
     "qob_fill_state": (C.c_int, [_vp, _i64, _i64, C.c_uint64, C.c_double, _vp]),
     "qob_norm2": (C.c_int, [_vp, _i64, C.POINTER(C.c_double), _vp]),
@@ -124,6 +125,10 @@ _sigs = {
     "qob_dist_info": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64)]),
     "qob_dist_bind": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "qob_dist_apply": (C.c_int, [_vp, c64, c64, _vp, _vp]),
+    "qob_dist_exchange_timing": (C.c_int, [_vp, _i32]),
+    "qob_dist_exchange_ms": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i32), C.POINTER(_i64)]),
+    "qob_dist_direct_capable": (C.c_int, [_vp, C.POINTER(_i32)]),
+    "qob_dist_bind_result": (C.c_int, [_vp, C.POINTER(_vp)]),
     "qob_dist_describe": (C.c_int, [_vp, C.c_char_p, _i64]),
     "qob_dist_destroy": (C.c_int, [_vp]),
     "qob_lazydirectsum_create": (C.c_int, [_vp, _i32, C.POINTER(_vp), C.POINTER(_vp)]),

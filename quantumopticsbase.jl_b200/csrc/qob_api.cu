@@ -14,6 +14,8 @@
 #include "qob_internal.h"
 
 std::atomic<int64_t> g_launch_count{0};
+std::atomic<int64_t> g_family_count[8];
+#define QT_MAXPEER_API 16
 thread_local bool t_planning_only = false;
 struct PlanningScope {
   bool prev;
@@ -694,6 +696,7 @@ struct LazySumOp : qob_op {
     // the communication-free group of a sharded apply is the bulk of its HBM traffic
     bool has_qreg = false;
     QRegProgram qreg;
+    uint64_t chunk_mask = 0;   // qob_layout_plan_set_chunk_bits
   };
   std::vector<std::unique_ptr<LayoutPlan>> layouts;
   LazySumOp(qob_ctx *c) : qob_op(c, OP_LAZYSUM) {}
@@ -1369,6 +1372,7 @@ int qob_op_apply_host(qob_op *op, int32_t side, qob_c64 alpha, const qob_c64 *x,
 }
 
 int64_t qob_launch_count(void) { return g_launch_count.load(); }
+int64_t qob_launch_count_of(int32_t family) { return family >= 0 && family < 8 ? g_family_count[family].load() : -1; }
 
 int qob_op_describe(qob_op *op, int32_t side, int64_t batch, char *buf, int64_t buflen) {
   if (!op || !buf || buflen < 1) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null argument");
@@ -1641,17 +1645,48 @@ int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const 
     std::lock_guard<std::mutex> lk(S->coef_mu);
     cf = S->coefs;
   }
-  // sm_budget < 0: the launch runs BESIDE another kernel (the fused exchange).  The round-2 kernel keeps 168 registers x 320
-  // threads and >= 130 KB of shared memory per SM for the whole launch, so no CTA of the other kernel fits next to it and the
-  // two would serialise (measured: 8 GPUs, N=33: 80 ms instead of 53 ms); the round-1 kernel (3 small CTAs per SM) shares SMs.
-  if (lp.has_qreg && npeers == 0 && !zadd && o.nchunks <= 1 && sm_budget == 0) {
-    QOB_TRY(qreg_set_coefs(lp.qreg, cf, s));
-    return qreg_launch(lp.qreg, C(alpha), x, C(beta), y, s);
+  // Which kernel.  The round-2 kernel (one persistent CTA fills an SM) runs every launch it supports: plain ones, peer-addressed
+  // ones (the exchange: contiguous pieces over NVLink) and tile ranges.  Two kernels that run beside each other split the SMs:
+  //   sm_budget  > 0 : at most that many SMs (the exchange);      sm_budget < -1 : all but |sm_budget| SMs (the local passes)
+  //   sm_budget == -1: the round-1 kernel, whose small CTAs fill whatever room the other kernel leaves on any SM
+  // (a full-grid round-2 launch beside a round-1 exchange serialised: 8 GPUs, N=33: 80 ms instead of 53 ms).
+  static const bool qreg_peer_off = getenv("QOB_DIST_QREG") && atoi(getenv("QOB_DIST_QREG")) == 0;
+  if (lp.has_qreg && !zadd && sm_budget != -1 && !(qreg_peer_off && (npeers > 0 || o.nchunks > 1 || sm_budget != 0))) {
+    QRegOpts ro;
+    ro.max_ctas = sm_budget > 0 ? sm_budget : (sm_budget < -1 ? std::max(1, S->ctx->sm_count + sm_budget) : 0);
+    ro.npeers = o.npeers;
+    ro.xpeer = o.xpeer;
+    ro.ypeer = o.ypeer;
+    ro.peer_shift = o.peer_shift;
+    ro.peer_rank = o.peer_rank;
+    ro.chunk_mask = lp.chunk_mask;
+    ro.chunk_index = o.chunk_index;
+    ro.nchunks = o.nchunks;
+    if (qreg_supports(lp.qreg, ro)) {
+      QOB_TRY(qreg_set_coefs(lp.qreg, cf, s));
+      return qreg_launch_ex(lp.qreg, C(alpha), x, C(beta), y, s, ro);
+    }
   }
   if (o.sm_budget < 0) o.sm_budget = 0;
   QOB_TRY(qtile_set_coefs(lp.prog, cf, s));
   return qtile_launch(lp.prog, C(alpha), x, C(beta), y, s, &o);
 }
+
+}  // extern "C"
+bool layout_plan_peer_qreg(qob_op *sum, int plan_id, int npeers, int peer_shift) {
+  LazySumOp *S = nullptr;
+  if (qubit_sum(sum, &S) != QOB_STATUS_OK || plan_id < 0 || plan_id >= (int)S->layouts.size()) return false;
+  const LazySumOp::LayoutPlan &lp = *S->layouts[plan_id];
+  if (!lp.has_qreg || (getenv("QOB_DIST_QREG") && atoi(getenv("QOB_DIST_QREG")) == 0)) return false;
+  static const void *dummy[QT_MAXPEER_API] = {};
+  QRegOpts ro;
+  ro.npeers = npeers;
+  ro.xpeer = dummy;
+  ro.ypeer = (void *const *)dummy;
+  ro.peer_shift = peer_shift;
+  return qreg_supports(lp.qreg, ro);
+}
+extern "C" {
 
 int qob_layout_plan_info(qob_op *sum, int32_t plan_id, int32_t *npasses, uint64_t *fixed_mask) {
   LazySumOp *S = nullptr;
@@ -1669,7 +1704,9 @@ int qob_layout_plan_set_chunk_bits(qob_op *sum, int32_t plan_id, uint64_t chunk_
   LazySumOp *S = nullptr;
   QOB_TRY(qubit_sum(sum, &S));
   if (plan_id < 0 || plan_id >= (int)S->layouts.size()) QOB_FAIL(QOB_STATUS_INVALID_ARG, "bad layout plan id");
-  return qtile_set_chunk_bits(S->layouts[plan_id]->prog, chunk_mask);
+  QOB_TRY(qtile_set_chunk_bits(S->layouts[plan_id]->prog, chunk_mask));
+  S->layouts[plan_id]->chunk_mask = chunk_mask;
+  return QOB_STATUS_OK;
 }
 
 int qob_layout_plan_describe(qob_op *sum, int32_t plan_id, char *buf, int64_t buflen) {

@@ -11,6 +11,10 @@
 //   side stream : barrier | remote-term pass, chunk 0 (PEER tile kernel: loads x tiles from the owners' slabs over NVLink,
 //                 stores results into the owners' contribution slabs) | barrier | chunk 1 | barrier | ...
 //   main stream : communication-free terms, group A (beside the exchange)      | group B chunk 0 (+ contributions) | chunk 1 ...
+// Direct mode (qob_dist_bind_result: the result slab is mapped by the peers too; no contribution slab, 2 slabs per rank):
+//   main stream : y = beta*y | ------------ every communication-free term, on all but k SMs, adding into y ------------ | wait
+//   side stream :             barrier | remote-term pass on k SMs: x pieces come from the owners' slabs by bulk copy, results
+//                                       are ADDED into the owners' y slabs (cp.reduce.async.bulk, f64 add in the owner's L2) | barrier
 // The barrier is a tiny kernel: every rank writes its epoch into every peer's signal pad (system-scope release) and spins until
 // every peer's epoch has arrived in its own pad (system-scope acquire).
 #include <algorithm>
@@ -25,6 +29,10 @@ struct qob_dist {
   int rank = 0, world = 1, p = 0, n = 0, nloc = 0;
   int n_local = 0, n_remote = 0;
   int plan_a = -1, plan_b = -1, plan_r = -1;
+  bool direct_ok = false;   // the exchange pass can ADD into the owners' result slabs (round-2 kernel, peer-addressed)
+  std::vector<void *> y_peers;
+  bool timing = false;      // qob_dist_exchange_timing: CUDA events around the exchange of every apply
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
   int swap_lo = -1;
   int nchunks = 1;
   uint64_t chunk_mask = 0;
@@ -215,6 +223,9 @@ int qob_dist_create(qob_op *sum, int32_t rank, int32_t world, qob_dist **out) {
     }
   }
   d->swap_sms = env_dist("QOB_DIST_SWAP_SMS", 32);
+  if (cR) {
+    d->direct_ok = layout_plan_peer_qreg(sum, d->plan_r, world, d->swap_lo);
+  }
   char buf[8192];
   std::string t = "dist[rank " + std::to_string(rank) + "/" + std::to_string(world) + ", 2^" + std::to_string(d->nloc) + " amplitudes per rank, " +
                   std::to_string(d->n_local) + " local + " + std::to_string(d->n_remote) + " exchanged terms, chunks=" + std::to_string(d->nchunks) + "]";
@@ -222,6 +233,7 @@ int qob_dist_create(qob_op *sum, int32_t rank, int32_t world, qob_dist **out) {
   if (d->plan_b >= 0 && qob_layout_plan_describe(sum, d->plan_b, buf, sizeof buf) == QOB_STATUS_OK) t += std::string(" | B: ") + buf;
   if (d->plan_r >= 0 && qob_layout_plan_describe(sum, d->plan_r, buf, sizeof buf) == QOB_STATUS_OK)
     t += " | exchanged (window bit " + std::to_string(d->swap_lo) + "): " + buf;
+  if (d->direct_ok) t += " | direct mode available (the exchange adds into the owners' result slabs)";
   d->text = t;
   *out = d.release();
   return QOB_STATUS_OK;
@@ -250,11 +262,14 @@ int qob_dist_bind(qob_dist *d, void *const *x_peers, void *const *z_peers, void 
   if (!d || !x_peers) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null argument");
   d->x_peers.assign(x_peers, x_peers + d->world);
   if (d->n_remote) {
-    if (!z_peers || !flag_peers) QOB_FAIL(QOB_STATUS_INVALID_ARG, "exchanged terms need contribution slabs and signal pads");
-    d->z_peers.assign(z_peers, z_peers + d->world);
+    if (!flag_peers) QOB_FAIL(QOB_STATUS_INVALID_ARG, "exchanged terms need signal pads");
+    if (!z_peers && !d->direct_ok)
+      QOB_FAIL(QOB_STATUS_INVALID_ARG, "exchanged terms need contribution slabs (this plan cannot add into the result slabs directly)");
+    if (z_peers) d->z_peers.assign(z_peers, z_peers + d->world);
+    else d->z_peers.clear();
     d->flag_peers.assign(flag_peers, flag_peers + d->world);
     for (int q = 0; q < d->world; ++q)
-      if (!d->x_peers[q] || !d->z_peers[q] || !d->flag_peers[q]) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null peer pointer %d", q);
+      if (!d->x_peers[q] || (z_peers && !d->z_peers[q]) || !d->flag_peers[q]) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null peer pointer %d", q);
     if (!d->ctx || d->ctx->device < 0) QOB_FAIL(QOB_STATUS_CUDA_ERROR, "planning-only context (no CUDA device): libqob200 has no CPU fallback");
     int prev = -1;
     cudaGetDevice(&prev);
@@ -278,6 +293,23 @@ int qob_dist_bind(qob_dist *d, void *const *x_peers, void *const *z_peers, void 
     }
   }
   d->bound = true;
+  return QOB_STATUS_OK;
+}
+
+// Direct mode: the result slab of every rank as mapped into this process.  An apply whose `y` is this rank's entry then needs no
+// contribution slab: the exchange pass adds into the owners' results.  yes = 0 from qob_dist_direct_capable: not available for
+// this plan (slabs below 2^20 amplitudes, scattered pieces); bind contribution slabs instead.
+int qob_dist_direct_capable(qob_dist *d, int32_t *yes) {
+  if (!d || !yes) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null argument");
+  *yes = (d->direct_ok && env_dist("QOB_DIST_DIRECT", 1) != 0) ? 1 : 0;
+  return QOB_STATUS_OK;
+}
+int qob_dist_bind_result(qob_dist *d, void *const *y_peers) {
+  if (!d || !y_peers) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null argument");
+  if (!d->direct_ok) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "this plan cannot add into the result slabs directly (see qob_dist_direct_capable)");
+  for (int q = 0; q < d->world; ++q)
+    if (!y_peers[q]) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null peer pointer %d", q);
+  d->y_peers.assign(y_peers, y_peers + d->world);
   return QOB_STATUS_OK;
 }
 
@@ -307,22 +339,82 @@ int qob_dist_apply(qob_dist *d, qob_c64 alpha, qob_c64 beta, void *y, void *stre
     if (d->plan_b >= 0 && !alpha_zero) QOB_TRY(qob_layout_plan_apply(d->sum, d->plan_b, alpha, x, one, y, stream));
     return QOB_STATUS_OK;
   }
-  void *z = d->z_peers[d->rank];
   int sms = qob_device_sm_count();
   const int k = std::max(4, std::min(d->swap_sms, sms / 2));
+  auto time_begin = [&]() -> int {
+    if (!d->timing) return QOB_STATUS_OK;
+    cudaEvent_t a, b;
+    QOB_CUDA(cudaEventCreate(&a));
+    QOB_CUDA(cudaEventCreate(&b));
+    d->timed.emplace_back(a, b);
+    QOB_CUDA(cudaEventRecord(a, d->side));
+    return QOB_STATUS_OK;
+  };
+  auto time_end = [&]() -> int {
+    if (d->timing && !d->timed.empty()) QOB_CUDA(cudaEventRecord(d->timed.back().second, d->side));
+    return QOB_STATUS_OK;
+  };
+  if (d->direct_ok && !d->y_peers.empty() && y == d->y_peers[d->rank] && env_dist("QOB_DIST_DIRECT", 1) != 0) {
+    // direct mode: prepare y, then every pass (local and exchanged, on any rank) adds into it
+    const int64_t namp = (int64_t)1 << d->nloc;
+    // QOB_DIST_TRACE=1: phase times of this apply on stderr (synchronises at the end of the call; debugging only)
+    const bool trace = env_dist("QOB_DIST_TRACE", 0) != 0;
+    cudaEvent_t te[7] = {};
+    auto mark = [&](int i, cudaStream_t s) {
+      if (!trace) return;
+      cudaEventCreate(&te[i]);
+      cudaEventRecord(te[i], s);
+    };
+    mark(0, main);
+    if (beta.re == 0.0 && beta.im == 0.0) QOB_CUDA(cudaMemsetAsync(y, 0, (size_t)namp * 16, main));
+    else if (!(beta.re == 1.0 && beta.im == 0.0)) QOB_TRY(launch_scale(y, namp, cplx(beta.re, beta.im), main));
+    QOB_CUDA(cudaEventRecord(d->ev_main, main));
+    mark(1, main);
+    QOB_CUDA(cudaStreamWaitEvent(d->side, d->ev_main, 0));
+    QOB_TRY(dist_barrier(d, d->side));                               // every rank: x ready, y prepared
+    QOB_TRY(time_begin());
+    mark(3, d->side);
+    QOB_TRY(qob_layout_plan_apply_ex(d->sum, d->plan_r, alpha, nullptr, one, nullptr, nullptr, d->world, (const void *const *)d->x_peers.data(),
+                                     d->y_peers.data(), d->swap_lo, k, 0, 1, d->side));
+    mark(4, d->side);
+    QOB_TRY(dist_barrier(d, d->side));                               // every contribution has landed; nobody reads this x any more
+    QOB_TRY(time_end());
+    mark(5, d->side);
+    QOB_CUDA(cudaEventRecord(d->ev_done, d->side));
+    // both groups of communication-free terms, on the SMs the exchange leaves free, adding into y
+    QOB_TRY(qob_layout_plan_apply_ex(d->sum, d->plan_a, alpha, x, one, y, nullptr, 0, nullptr, nullptr, 0, -k, 0, 1, main));
+    if (d->plan_b >= 0) QOB_TRY(qob_layout_plan_apply_ex(d->sum, d->plan_b, alpha, x, one, y, nullptr, 0, nullptr, nullptr, 0, -k, 0, 1, main));
+    mark(2, main);
+    QOB_CUDA(cudaStreamWaitEvent(main, d->ev_done, 0));
+    mark(6, main);
+    if (trace) {
+      cudaStreamSynchronize(main);
+      cudaStreamSynchronize(d->side);
+      float t[7] = {};
+      for (int i = 1; i < 7; ++i) cudaEventElapsedTime(&t[i], te[0], te[i]);
+      fprintf(stderr, "[qob_dist trace] rank %d: y prepared %.2f | local passes done %.2f | exchange: barrier passed %.2f, kernel done %.2f, "
+                      "all ranks done %.2f | apply done %.2f ms\n", d->rank, t[1], t[2], t[3], t[4], t[5], t[6]);
+      for (auto &e : te) cudaEventDestroy(e);
+    }
+    return QOB_STATUS_OK;
+  }
+  if (d->z_peers.empty()) QOB_FAIL(QOB_STATUS_INVALID_ARG, "no contribution slabs bound and y is not the bound result slab");
+  void *z = d->z_peers[d->rank];
   if (d->plan_b >= 0) {
     const int nc = d->nchunks;
     QOB_CUDA(cudaEventRecord(d->ev_main, main));
     QOB_CUDA(cudaStreamWaitEvent(d->side, d->ev_main, 0));            // x is ready on this rank
     QOB_TRY(dist_barrier(d, d->side));                               // ... and on every rank; last apply's contributions are consumed
+    QOB_TRY(time_begin());
     for (int c = 0; c < nc; ++c) {
       QOB_TRY(qob_layout_plan_apply_ex(d->sum, d->plan_r, alpha, nullptr, zero, nullptr, nullptr, d->world, (const void *const *)d->x_peers.data(),
                                        d->z_peers.data(), d->swap_lo, k, c, nc, d->side));
       QOB_TRY(dist_barrier(d, d->side));                             // chunk c of every rank's contributions has landed
       QOB_CUDA(cudaEventRecord(d->ev_chunk[c], d->side));
     }
-    // beside the exchange: the communication-free group A (sm_budget -1: the kernel whose CTAs share SMs with the exchange's)
-    QOB_TRY(qob_layout_plan_apply_ex(d->sum, d->plan_a, alpha, x, beta, y, nullptr, 0, nullptr, nullptr, 0, -1, 0, 1, main));
+    QOB_TRY(time_end());
+    // beside the exchange: the communication-free group A on the SMs the exchange leaves free (sm_budget -k)
+    QOB_TRY(qob_layout_plan_apply_ex(d->sum, d->plan_a, alpha, x, beta, y, nullptr, 0, nullptr, nullptr, 0, -k, 0, 1, main));
     for (int c = 0; c < nc; ++c) {                                   // fold the contributions in, chunk by chunk, behind the exchange
       QOB_CUDA(cudaStreamWaitEvent(main, d->ev_chunk[c], 0));
       QOB_TRY(qob_layout_plan_apply_ex(d->sum, d->plan_b, alpha, x, one, y, z, 0, nullptr, nullptr, 0, 0, c, nc, main));
@@ -334,6 +426,34 @@ int qob_dist_apply(qob_dist *d, qob_c64 alpha, qob_c64 beta, void *y, void *stre
     QOB_TRY(dist_barrier(d, main));
     QOB_TRY(qob_layout_plan_apply_ex(d->sum, d->plan_a, alpha, x, beta, y, z, 0, nullptr, nullptr, 0, 0, 0, 1, main));
   }
+  return QOB_STATUS_OK;
+}
+
+// CUDA-event timing of the exchange (first barrier passed -> last contributions landed on every rank) of the applies issued
+// while it is enabled; qob_dist_exchange_ms synchronises the exchange stream and returns the mean over those applies
+int qob_dist_exchange_timing(qob_dist *d, int32_t enable) {
+  if (!d) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null handle");
+  d->timing = enable != 0;
+  return QOB_STATUS_OK;
+}
+int qob_dist_exchange_ms(qob_dist *d, double *mean_ms, int32_t *count, int64_t *bytes_per_direction) {
+  if (!d) QOB_FAIL(QOB_STATUS_INVALID_ARG, "null handle");
+  double sum = 0.0;
+  int n = 0;
+  if (d->side) QOB_CUDA(cudaStreamSynchronize(d->side));
+  for (auto &ev : d->timed) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) sum += ms, ++n;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  cudaGetLastError();
+  d->timed.clear();
+  if (mean_ms) *mean_ms = n ? sum / n : 0.0;
+  if (count) *count = n;
+  // per apply and direction on this GPU's links: the (1 - 1/P) share of its swapped-layout x pieces comes in from the peers and the
+  // same share of the peers' results comes in too (and the mirror image goes out)
+  if (bytes_per_direction) *bytes_per_direction = (int64_t)(2.0 * (1.0 - 1.0 / d->world) * 16.0 * (double)((int64_t)1 << d->nloc));
   return QOB_STATUS_OK;
 }
 

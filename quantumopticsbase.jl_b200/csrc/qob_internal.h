@@ -45,6 +45,10 @@ extern std::atomic<int64_t> g_launch_count;
 // become no-ops so that validation and planning can be exercised (and tested) on a box without a GPU.
 extern thread_local bool t_planning_only;
 #define QOB_LAUNCHED() (g_launch_count.fetch_add(1, std::memory_order_relaxed))
+// launches per kernel family (qob_launch_count_of): 0 gather, 1 round-1 tile kernel, 2 round-2 tile kernel, 3 round-2 tile kernel
+// peer-addressed (exchange over NVLink), 4 round-1 tile kernel peer-addressed
+extern std::atomic<int64_t> g_family_count[8];
+#define QOB_LAUNCHED_FAMILY(f) (g_family_count[f].fetch_add(1, std::memory_order_relaxed))
 
 // ---------------------------------------------------------------- host matrices
 // A site factor after `trans` has been applied, in one of three normal forms.
@@ -229,8 +233,26 @@ struct QRegProgram {
 // Returns QOB_STATUS_UNSUPPORTED when the terms do not fit the scheme (the caller then uses the qtile kernel).
 int qreg_build(QRegProgram &p, int nbits, uint64_t hi_value, const std::vector<QTerm> &terms, int sm_count);
 int qreg_set_coefs(QRegProgram &p, const std::vector<cplx> &coefs, cudaStream_t s);
-// max_ctas > 0: another kernel runs beside this one: use two tile buffers instead of three so that its CTAs fit on every SM
+// max_ctas > 0: the launch occupies at most that many SMs (one persistent CTA each); the others stay free for a kernel of
+// another stream (the fused exchange of a sharded apply and the local passes share the GPU this way)
 int qreg_launch(const QRegProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, int max_ctas = 0);
+// Peer-addressed launch / launch over one tile range (the exchange step of a sharded apply; qob_layout_plan_apply_ex).
+struct QRegOpts {
+  int max_ctas = 0;
+  int npeers = 0;                       // > 0: x and y are the SWAPPED layout spread over the ranks' slabs
+  const void *const *xpeer = nullptr;
+  void *const *ypeer = nullptr;
+  int peer_shift = 0, peer_rank = 0;
+  uint64_t chunk_mask = 0;              // nchunks > 1: these fixed index bits number the tile ranges
+  int chunk_index = 0, nchunks = 1;
+};
+// can this program run peer-addressed / chunked with these options? (single pass, contiguous pieces of >= 1 KiB, ...)
+bool qreg_supports(const QRegProgram &p, const QRegOpts &o);
+// can layout plan `plan_id` of a LazySum run its peer-addressed launches on the round-2 kernel (bulk-copy pieces, adds into the
+// owners' buffers)?  (qob_api.cu; used by the sharded apply to choose its schedule)
+struct qob_op;
+bool layout_plan_peer_qreg(qob_op *sum, int plan_id, int npeers, int peer_shift);
+int qreg_launch_ex(const QRegProgram &p, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, const QRegOpts &o);
 
 // <x| op |x> in one sweep over x (no result vector is written): every pass reduces conj(x)*acc; deterministic
 int qreg_expect(const QRegProgram &p, const void *x, cplx *out, cudaStream_t s);

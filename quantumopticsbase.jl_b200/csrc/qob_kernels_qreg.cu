@@ -59,6 +59,7 @@ struct QRComp {       // 32 bytes
   uint32_t code;      // dense body number for the dispatch switch
 };
 
+#define QR_MAXPEER 16
 struct QRPass {
   unsigned long long rstride[4];  // element stride in global memory of R bit k
   unsigned char tgbit[8];         // consumer-thread bit b -> flat-index bit
@@ -81,6 +82,10 @@ struct QRPass {
   // chained launches: compact tile id = deposit(chunk id, cs_*) | deposit(tile within chunk, js_*)
   int ncs, njs;
   unsigned char cs_l[4], cs_n[4], cs_d[4], js_l[4], js_n[4], js_d[4];
+  // peer-addressed pass (the exchange of a sharded state): the pass works on the SWAPPED layout of the ranks' slabs.  Index
+  // bits [peer_shift, peer_shift + peer_bits) of an element's address name the rank that holds it; there it sits at the same
+  // address with those bits replaced by this rank's number.  The tile moves as 2^(T - piece_log2) contiguous pieces.
+  int peer_bits, peer_shift, peer_rank, piece_log2;
   QRComp comps[QR_MAXC];
 };
 
@@ -97,6 +102,10 @@ struct QRLaunch {
   double2 *partials;     // mode 3: one partial sum per consumer warp, [blockIdx.x * 8 + warp]
   long long *stats;      // debug (QOB_QREG_STATS=1): per-CTA cycle counts of the pipeline phases, 16 per CTA
   double2 alpha, beta;
+  int remap;             // single pass over one tile range: compact tile id = deposit(chunk_fixed, cs_*) | deposit(item, js_*)
+  unsigned chunk_fixed;
+  const double2 *xpeer[QR_MAXPEER];   // peer-addressed pass: every rank's slab of x and of the buffer that receives the results
+  double2 *ypeer[QR_MAXPEER];
   QRPass pass[2];
 };
 
@@ -172,6 +181,25 @@ __device__ __forceinline__ void qr_tma_store(const CUtensorMap *map, unsigned sr
     default: QR_TS("5d", "{%2, %3, %4, %5, %6}", "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])) break;
   }
 #undef QR_TS
+}
+
+// peer-addressed passes: one contiguous piece of a tile, global (any rank's slab, over NVLink) <-> shared memory
+__device__ __forceinline__ void qr_bulk_load(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void qr_bulk_store(void *dst, unsigned src, unsigned bytes, bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;\n" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+  else
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+// element `a` of the swapped layout -> (owning rank, element offset in that rank's slab)
+__device__ __forceinline__ unsigned qr_peer_of(const QRPass &P, unsigned long long a, unsigned long long &phys) {
+  const unsigned long long m = ((1ull << P.peer_bits) - 1ull) << P.peer_shift;
+  phys = (a & ~m) | ((unsigned long long)P.peer_rank << P.peer_shift);
+  return (unsigned)((a & m) >> P.peer_shift);
 }
 
 // pull a tile into L2 without occupying shared memory (the DRAM latency is paid here, several tiles ahead)
@@ -344,7 +372,8 @@ struct QRItem {     // 64 bytes, written by the producer for the consumers
   unsigned pad;
   double dre, dim;  // diagonal weight that is the same for every amplitude of the tile
   int co[5];        // tensor-map coordinates of the tile (the result goes out through the same box)
-  int pad2[3];
+  int pad2;
+  unsigned long long tbase;   // element offset of the tile (peer-addressed passes move the tile piece by piece)
 };
 
 // work item -> (pass, chunk, tile within chunk); false when the queue is exhausted
@@ -433,7 +462,16 @@ __global__ void __launch_bounds__((1 << (T - 4)) + 64, T == 12 ? 1 : 2)
         if (it.pass < 0) break;
         const QRPass &P = L.pass[it.pass];
         if (P.mode != 3) {
-          qr_tma_store(it.pass ? &my1 : &my0, qr_smem(xs0 + stage * QR_TILE_BYTES), P.rank, it.co, P.mode != 0);
+          if (P.peer_bits > 0) {
+            const unsigned pbytes = 16u << P.piece_log2;
+            for (unsigned jp = 0; jp < (1u << (T - P.piece_log2)); ++jp) {
+              unsigned long long phys;
+              const unsigned q = qr_peer_of(P, it.tbase | qr_expand(jp << P.piece_log2, P.nfree_seg, P.fs_l, P.fs_n, P.fs_g), phys);
+              qr_bulk_store(L.ypeer[q] + phys, qr_smem(xs0 + stage * QR_TILE_BYTES + jp * pbytes), pbytes, P.mode != 0);
+            }
+          } else {
+            qr_tma_store(it.pass ? &my1 : &my0, qr_smem(xs0 + stage * QR_TILE_BYTES), P.rank, it.co, P.mode != 0);
+          }
           asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
         }
@@ -492,7 +530,9 @@ __global__ void __launch_bounds__((1 << (T - 4)) + 64, T == 12 ? 1 : 2)
       }
       ++st_n;
       const QRPass &P = L.pass[p];
-      t = L.npass == 1 ? j : (qr_deposit(c, P.ncs, P.cs_l, P.cs_n, P.cs_d) | qr_deposit(j, P.njs, P.js_l, P.js_n, P.js_d));
+      t = (L.npass == 1 && !L.remap) ? j
+                                     : (qr_deposit(L.remap ? L.chunk_fixed : c, P.ncs, P.cs_l, P.cs_n, P.cs_d) |
+                                        qr_deposit(j, P.njs, P.js_l, P.js_n, P.js_d));
       // tile-constant diagonal weight: lane k evaluates table k
       double dre = 0.0, dim = 0.0;
       if (P.n_pretile > 0) {
@@ -524,6 +564,8 @@ __global__ void __launch_bounds__((1 << (T - 4)) + 64, T == 12 ? 1 : 2)
         it.dim = dim;
 #pragma unroll
         for (int d = 0; d < 5; ++d) it.co[d] = co[d];
+        it.pad2 = 0;
+        it.tbase = P.peer_bits > 0 ? qr_expand(t, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g) : 0ull;
         slots[stage] = it;
         if (P.wait) {
           const unsigned need = 1u << L.tpc_log2;   // every pass-1 tile of the chunk
@@ -538,10 +580,20 @@ __global__ void __launch_bounds__((1 << (T - 4)) + 64, T == 12 ? 1 : 2)
         }
         const unsigned long long pol = P.stream_out ? pol_stream : pol_keep;
         qr_mbar_expect(qr_smem(bars + stage), QR_TILE_BYTES);
-        qr_tma_load(qr_smem(xs0 + stage * QR_TILE_BYTES), p ? &mx1 : &mx0, qr_smem(bars + stage), P.rank, co, pol);
+        if (P.peer_bits == 0) qr_tma_load(qr_smem(xs0 + stage * QR_TILE_BYTES), p ? &mx1 : &mx0, qr_smem(bars + stage), P.rank, co, pol);
         item = L.static_queue ? item + gridDim.x : atomicAdd(L.queue, 1u);   // the next item: the atomic's latency overlaps the consumers' work
       }
       __syncwarp();
+      if (P.peer_bits > 0) {
+        // every lane fetches its pieces of the tile from the ranks that hold them (NVLink loads straight into shared memory)
+        const unsigned long long tb = qr_expand(t, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g);
+        const unsigned pbytes = 16u << P.piece_log2;
+        for (unsigned jp = lane; jp < (1u << (T - P.piece_log2)); jp += 32) {
+          unsigned long long phys;
+          const unsigned q = qr_peer_of(P, tb | qr_expand(jp << P.piece_log2, P.nfree_seg, P.fs_l, P.fs_n, P.fs_g), phys);
+          qr_bulk_load(qr_smem(xs0 + stage * QR_TILE_BYTES + jp * pbytes), L.xpeer[q] + phys, pbytes, qr_smem(bars + stage));
+        }
+      }
       stage = stage + 1 == nst ? 0 : stage + 1;
     }
     return;
@@ -1491,19 +1543,53 @@ int qreg_set_coefs(QRegProgram &prog, const std::vector<cplx> &coefs, cudaStream
 }
 
 
-static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, int max_ctas,
+static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, const QRegOpts &o,
                             cplx *expect_out);
 int qreg_launch(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, int max_ctas) {
-  return qreg_launch_impl(prog, alpha, x, beta, y, s, max_ctas, nullptr);
+  QRegOpts o;
+  o.max_ctas = max_ctas;
+  return qreg_launch_impl(prog, alpha, x, beta, y, s, o, nullptr);
+}
+int qreg_launch_ex(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, const QRegOpts &o) {
+  if (!qreg_supports(prog, o)) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: peer-addressed / chunked launch not supported by this program");
+  return qreg_launch_impl(prog, alpha, x, beta, y, s, o, nullptr);
+}
+// lowest run of free bits of a pass = the contiguous pieces a peer-addressed launch moves
+static int qr_low_run(const QRPassHost &ph) {
+  int r = 0;
+  while (r < (int)ph.free_bits.size() && ph.free_bits[r] == r) ++r;
+  return r;
+}
+bool qreg_supports(const QRegProgram &prog, const QRegOpts &o) {
+  if (!prog.h) return false;
+  const QRegProgramHost &h = *prog.h;
+  if (o.npeers == 0 && o.nchunks <= 1) return true;
+  if (h.passes.size() != 1 || h.T != 12) return false;
+  const QRPassHost &ph = *h.passes[0];
+  if (o.npeers > 0) {
+    if (o.npeers > QR_MAXPEER || (o.npeers & (o.npeers - 1)) || !o.xpeer || !o.ypeer) return false;
+    const int r = qr_low_run(ph);
+    if (r < 6 || o.peer_shift < r) return false;       // pieces of >= 1 KiB that never straddle two ranks
+  }
+  if (o.nchunks > 1) {
+    if (o.nchunks & (o.nchunks - 1)) return false;
+    if (__builtin_popcountll(o.chunk_mask) != __builtin_ctz((unsigned)o.nchunks)) return false;
+    for (int b : ph.free_bits)
+      if (o.chunk_mask >> b & 1) return false;         // range bits must be fixed bits of the pass
+    if (o.chunk_mask >> h.nbits) return false;
+  }
+  return true;
 }
 // <x| op |x> without writing op*x: every launch runs in mode 3 and leaves per-warp partial sums; tiles are dealt statically
 // and the partials are added in a fixed order, so the result is reproducible bit for bit
 int qreg_expect(const QRegProgram &prog, const void *x, cplx *out, cudaStream_t s) {
-  return qreg_launch_impl(prog, cplx(1.0, 0.0), x, cplx(0.0, 0.0), nullptr, s, 0, out);
+  return qreg_launch_impl(prog, cplx(1.0, 0.0), x, cplx(0.0, 0.0), nullptr, s, QRegOpts(), out);
 }
-static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, int max_ctas,
+static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, cplx beta, void *y, cudaStream_t s, const QRegOpts &o,
                             cplx *expect_out) {
   QRegProgramHost &h = *prog.h;
+  const int max_ctas = o.max_ctas;
+  const bool peer = o.npeers > 0;
   int dev = 0, sms = 148;
   QOB_CUDA(cudaGetDevice(&dev));
   QOB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1520,6 +1606,8 @@ static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, 
   }
   // y = alpha*H x + beta*y: beta == 0 -> the first pass stores (y is never read); beta == 1 -> every pass adds; any other
   // beta -> y is scaled first (one extra light pass), then every pass adds
+  if (peer && beta != cplx(0.0, 0.0) && beta != cplx(1.0, 0.0))
+    QOB_FAIL(QOB_STATUS_INVALID_ARG, "peer-addressed launch: beta must be 0 (store) or 1 (add into the owners' buffers)");
   if (!expect_out && beta != cplx(0.0, 0.0) && beta != cplx(1.0, 0.0)) QOB_TRY(launch_scale(y, (int64_t)1 << h.nbits, beta, s));
   double2 *partials = nullptr;
   const size_t part_per_launch = (size_t)sms * 8;   // consumer warps per SM: 1 CTA x 8 (T = 12) or 2 CTAs x 4 (T = 11)
@@ -1566,11 +1654,15 @@ static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, 
       QRPassHost &ph = *h.passes[g.first + q];
       {
         std::lock_guard<std::mutex> lk(h.mu);
-        if (ph.map_x_ptr != x) {
+        if (peer) {
+          // no tensor maps: the tile moves as contiguous pieces addressed per rank (any valid map fills the parameter slots)
+          if (!ph.map_x_ptr) QOB_TRY(qr_encode_map(ph, o.xpeer[0], &ph.map_x));
+          if (!ph.map_y_ptr) ph.map_y = ph.map_x;
+        } else if (ph.map_x_ptr != x) {
           QOB_TRY(qr_encode_map(ph, x, &ph.map_x));
           ph.map_x_ptr = x;
         }
-        if (!expect_out && ph.map_y_ptr != y) {
+        if (!peer && !expect_out && ph.map_y_ptr != y) {
           QOB_TRY(qr_encode_map(ph, y, &ph.map_y));
           ph.map_y_ptr = y;
         }
@@ -1591,19 +1683,64 @@ static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, 
       maps[2] = maps[0];
       maps[3] = maps[1];
     }
-    Lp.nstage = max_ctas > 0 ? 2 : QR_NSTAGE;
+    Lp.nstage = QR_NSTAGE;
+    unsigned items = ntiles * (unsigned)g.count;
+    if (peer) {
+      QRPass &P = Lp.pass[0];
+      P.peer_bits = __builtin_ctz((unsigned)o.npeers);
+      P.peer_shift = o.peer_shift;
+      P.peer_rank = o.peer_rank;
+      P.piece_log2 = std::min(qr_low_run(*h.passes[g.first]), 10);   // pieces of <= 16 KiB
+      for (int q = 0; q < o.npeers; ++q) {
+        Lp.xpeer[q] = (const double2 *)o.xpeer[q];
+        Lp.ypeer[q] = (double2 *)o.ypeer[q];
+      }
+    }
+    if (o.nchunks > 1) {
+      // tile range `chunk_index`: the chunk bits (fixed bits of the pass) hold chunk_index, the other fixed bits count the tiles
+      QRPassHost &ph = *h.passes[g.first];
+      QRPass &P = Lp.pass[0];
+      std::vector<int> fixed;
+      for (int b = 0; b < h.nbits; ++b)
+        if (std::find(ph.free_bits.begin(), ph.free_bits.end(), b) == ph.free_bits.end()) fixed.push_back(b);
+      int ci = 0, ji = 0, prev_kind = -1;
+      P.ncs = P.njs = 0;
+      for (size_t k = 0; k < fixed.size(); ++k) {
+        const int kind = (o.chunk_mask >> fixed[k] & 1) ? 0 : 1;   // 0: numbers the range, 1: counts inside it
+        unsigned char *sl = kind ? P.js_l : P.cs_l, *sn = kind ? P.js_n : P.cs_n, *sd = kind ? P.js_d : P.cs_d;
+        int &ns = kind ? P.njs : P.ncs;
+        int &src = kind ? ji : ci;
+        if (kind == prev_kind) {
+          sn[ns - 1]++;
+        } else {
+          if (ns >= 4) QOB_FAIL(QOB_STATUS_UNSUPPORTED, "qreg: tile-range structure too scattered");
+          sl[ns] = (unsigned char)src;
+          sn[ns] = 1;
+          sd[ns] = (unsigned char)k;
+          ++ns;
+        }
+        ++src;
+        prev_kind = kind;
+      }
+      Lp.remap = 1;
+      Lp.chunk_fixed = (unsigned)o.chunk_index;
+      items = ntiles / (unsigned)o.nchunks;
+      Lp.total_items = items;
+    }
     Lp.static_queue = expect_out ? 1 : 0;
     Lp.partials = expect_out ? partials + (size_t)(gi - 1) * part_per_launch : nullptr;
     const size_t smem = (size_t)Lp.nstage * ((size_t)16 << h.T) + tab_off + 16 + 96 + QR_NSTAGE * sizeof(QRItem) + 2 * QR_MAXC * 16 + 128;
     QOB_CUDA(cudaMemsetAsync(sync, 0, (32 + (size_t)g.nchunks) * sizeof(unsigned), s));
-    // one persistent CTA per SM.  A caller that runs another kernel beside this one (the fused exchange of a sharded apply,
-    // max_ctas > 0) gets the two-buffer variant: 130 KB of shared memory per SM instead of 195 KB, so that one 64 KB CTA of
-    // the other kernel fits on every SM next to it
-    const unsigned grid = std::min<unsigned>((unsigned)sms * (h.T == 11 ? 2u : 1u), ntiles * (unsigned)g.count);
+    // one persistent CTA per SM; max_ctas > 0 leaves the other SMs to a kernel of another stream (a CTA of this kernel fills
+    // an SM's shared memory, so the two kernels never share an SM: the exchange of a sharded apply gets its own SMs and NVLink
+    // rate, the local passes the rest)
+    unsigned grid = std::min<unsigned>((unsigned)sms * (h.T == 11 ? 2u : 1u), items);
+    if (max_ctas > 0) grid = std::min<unsigned>(grid, (unsigned)max_ctas);
     auto launch = [&](auto kern) -> int {
       QOB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       kern<<<grid, (1u << (h.T - 4)) + 64u, smem, s>>>(Lp, maps[0], maps[1], maps[2], maps[3]);
       QOB_LAUNCHED();
+      QOB_LAUNCHED_FAMILY(peer ? 3 : 2);
       QOB_CUDA(cudaGetLastError());
       return QOB_STATUS_OK;
     };

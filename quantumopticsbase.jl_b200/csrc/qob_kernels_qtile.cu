@@ -967,6 +967,7 @@ static int launch_pass(const QTileProgramHost &h, const QPassHost &p, const QPas
   uint64_t grid = std::min<uint64_t>(ntiles, (uint64_t)std::max(1, max_ctas));
   qtile_kernel<T, THREADS, MINB, IDX64, REALW, PEER><<<(unsigned)grid, THREADS, smem, s>>>(P, (const double2 *)x, (double2 *)y);
   QOB_LAUNCHED();
+  QOB_LAUNCHED_FAMILY(PEER ? 4 : 1);
   QOB_CUDA(cudaGetLastError());
   return QOB_STATUS_OK;
 }

@@ -250,9 +250,9 @@ class ShardedLazySum:
                     self._ex_events.append((e0, e1))
             # beside the exchange: the local passes use a full grid; the exchange kernel is persistent with k*occupancy
             # CTAs on a high-priority stream, so it keeps its share of the slots while local CTAs come and go
-            # sm_budget = -1: "runs beside another kernel" -> the library picks the tile kernel whose CTAs share SMs with the
-            # exchange kernel's (the persistent one-CTA-per-SM kernel would serialise with it)
-            self._apply_ex(self.plan_local, alpha, x, beta, y, sm_budget=self.local_budget if self.local_budget else -1)
+            # sm_budget = -k: "all but k SMs": the exchange pass (round-2 kernel, one persistent CTA per SM on k SMs) and the
+            # local passes (the same kernel on the other SMs) never share an SM, so the exchange keeps its NVLink rate
+            self._apply_ex(self.plan_local, alpha, x, beta, y, sm_budget=self.local_budget if self.local_budget else -k)
             for c in range(nc):                        # fold the contributions in, chunk by chunk, behind the exchange
                 main.wait_event(events[c])
                 self._apply_ex(self.plan_local_b, alpha, x, 1.0, y, zadd=self._zbuf, chunk=(c, nc))
@@ -347,7 +347,10 @@ class DistLazySum:
         sh.mul_(y, alpha, beta)              # y_local = alpha * (H x)_local + beta * y_local, collective
     """
 
-    def __init__(self, H: LazySum, rank: int, world: int, group=None, ctx=None):
+    def __init__(self, H: LazySum, rank: int, world: int, group=None, ctx=None, direct=None):
+        """direct: None = use the direct mode when the plan allows it (the result slab `self.y` is library memory mapped by the
+        peers, the exchange adds into it, no contribution slab: 2 slabs per rank); False = contribution slabs (3 per rank,
+        any result buffer)."""
         import torch
         import torch.distributed as dist
 
@@ -363,6 +366,13 @@ class DistLazySum:
         self.nloc, self.n_remote, self.nchunks = nloc.value, nrem.value, nch.value
         self.n = len(H.basis_l.shape)
         self._own, self._peers = [], []
+        self._timing = False
+        self._ex_events = []
+        cap = C.c_int32()
+        _lib.check(lib.qob_dist_direct_capable(d, C.byref(cap)))
+        self.direct = bool(cap.value) and direct is not False and self.n_remote > 0 and world > 1
+        if direct and not self.direct:
+            raise _lib.ArgumentError("direct mode is not available for this plan")
 
         def alloc(nbytes):
             p = C.c_void_p()
@@ -370,15 +380,22 @@ class DistLazySum:
             self._own.append(p)
             return p
 
+        def view(ptr, nbytes):
+            return torch.view_as_complex(torch.as_tensor(_DevBuf(ptr.value, nbytes), device="cuda").view(-1, 2))
+
         px = alloc(slab.value)
-        self.x = torch.view_as_complex(torch.as_tensor(_DevBuf(px.value, slab.value), device="cuda").view(-1, 2))
+        self.x = view(px, slab.value)
+        self.y = None
         tables = [[px.value] * world, None, None]
         if self.n_remote and world > 1:
-            pz, pf = alloc(slab.value), alloc(flagb.value)
+            # second slab: the result (direct mode) or the contribution buffer
+            p2, pf = alloc(slab.value), alloc(flagb.value)
+            if self.direct:
+                self.y = view(p2, slab.value)
             torch.as_tensor(_DevBuf(pf.value, flagb.value), device="cuda").zero_()
             torch.cuda.synchronize()
             mine = torch.empty(3 * 64, dtype=torch.uint8)
-            for k, p in enumerate((px, pz, pf)):
+            for k, p in enumerate((px, p2, pf)):
                 hb = (C.c_uint8 * 64)()
                 _lib.check(lib.qob_ipc_export(p, hb))
                 mine[64 * k:64 * (k + 1)] = torch.frombuffer(bytearray(hb), dtype=torch.uint8)
@@ -387,7 +404,7 @@ class DistLazySum:
             allh = torch.empty(world * 3 * 64, dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(allh, mine.to(dev), group=group)
             allh = allh.cpu().view(world, 3, 64)
-            own = (px.value, pz.value, pf.value)
+            own = (px.value, p2.value, pf.value)
             tables = [[], [], []]
             for q in range(world):
                 for k in range(3):
@@ -401,16 +418,38 @@ class DistLazySum:
                     tables[k].append(pp.value)
             dist.barrier(group=group)   # every pad is zeroed and every mapping exists before the first apply
         arr = [None if t is None else (C.c_void_p * world)(*t) for t in tables]
-        _lib.check(lib.qob_dist_bind(d, arr[0], arr[1], arr[2]))
+        if self.direct:
+            _lib.check(lib.qob_dist_bind(d, arr[0], None, arr[2]))
+            _lib.check(lib.qob_dist_bind_result(d, arr[1]))
+        else:
+            _lib.check(lib.qob_dist_bind(d, arr[0], arr[1], arr[2]))
 
     def describe(self):
         buf = C.create_string_buffer(1 << 15)
         _lib.check(lib.qob_dist_describe(self.d, buf, len(buf)))
         return buf.value.decode()
 
-    def mul_(self, y, alpha=1.0, beta=0.0):
+    @property
+    def time_exchange(self):
+        return self._timing
+
+    @time_exchange.setter
+    def time_exchange(self, on):
+        self._timing = bool(on)
+        _lib.check(lib.qob_dist_exchange_timing(self.d, int(bool(on))))
+
+    def exchange_stats(self):
+        """(mean ms of the exchanges timed since the last call, bytes over NVLink per direction per apply on this GPU)"""
+        ms, cnt, nb = C.c_double(), C.c_int32(), C.c_int64()
+        _lib.check(lib.qob_dist_exchange_ms(self.d, C.byref(ms), C.byref(cnt), C.byref(nb)))
+        return (ms.value if cnt.value else None), float(nb.value)
+
+    def mul_(self, y=None, alpha=1.0, beta=0.0):
+        """y_local = alpha * (H x)_local + beta * y_local, collective.  Direct mode: y is `self.y` (the default)."""
         import torch
 
+        if y is None:
+            y = self.y
         handle(self.H, self.ctx)   # coefficients may have been mutated (TimeDependentSum): re-sent here
         _lib.check(lib.qob_dist_apply(self.d, c64.of(complex(alpha)), c64.of(complex(beta)), C.c_void_p(y.data_ptr()),
                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
@@ -424,6 +463,7 @@ class DistLazySum:
             lib.qob_dist_destroy(self.d)
             self.d = None
             self.x = None
+            self.y = None
             for p in self._peers:
                 lib.qob_ipc_close(self.ctx, p)
             for p in self._own:

@@ -878,8 +878,10 @@ def dot(x, y):
     return complex(out.re, out.im)
 
 
-def launch_count():
-    return int(lib.qob_launch_count())
+def launch_count(family=None):
+    """kernel launches issued by the library in this process; `family`: 1 round-1 tile kernel, 2 round-2 tile kernel,
+    3 round-2 peer-addressed (exchange), 4 round-1 peer-addressed"""
+    return int(lib.qob_launch_count() if family is None else lib.qob_launch_count_of(family))
 
 
 def expect(op, state):

@@ -81,7 +81,9 @@ def test_sharded_apply_all_ranks_on_one_gpu(world, n, beta):
     assert H.rel_err(got, oracle_result(n, spec, alpha, beta, xfull, yfull0)) <= 1e-12
 
 
-@pytest.mark.parametrize("world,n", [(2, 14), (4, 16), (8, 17), (2, 20), (4, 20), (8, 21)])   # the last three run chunked
+# (2, 20) ... (8, 21) run chunked; from 2^20 amplitudes per rank on, the exchange and the budgeted local launches run the round-2
+# kernel (peer-addressed: contiguous pieces by bulk copy; tile ranges by re-numbering the tiles)
+@pytest.mark.parametrize("world,n", [(2, 14), (4, 16), (8, 17), (2, 20), (4, 20), (8, 21), (2, 21), (4, 22), (8, 23)])
 @pytest.mark.parametrize("beta", [0.0, 0.5 + 0.25j])
 def test_fused_peer_exchange_all_ranks_on_one_gpu(world, n, beta):
     """The PEER variant of the tile kernel (loads x tiles from the owners' slabs, stores contributions into the owners'
@@ -105,10 +107,14 @@ def test_fused_peer_exchange_all_ranks_on_one_gpu(world, n, beta):
     ys = [torch.from_numpy(yfull0[r << nloc:(r + 1) << nloc].copy()).cuda() for r in range(world)]
     zs = [torch.full((1 << nloc,), float("nan"), dtype=torch.complex128, device="cuda") for _ in range(world)]
     xptrs, zptrs = [t.data_ptr() for t in xs], [t.data_ptr() for t in zs]
+    l3, l4 = Q.launch_count(3), Q.launch_count(4)
     for r, sh in enumerate(ranks):
         for c in reversed(range(sh.nchunks)):   # chunked launches of the exchange pass, in any order
             sh._apply_ex(sh.plan_swapped, alpha, None, 0.0, None, peers=(xptrs, zptrs), sm_budget=8 + r, chunk=(c, sh.nchunks))
     torch.cuda.synchronize()
+    assert (Q.launch_count(3) - l3) + (Q.launch_count(4) - l4) >= world * ranks[0].nchunks
+    if nloc >= 20:   # the round-2 kernel ran the exchange
+        assert Q.launch_count(3) - l3 == world * ranks[0].nchunks and Q.launch_count(4) == l4
     for r, sh in enumerate(ranks):
         assert torch.isfinite(torch.view_as_real(zs[r])).all()   # every element written exactly once
         if sh.plan_local_b is not None:
@@ -121,15 +127,50 @@ def test_fused_peer_exchange_all_ranks_on_one_gpu(world, n, beta):
     assert H.rel_err(got, oracle_result(n, spec, alpha, beta, xfull, yfull0)) <= 1e-12
 
 
-def test_chunks_cover_the_same_amplitudes_in_both_plans():
+@pytest.mark.parametrize("world,n", [(2, 21), (8, 23)])
+@pytest.mark.parametrize("beta", [0.0, 0.5 + 0.25j])
+def test_peer_exchange_adds_into_the_owners_result(world, n, beta):
+    """The exchange without a contribution buffer: the peer-addressed pass ADDS its results into the owners' y slabs (f64 add
+    performed by the owner's L2: cp.reduce.async.bulk), in any order relative to the local passes, once y holds beta*y."""
+    import torch
+
+    import qob200 as Q
+    from qob200.dist import ShardedLazySum
+
+    p = world.bit_length() - 1
+    nloc = n - p
+    spec = chain_spec(n, 31)
+    xfull = O.fill_state(1 << n, 5, 2.0 ** (-n / 2))
+    yfull0 = O.fill_state(1 << n, 6, 1.0)
+    alpha = 0.8 + 0.1j
+    ranks = [ShardedLazySum(build_q(Q, n, spec), r, world) for r in range(world)]
+    xs = [torch.from_numpy(xfull[r << nloc:(r + 1) << nloc].copy()).cuda() for r in range(world)]
+    ys = [torch.from_numpy(yfull0[r << nloc:(r + 1) << nloc].copy()).cuda() for r in range(world)]
+    xptrs, yptrs = [t.data_ptr() for t in xs], [t.data_ptr() for t in ys]
+    for y in ys:
+        y.mul_(beta)          # y prepared on every rank before any contribution arrives
+    order = list(range(world))
+    for r in order[::2]:      # some ranks exchange before their local passes, some after
+        ranks[r]._apply_ex(ranks[r].plan_swapped, alpha, None, 1.0, None, peers=(xptrs, yptrs), sm_budget=16)
+    for r, sh in enumerate(ranks):
+        sh._apply_ex(sh.plan_local, alpha, xs[r], 1.0, ys[r], sm_budget=-32)
+        if sh.plan_local_b is not None:
+            sh._apply_ex(sh.plan_local_b, alpha, xs[r], 1.0, ys[r], sm_budget=-32)
+    for r in order[1::2]:
+        ranks[r]._apply_ex(ranks[r].plan_swapped, alpha, None, 1.0, None, peers=(xptrs, yptrs), sm_budget=16)
+    got = np.concatenate([y.cpu().numpy() for y in ys])
+    assert H.rel_err(got, oracle_result(n, spec, alpha, beta, xfull, yfull0)) <= 1e-12
+
+
+@pytest.mark.parametrize("world,n", [(4, 20), (4, 22)])
+def test_chunks_cover_the_same_amplitudes_in_both_plans(world, n):
     """chunk c of the exchange pass writes exactly the contribution amplitudes that chunk c of the last local group reads"""
     import torch
 
     import qob200 as Q
     from qob200.dist import ShardedLazySum
 
-    world, n = 4, 20
-    p, nloc = 2, 18
+    p, nloc = 2, n - 2
     spec = chain_spec(n, 29)
     ranks = [ShardedLazySum(build_q(Q, n, spec), r, world) for r in range(world)]
     if ranks[0].nchunks < 2:
@@ -172,33 +213,38 @@ def _nccl_worker(rank, world, port, n, beta, out_dir, fused):
         p = world.bit_length() - 1
         nloc = n - p
         spec = chain_spec(n, 21)
-        if fused == "capi":   # everything behind the C ABI: qob_dist_* (IPC mapping, device barriers, choreography)
+        capi = fused in ("capi", "capi_z")
+        if capi:   # everything behind the C ABI: qob_dist_* (IPC mapping, device barriers, choreography)
             from qob200.dist import DistLazySum
 
-            sh = DistLazySum(build_q(Q, n, spec), rank, world)
+            # "capi": direct mode when the plan allows it (>= 2^20 amplitudes per rank: the exchange adds into the owners'
+            # result slabs); "capi_z": contribution slabs
+            sh = DistLazySum(build_q(Q, n, spec), rank, world, direct=None if fused == "capi" else False)
+            assert sh.direct == (fused == "capi" and nloc >= 20)
             x = sh.x
         else:
             sh = ShardedLazySum(build_q(Q, n, spec), rank, world)
             x = sh.empty_state() if fused else torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
         Q.fill_state(x, 3, 2.0 ** (-n / 2), offset=rank << nloc)
-        y = torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
+        y = sh.y if capi and sh.direct else torch.empty(1 << nloc, dtype=torch.complex128, device="cuda")
         Q.fill_state(y, 4, 1.0, offset=rank << nloc)
         for _ in range(2):   # twice: the second call reuses the contribution buffer
             Q.fill_state(y, 4, 1.0, offset=rank << nloc)
-            if fused == "capi":
+            if capi:
                 sh.mul_(y, 0.7 - 0.2j, beta)
             else:
                 (sh.mul_fused_ if fused else sh.mul_)(y, x, 0.7 - 0.2j, beta)
         torch.cuda.synchronize()
-        if fused == "capi":
+        out = y.cpu().numpy()
+        if capi:
             sh.close()
-        np.save(os.path.join(out_dir, f"y{rank}.npy"), y.cpu().numpy())
+        np.save(os.path.join(out_dir, f"y{rank}.npy"), out)
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("n", [18, 21])   # 21 spins: the fused schedule runs its exchange / fold-in passes in 4 chunks
-@pytest.mark.parametrize("fused", [False, True, "capi"])
+@pytest.mark.parametrize("fused", [False, True, "capi", "capi_z"])
 @pytest.mark.parametrize("beta", [0.0, 0.5 + 0.25j])
 def test_sharded_apply_nccl(tmp_path, beta, fused, n):
     import torch

@@ -1,0 +1,242 @@
+// Microbenchmark: how fast can an SM kernel move 16-byte amplitudes between two B200s over NVLink, by access method?
+//   lsu     : ld.global.v2.f64 from the peer, st to local memory (coalesced, 512 B per warp instruction)
+//   cpasync : cp.async.cg 16 B peer -> shared (what the round-1 exchange kernel does), then st to local memory
+//   bulk    : cp.async.bulk (TMA, non-tensor) peer -> shared in PIECE-byte pieces, 3-stage ring, bulk store to local memory
+//   bulkst  : local -> shared by bulk load, shared -> PEER by cp.async.bulk store
+//   bulkred : same with cp.reduce.async.bulk .add.f64 into the peer's memory (checks the result)
+//   xchg    : bulk load from the peer AND bulk store to the peer (the exchange pattern: x tiles come, contributions go)
+// every test runs on both GPUs at once (both directions loaded), `ctas` persistent CTAs per GPU.  GB/s = bytes that crossed the
+// link in ONE direction / time.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench_peer tools/ubench_peer.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <vector>
+
+#define CK(x)                                                                         \
+  do {                                                                                \
+    cudaError_t e = (x);                                                              \
+    if (e != cudaSuccess) {                                                           \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); \
+      exit(1);                                                                        \
+    }                                                                                 \
+  } while (0)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity), "r"(0x989680u)
+                 : "memory");
+}
+
+__global__ void k_lsu(const double2 *__restrict__ src, double2 *__restrict__ dst, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4 * stride) {
+    double2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < n) v[u] = src[i + u * stride];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * stride < n) dst[i + u * stride] = v[u];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cpasync(const double2 *__restrict__ src, double2 *__restrict__ dst, size_t n) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  // tiles of 4096 amplitudes (64 KiB), one in flight per CTA like the round-1 tile kernel (2 CTAs per SM)
+  const size_t ntiles = n >> 12;
+  for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const double2 *s = src + (t << 12);
+    for (int e = threadIdx.x; e < 4096; e += 256)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(sm + e * 16)), "l"(s + e));
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    double2 *d = dst + (t << 12);
+    for (int e = threadIdx.x; e < 4096; e += 256) d[e] = *reinterpret_cast<double2 *>(sm + e * 16);
+    __syncthreads();
+  }
+}
+
+// mode bit 0: loads come from `src` (may be peer), bit 1 unused; stores go to `dst` (may be peer); red: reduce-add instead of store
+template <bool RED>
+__global__ void __launch_bounds__(64) k_bulk(const unsigned char *__restrict__ src, unsigned char *__restrict__ dst, size_t bytes, unsigned piece) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  constexpr unsigned TILE = 65536, NST = 3;
+  __shared__ __align__(8) unsigned long long bars[2 * NST];   // [s]: landed, [NST+s]: free
+  const unsigned tid = threadIdx.x;
+  if (tid == 0) {
+    for (unsigned s = 0; s < NST; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(bars + s)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(bars + NST + s)));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+  }
+  __syncthreads();
+  const size_t ntiles = bytes / TILE;
+  const unsigned npieces = TILE / piece;
+  if (tid < 32) {   // loader warp: lane j issues pieces j, j+32, ...
+    unsigned stage = 0, ph = 0;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      if (tid == 0) {
+        mbar_wait(smem_u32(bars + NST + stage), ((ph >> stage) & 1u) ^ 1u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bars + stage)), "r"(TILE) : "memory");
+      }
+      ph ^= 1u << stage;
+      __syncwarp();
+      for (unsigned j = tid; j < npieces; j += 32)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                         smem_u32(sm + stage * TILE + j * piece)),
+                     "l"(src + t * TILE + (size_t)j * piece), "r"(piece), "r"(smem_u32(bars + stage))
+                     : "memory");
+      stage = stage + 1 == NST ? 0 : stage + 1;
+    }
+  } else if (tid == 32) {   // storer thread
+    unsigned stage = 0, ph = 0;
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      mbar_wait(smem_u32(bars + stage), (ph >> stage) & 1u);
+      ph ^= 1u << stage;
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      for (unsigned j = 0; j < npieces; ++j) {
+        if (RED)
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;\n" ::"l"(dst + t * TILE + (size_t)j * piece),
+                       "r"(smem_u32(sm + stage * TILE + j * piece)), "r"(piece)
+                       : "memory");
+        else
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst + t * TILE + (size_t)j * piece),
+                       "r"(smem_u32(sm + stage * TILE + j * piece)), "r"(piece)
+                       : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;\ncp.async.bulk.wait_group.read 0;\n" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bars + NST + stage)) : "memory");
+      stage = stage + 1 == NST ? 0 : stage + 1;
+    }
+    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+  }
+}
+
+__global__ void k_fill(double *p, size_t n, double v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_check(const double *p, size_t n, double v, unsigned long long *bad) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    if (p[i] != v) atomicAdd(bad, 1ull);
+}
+
+int main(int argc, char **argv) {
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev < 2) {
+    printf("needs 2 GPUs\n");
+    return 0;
+  }
+  const size_t bytes = (size_t)(argc > 1 ? atoi(argv[1]) : 4) << 30;
+  unsigned char *loc[2], *rem[2];   // loc: private buffer, rem: the buffer the PEER accesses
+  cudaStream_t st[2];
+  cudaEvent_t e0[2], e1[2];
+  for (int d = 0; d < 2; ++d) {
+    CK(cudaSetDevice(d));
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, d, 1 - d));
+    if (!can) {
+      printf("no peer access\n");
+      return 0;
+    }
+    CK(cudaDeviceEnablePeerAccess(1 - d, 0));
+    CK(cudaMalloc(&loc[d], bytes));
+    CK(cudaMalloc(&rem[d], bytes));
+    CK(cudaStreamCreate(&st[d]));
+    CK(cudaEventCreate(&e0[d]));
+    CK(cudaEventCreate(&e1[d]));
+    k_fill<<<1024, 256>>>((double *)loc[d], bytes / 8, 1.0);
+    k_fill<<<1024, 256>>>((double *)rem[d], bytes / 8, 2.0);
+    CK(cudaFuncSetAttribute(k_bulk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 128));
+    CK(cudaFuncSetAttribute(k_bulk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 65536 + 128));
+    CK(cudaFuncSetAttribute(k_cpasync, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    CK(cudaDeviceSynchronize());
+  }
+  auto run = [&](const char *name, int ctas, double link_bytes_per_dir, auto launch, int ndirs = 2) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      for (int d = 0; d < ndirs; ++d) {
+        CK(cudaSetDevice(d));
+        CK(cudaEventRecord(e0[d], st[d]));
+        launch(d);
+        CK(cudaEventRecord(e1[d], st[d]));
+      }
+      float worst = 0;
+      for (int d = 0; d < ndirs; ++d) {
+        CK(cudaSetDevice(d));
+        CK(cudaStreamSynchronize(st[d]));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0[d], e1[d]));
+        worst = ms > worst ? ms : worst;
+      }
+      if (rep > 0 && worst < best) best = worst;
+    }
+    printf("%-44s ctas=%3d %s %8.2f ms  %7.1f GB/s per direction\n", name, ctas, ndirs == 2 ? "both GPUs" : "one GPU  ", best,
+           link_bytes_per_dir / 1e9 / (best * 1e-3));
+    fflush(stdout);
+  };
+  const size_t n16 = bytes / 16;
+  for (int both = 2; both >= 1; --both) {
+    for (int ctas : {148 * 8}) {
+      run("lsu: ld.v2.f64 peer -> st local", ctas, (double)bytes, [&](int d) { k_lsu<<<ctas, 256, 0, st[d]>>>((const double2 *)rem[1 - d], (double2 *)loc[d], n16); }, both);
+      run("lsu: ld local -> st.v2.f64 peer", ctas, (double)bytes, [&](int d) { k_lsu<<<ctas, 256, 0, st[d]>>>((const double2 *)loc[d], (double2 *)rem[1 - d], n16); }, both);
+    }
+    for (int ctas : {64, 296}) run("cp.async 16 B peer -> smem -> st local", ctas, (double)bytes, [&](int d) { k_cpasync<<<ctas, 256, 65536, st[d]>>>((const double2 *)rem[1 - d], (double2 *)loc[d], n16); }, both);
+    for (unsigned piece : {65536u, 4096u, 1024u, 256u})
+      for (int ctas : {16, 32, 64, 148}) {
+        char nm[96];
+        snprintf(nm, sizeof nm, "bulk load peer (%u B pieces) -> bulk st local", piece);
+        run(nm, ctas, (double)bytes, [&](int d) { k_bulk<false><<<ctas, 64, 3 * 65536 + 128, st[d]>>>(rem[1 - d], loc[d], bytes, piece); }, both);
+      }
+    for (unsigned piece : {65536u, 4096u, 256u})
+      for (int ctas : {16, 32, 64, 148}) {
+        char nm[96];
+        snprintf(nm, sizeof nm, "bulk load local -> bulk STORE peer (%u B)", piece);
+        run(nm, ctas, (double)bytes, [&](int d) { k_bulk<false><<<ctas, 64, 3 * 65536 + 128, st[d]>>>(loc[d], rem[1 - d], bytes, piece); }, both);
+      }
+    for (unsigned piece : {4096u})
+      for (int ctas : {16, 32, 64}) {
+        char nm[96];
+        snprintf(nm, sizeof nm, "bulk load local -> bulk REDUCE-ADD f64 peer (%u B)", piece);
+        run(nm, ctas, (double)bytes, [&](int d) { k_bulk<true><<<ctas, 64, 3 * 65536 + 128, st[d]>>>(loc[d], rem[1 - d], bytes, piece); }, both);
+      }
+    // the exchange pattern: half the CTAs' traffic is peer loads, the other half peer stores; per direction: bytes (loads served to
+    // the peer) + bytes (stores received from the peer)... each GPU loads `bytes` from the peer and stores `bytes` to the peer
+    for (unsigned piece : {4096u, 16384u})
+      for (int ctas : {16, 32, 64, 148}) {
+        char nm[96];
+        snprintf(nm, sizeof nm, "xchg: bulk load PEER -> bulk store PEER (%u B)", piece);
+        run(nm, ctas, 2.0 * (double)bytes, [&](int d) { k_bulk<false><<<ctas, 64, 3 * 65536 + 128, st[d]>>>(rem[1 - d], loc[1 - d], bytes, piece); }, both);
+      }
+  }
+  // reduce-add correctness: rem[d] was 2.0 and received loc (1.0) 3 reps x 3 configs -> only check it changed consistently
+  for (int d = 0; d < 2; ++d) {
+    CK(cudaSetDevice(d));
+    k_fill<<<1024, 256>>>((double *)rem[d], bytes / 8, 2.0);
+    CK(cudaDeviceSynchronize());
+  }
+  for (int d = 0; d < 2; ++d) {
+    CK(cudaSetDevice(d));
+    k_bulk<true><<<32, 64, 3 * 65536 + 128, st[d]>>>(loc[d], rem[1 - d], bytes, 4096);
+  }
+  for (int d = 0; d < 2; ++d) {
+    CK(cudaSetDevice(d));
+    CK(cudaDeviceSynchronize());
+  }
+  for (int d = 0; d < 2; ++d) {
+    CK(cudaSetDevice(d));
+    unsigned long long *bad, hb = 0;
+    CK(cudaMalloc(&bad, 8));
+    CK(cudaMemset(bad, 0, 8));
+    k_check<<<1024, 256>>>((const double *)rem[d], bytes / 8, 3.0, bad);
+    CK(cudaMemcpy(&hb, bad, 8, cudaMemcpyDeviceToHost));
+    printf("reduce-add into peer memory: GPU %d buffer has %llu wrong values (expected 2.0 + 1.0 everywhere)\n", d, hb);
+  }
+  return 0;
+}
