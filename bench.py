@@ -314,7 +314,16 @@ def run_product_dist(args, rank, world, local_rank):
     n = args.spins or 33
     mode = os.environ.get("QOB_DIST_EXCHANGE", DEFAULT_EXCHANGE)
     # slabs per rank: x, y (capi in direct mode: the exchange adds into the owners' y); + contributions (fused); + staging (nccl)
-    nbuf = {"capi": 2 if os.environ.get("QOB_DIST_DIRECT", "1") != "0" else 3, "fused": 3}.get(mode, 4)
+    # capi: contribution slabs (3 per rank) when they fit — the fold-in then pipelines behind the exchange and y needs no zero-fill:
+    # 8 GPUs, N=33: 47.8 ms against 49.8 ms — and the direct mode (2 per rank) when they do not: N=33 on 2 GPUs
+    direct = None
+    if mode == "capi":
+        want_direct = os.environ.get("QOB_DIST_DIRECT")
+        if want_direct is not None:
+            direct = want_direct != "0"
+        else:
+            direct = 3 * 16 * (1 << (n - p)) > 0.85 * free
+    nbuf = {"capi": 2 if direct else 3, "fused": 3}.get(mode, 4)
     while nbuf * 16 * (1 << (n - p)) > 0.85 * free and n > 20:
         n -= 1
     nloc = n - p
@@ -326,7 +335,7 @@ def run_product_dist(args, rank, world, local_rank):
         from qob200.dist import DistLazySum
 
         try:
-            sh = DistLazySum(H, rank, world)
+            sh = DistLazySum(H, rank, world, direct=True if direct else False)
             x = sh.x
         except Exception as e:     # CUDA IPC between the ranks' processes unavailable on this box
             if rank == 0:
@@ -633,8 +642,13 @@ def run_common(args, Q, rank, world, step, xs, ys, n, nloc, plan, warmup, steps,
                    "state_bytes": 16 * (1 << n), "l2": "operands (>= 4 GiB per GPU) exceed the 126 MB L2; no flush needed",
                    "plan": plan, "parallelism": "single GPU" if world == 1 else
                    f"state sharded on the top {world.bit_length() - 1} spin axes ({16 * (1 << nloc) / 2**30:.0f} GiB slab per GPU, the largest "
-                   f"chain that fits); remote terms " + ("exchanged by the fused peer-memory tile pass over NVLink"
-                                                         if plan.startswith("exchange=fused") else "through NCCL all-to-all axis swaps")},
+                   f"chain that fits); remote terms " + (
+                       "exchanged by the fused peer-memory tile pass over NVLink, orchestrated behind the C ABI (qob_dist_*); the pass "
+                       "adds into the owners' result slabs (2 slabs per rank)" if plan.startswith("exchange=capi-direct") else
+                       "exchanged by the fused peer-memory tile pass over NVLink, orchestrated behind the C ABI (qob_dist_*)"
+                       if plan.startswith("exchange=capi") else
+                       "exchanged by the fused peer-memory tile pass over NVLink (torch symmetric memory orchestration)"
+                       if plan.startswith("exchange=fused") else "through NCCL all-to-all axis swaps")},
         "term_updates_per_s": value * nterms,
         "hbm_GBps_algorithmic": 32.0 * (1 << nloc) * world / 1e9 / (ms_step * 1e-3),
         "clocks": clocks,

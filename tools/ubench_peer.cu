@@ -219,6 +219,7 @@ int main(int argc, char **argv) {
   for (int d = 0; d < 2; ++d) {
     CK(cudaSetDevice(d));
     k_fill<<<1024, 256>>>((double *)rem[d], bytes / 8, 2.0);
+    k_fill<<<1024, 256>>>((double *)loc[d], bytes / 8, 1.0);   // the timed tests overwrote the source buffers
     CK(cudaDeviceSynchronize());
   }
   for (int d = 0; d < 2; ++d) {
