@@ -82,11 +82,12 @@ struct QRPass {
   // chained launches: compact tile id = deposit(chunk id, cs_*) | deposit(tile within chunk, js_*)
   int ncs, njs;
   unsigned char cs_l[4], cs_n[4], cs_d[4], js_l[4], js_n[4], js_d[4];
+  QRComp comps[QR_MAXC];
   // peer-addressed pass (the exchange of a sharded state): the pass works on the SWAPPED layout of the ranks' slabs.  Index
   // bits [peer_shift, peer_shift + peer_bits) of an element's address name the rank that holds it; there it sits at the same
   // address with those bits replaced by this rank's number.  The tile moves as 2^(T - piece_log2) contiguous pieces.
+  // (kept behind the lookup records: the offsets the single-GPU launches read stay where the constant cache had them)
   int peer_bits, peer_shift, peer_rank, piece_log2;
-  QRComp comps[QR_MAXC];
 };
 
 struct QRLaunch {
@@ -102,11 +103,11 @@ struct QRLaunch {
   double2 *partials;     // mode 3: one partial sum per consumer warp, [blockIdx.x * 8 + warp]
   long long *stats;      // debug (QOB_QREG_STATS=1): per-CTA cycle counts of the pipeline phases, 16 per CTA
   double2 alpha, beta;
+  QRPass pass[2];
   int remap;             // single pass over one tile range: compact tile id = deposit(chunk_fixed, cs_*) | deposit(item, js_*)
   unsigned chunk_fixed;
   const double2 *xpeer[QR_MAXPEER];   // peer-addressed pass: every rank's slab of x and of the buffer that receives the results
   double2 *ypeer[QR_MAXPEER];
-  QRPass pass[2];
 };
 
 // ------------------------------------------------------------------------------------------ device helpers
@@ -406,7 +407,8 @@ __device__ __forceinline__ bool qr_decode(const QRLaunch &L, unsigned item, int 
   return true;
 }
 
-template <bool REALW, int T>
+// PEER: the peer-addressed variant (exchange of a sharded state); the single-GPU instantiations carry none of its code
+template <bool REALW, int T, bool PEER = false>
 __global__ void __launch_bounds__((1 << (T - 4)) + 64, T == 12 ? 1 : 2)
     qreg_kernel(const __grid_constant__ QRLaunch L, const __grid_constant__ CUtensorMap mx0, const __grid_constant__ CUtensorMap my0,
                 const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap my1) {
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__((1 << (T - 4)) + 64, T == 12 ? 1 : 2)
         if (it.pass < 0) break;
         const QRPass &P = L.pass[it.pass];
         if (P.mode != 3) {
-          if (P.peer_bits > 0) {
+          if (PEER) {
             const unsigned pbytes = 16u << P.piece_log2;
             for (unsigned jp = 0; jp < (1u << (T - P.piece_log2)); ++jp) {
               unsigned long long phys;
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__((1 << (T - 4)) + 64, T == 12 ? 1 : 2)
 #pragma unroll
         for (int d = 0; d < 5; ++d) it.co[d] = co[d];
         it.pad2 = 0;
-        it.tbase = P.peer_bits > 0 ? qr_expand(t, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g) : 0ull;
+        it.tbase = PEER ? qr_expand(t, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g) : 0ull;
         slots[stage] = it;
         if (P.wait) {
           const unsigned need = 1u << L.tpc_log2;   // every pass-1 tile of the chunk
@@ -580,11 +582,11 @@ __global__ void __launch_bounds__((1 << (T - 4)) + 64, T == 12 ? 1 : 2)
         }
         const unsigned long long pol = P.stream_out ? pol_stream : pol_keep;
         qr_mbar_expect(qr_smem(bars + stage), QR_TILE_BYTES);
-        if (P.peer_bits == 0) qr_tma_load(qr_smem(xs0 + stage * QR_TILE_BYTES), p ? &mx1 : &mx0, qr_smem(bars + stage), P.rank, co, pol);
+        if (!PEER) qr_tma_load(qr_smem(xs0 + stage * QR_TILE_BYTES), p ? &mx1 : &mx0, qr_smem(bars + stage), P.rank, co, pol);
         item = L.static_queue ? item + gridDim.x : atomicAdd(L.queue, 1u);   // the next item: the atomic's latency overlaps the consumers' work
       }
       __syncwarp();
-      if (P.peer_bits > 0) {
+      if (PEER) {
         // every lane fetches its pieces of the tile from the ranks that hold them (NVLink loads straight into shared memory)
         const unsigned long long tb = qr_expand(t, P.nfixed_seg, P.xs_l, P.xs_n, P.xs_g);
         const unsigned pbytes = 16u << P.piece_log2;
@@ -1748,8 +1750,14 @@ static int qreg_launch_impl(const QRegProgram &prog, cplx alpha, const void *x, 
       if (h.real_tables) QOB_TRY(launch(qreg_kernel<true, 11>));
       else QOB_TRY(launch(qreg_kernel<false, 11>));
     } else {
-      if (h.real_tables) QOB_TRY(launch(qreg_kernel<true, 12>));
-      else QOB_TRY(launch(qreg_kernel<false, 12>));
+      if (peer) {
+        if (h.real_tables) QOB_TRY(launch(qreg_kernel<true, 12, true>));
+        else QOB_TRY(launch(qreg_kernel<false, 12, true>));
+      } else if (h.real_tables) {
+        QOB_TRY(launch(qreg_kernel<true, 12>));
+      } else {
+        QOB_TRY(launch(qreg_kernel<false, 12>));
+      }
     }
     qprof_end(s, prof_token);
     if (want_stats && !expect_out) {
