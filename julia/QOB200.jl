@@ -348,6 +348,7 @@ mutable struct ShardedLazySum
     world::Int
     nbits_local::Int
     x::CuVector{ComplexF64}       # this rank's slab of the state (library memory, visible to the peers)
+    y::Union{Nothing,CuVector{ComplexF64}}   # direct mode: this rank's slab of the result (also visible to the peers)
     own::Vector{Ptr{Cvoid}}
     peers::Vector{Ptr{Cvoid}}
 end
@@ -356,7 +357,9 @@ function _dist_alloc(bytes)
     check(ccall((:qob_dist_alloc, libqob200), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), context(), bytes, p))
     p[]
 end
-function ShardedLazySum(op::LazySum, rank::Integer, world::Integer; allgather, barrier)
+# direct = true (default when the plan allows it): the exchange adds into the owners' result slabs `sh.y`; a rank holds 2 slabs
+# instead of 3 (x, contributions, y) and `apply!(sh)` writes `sh.y`.  direct = false: any CuVector can receive the result.
+function ShardedLazySum(op::LazySum, rank::Integer, world::Integer; allgather, barrier, direct::Bool=true)
     h = handle(op)
     d = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:qob_dist_create, libqob200), Cint, (Ptr{Cvoid}, Int32, Int32, Ref{Ptr{Cvoid}}), h.ptr, rank, world, d))
@@ -367,9 +370,15 @@ function ShardedLazySum(op::LazySum, rank::Integer, world::Integer; allgather, b
     own, peers = Ptr{Cvoid}[], Ptr{Cvoid}[]
     px = _dist_alloc(slab[]); push!(own, px)
     x = unsafe_wrap(CuArray, CuPtr{ComplexF64}(UInt(px)), slab[] >> 4)
+    y = nothing
+    cap = Ref{Int32}(0)
+    check(ccall((:qob_dist_direct_capable, libqob200), Cint, (Ptr{Cvoid}, Ref{Int32}), d[], cap))
+    direct = direct && cap[] != 0 && nrem[] > 0 && world > 1
     tx, tz, tf = fill(px, world), nothing, nothing
     if nrem[] > 0 && world > 1
+        # second slab: the result (direct mode) or the contribution buffer
         pz, pf = _dist_alloc(slab[]), _dist_alloc(flagb[]); push!(own, pz, pf)
+        direct && (y = unsafe_wrap(CuArray, CuPtr{ComplexF64}(UInt(pz)), slab[] >> 4))
         fill!(unsafe_wrap(CuArray, CuPtr{UInt8}(UInt(pf)), flagb[]), 0x00); CUDA.synchronize()
         mine = Vector{UInt8}(undef, 192)
         for (k, p) in enumerate((px, pz, pf))
@@ -391,11 +400,13 @@ function ShardedLazySum(op::LazySum, rank::Integer, world::Integer; allgather, b
         barrier()   # every pad is zeroed and every mapping exists before the first apply
     end
     check(ccall((:qob_dist_bind, libqob200), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
-                d[], tx, tz === nothing ? C_NULL : tz, tf === nothing ? C_NULL : tf))
-    sh = ShardedLazySum(d[], op, rank, world, nloc[], x, own, peers)
+                d[], tx, (direct || tz === nothing) ? C_NULL : tz, tf === nothing ? C_NULL : tf))
+    direct && check(ccall((:qob_dist_bind_result, libqob200), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), d[], tz))
+    sh = ShardedLazySum(d[], op, rank, world, nloc[], x, y, own, peers)
     finalizer(close!, sh)
 end
 "y_local = alpha * (op * x)_local + beta * y_local with x = `sh.x` on every rank; collective over the ranks"
+apply!(sh::ShardedLazySum, alpha=true, beta=false) = apply!(sh.y, sh, alpha, beta)   # direct mode: the result slab `sh.y`
 function apply!(y::DevVec, sh::ShardedLazySum, alpha=true, beta=false)
     handle(sh.op)   # re-sends mutated coefficients (time-dependent sums)
     GC.@preserve sh check(ccall((:qob_dist_apply, libqob200), Cint, (Ptr{Cvoid}, C64, C64, CuPtr{Cvoid}, Ptr{Cvoid}),
