@@ -433,4 +433,22 @@ def test_dist_planning_behind_the_abi(Q):
     # apply without bound buffers / on a planning-only context fails loudly
     assert _lib.lib.qob_dist_apply(d, _lib.c64.of(1.0), _lib.c64.of(0.0), C.c_void_p(16), None) == 3
     assert _lib.lib.qob_dist_create(h, 3, 6, C.byref(C.c_void_p())) == 3      # world must be a power of two
+    # direct mode: the exchange pass of this plan can add into the owners' result slabs (round-2 kernel, 4 KiB pieces)
+    cap = C.c_int32(-1)
+    _lib.check(_lib.lib.qob_dist_direct_capable(d, C.byref(cap)))
+    assert cap.value == 1 and "direct mode available" in text
+    assert "exchanged (window bit 26)" in text and "free:0-7,26-29" in text
+    assert _lib.lib.qob_dist_bind_result(d, None) == 3
+    ms, cnt, nb = C.c_double(-1), C.c_int32(-1), C.c_int64()
+    _lib.check(_lib.lib.qob_dist_exchange_timing(d, 1))
+    _lib.check(_lib.lib.qob_dist_exchange_ms(d, C.byref(ms), C.byref(cnt), C.byref(nb)))
+    assert (ms.value, cnt.value) == (0.0, 0) and nb.value == int(2 * (7 / 8) * 16 * 2 ** 30)
     _lib.check(_lib.lib.qob_dist_destroy(d))
+    # small slabs: the round-2 kernel is not planned below 2^20 amplitudes per rank, so no direct mode
+    _, Hs = chain(Q, 18)
+    d2 = C.c_void_p()
+    _lib.check(_lib.lib.qob_dist_create(handle(Hs, ctx), 1, 2, C.byref(d2)))
+    _lib.check(_lib.lib.qob_dist_direct_capable(d2, C.byref(cap)))
+    assert cap.value == 0
+    assert _lib.lib.qob_dist_bind_result(d2, (C.c_void_p * 2)(16, 32)) == 4   # QOB_STATUS_UNSUPPORTED
+    _lib.check(_lib.lib.qob_dist_destroy(d2))
