@@ -212,9 +212,14 @@ int qob_layout_plan_describe(qob_op *sum, int32_t plan_id, char *buf, int64_t bu
  *            of an address select the owning rank; the tile kernel loads x straight from x_peers[owner] and stores its
  *            result straight into y_peers[owner] (device pointers into every rank's symmetric / IPC-mapped memory).
  *            x and y are ignored in that case.
- *   sm_budget>0 limits the persistent tile kernel to that many SMs so that another kernel (the local passes) runs beside it;
- *   sm_budget<0 says that this launch itself runs beside another kernel: the library then uses the tile kernel whose small CTAs
- *            share SMs with it (the one-CTA-per-SM kernel used for plain launches would serialise with the other kernel).
+ *            beta = 0: the results are stored (every element of the owners' buffers is written exactly once);
+ *            beta = 1: the results are ADDED into the owners' buffers (f64 add performed by the owner's L2; needs the
+ *            round-2 tile kernel: slabs of >= 2^20 amplitudes, contiguous pieces of >= 1 KiB); other values: INVALID_ARG.
+ *   sm_budget>0 limits the launch to that many SMs so that another kernel runs beside it (the exchange pass);
+ *   sm_budget<-1 leaves |sm_budget| SMs free: the launch runs on all the others (the local passes beside the exchange).  One
+ *            persistent CTA of the round-2 tile kernel fills an SM, so two launches split this way never share an SM;
+ *   sm_budget=-1 says that this launch runs beside another kernel and should SHARE SMs with it: the round-1 tile kernel,
+ *            whose small CTAs fit next to another kernel's (the pre-round-2 schedule);
  *   chunk_index/nchunks: run one of nchunks equal tile ranges (nchunks <= 1: the whole pass). */
 int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const void *x, qob_c64 beta, void *y,
                              const void *zadd, int32_t npeers, const void *const *x_peers, void *const *y_peers,

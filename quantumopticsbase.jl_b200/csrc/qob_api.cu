@@ -1667,6 +1667,9 @@ int qob_layout_plan_apply_ex(qob_op *sum, int32_t plan_id, qob_c64 alpha, const 
       return qreg_launch_ex(lp.qreg, C(alpha), x, C(beta), y, s, ro);
     }
   }
+  if (npeers > 0 && C(beta) != ZERO)
+    QOB_FAIL(QOB_STATUS_UNSUPPORTED, "peer-addressed launch with beta != 0 needs the round-2 tile kernel (adds performed by the owner's L2); "
+                                     "this plan runs the round-1 kernel, which can only store");
   if (o.sm_budget < 0) o.sm_budget = 0;
   QOB_TRY(qtile_set_coefs(lp.prog, cf, s));
   return qtile_launch(lp.prog, C(alpha), x, C(beta), y, s, &o);
