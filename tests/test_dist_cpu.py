@@ -152,3 +152,41 @@ def test_chunk_bits_are_fixed_in_both_single_pass_plans(world, n):
         assert m & (((1 << sh.p) - 1) << sh.swap_lo) == 0 and m < (1 << sh.nloc)
         chosen.add(m)
     assert len(chosen) == 1
+
+
+@pytest.mark.parametrize("world,n", [(2, 20), (4, 22), (8, 23), (8, 33), (2, 33), (4, 33), (2, 14)])
+def test_c_abi_planner_agrees_with_the_python_orchestration(world, n):
+    """Planning only (no GPU): qob_dist_create (csrc/qob_dist.cu) restates the planning of ShardedLazySum (dist.py) — term
+    classes, swap window, tile ranges — and must arrive at the same schedule on every rank; the direct mode (the exchange adds
+    into the owners' result slabs) is offered exactly when the slab has >= 2^20 amplitudes."""
+    import ctypes as C
+
+    import qob200 as Q
+    from qob200 import _lib
+    from qob200.dist import ShardedLazySum
+    from qob200.operators import handle
+
+    spec = chain_spec(n, 11)
+    b = Q.SpinBasis(0.5)
+    B = Q.tensor(*[b] * n)
+    sig = (Q.sigmax(b), Q.sigmay(b), Q.sigmaz(b))
+    Hq = Q.LazySum([c for c, _, _ in spec], [Q.LazyTensor(B, idx, (sig[a], sig[a])) for _, idx, a in spec])
+    ctx = Q.context(-1)
+    for rank in (0, world - 1):
+        sh = ShardedLazySum(Hq, rank, world, ctx=ctx)
+        d = C.c_void_p()
+        _lib.check(_lib.lib.qob_dist_create(handle(Hq, ctx), rank, world, C.byref(d)))
+        nloc, nrem, nch = C.c_int32(), C.c_int32(), C.c_int32()
+        slab, flagb = C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib.qob_dist_info(d, C.byref(nloc), C.byref(nrem), C.byref(nch), C.byref(slab), C.byref(flagb)))
+        assert (nloc.value, nrem.value, nch.value) == (sh.nloc, sh.n_remote, sh.nchunks)
+        assert slab.value == 16 << sh.nloc
+        buf = C.create_string_buffer(1 << 15)
+        _lib.check(_lib.lib.qob_dist_describe(d, buf, len(buf)))
+        text = buf.value.decode()
+        assert f"{sh.n_local} local + {sh.n_remote} exchanged terms" in text
+        assert f"exchanged (window bit {sh.swap_lo})" in text
+        cap = C.c_int32()
+        _lib.check(_lib.lib.qob_dist_direct_capable(d, C.byref(cap)))
+        assert bool(cap.value) == (sh.nloc >= 20), text
+        _lib.check(_lib.lib.qob_dist_destroy(d))
